@@ -1,0 +1,267 @@
+"""Pins oracle/bcp_oracle.py against golden vectors minted from the UNMODIFIED reference
+(tests/golden/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import bcp_oracle as O
+from tests.golden.golden_common import inject_dropout, digest_named, tensor_digest
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(G, name + ".npz"))
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def close(a, b, rtol=1e-5, atol=1e-6):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert np.allclose(a, b, rtol=rtol, atol=atol), float(np.abs(a - b).max())
+
+
+def digests_close(a, b, rtol=2e-4):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape
+    scale = np.abs(b[:, 1:2]) + 1e-12           # abs-sum of each tensor
+    err = np.abs(a - b)
+    assert (err[:, :2] <= rtol * scale + 1e-7).all(), float((err[:, :2] / scale).max())
+
+
+def test_function_vectors():
+    g = load("functions")
+    lg, la, lb, m = T(g["la_logits"]), T(g["la_lab_a"]), T(g["la_lab_b"]), T(g["la_mask"])
+    close(O.mask_dice_loss(lg, la, m), g["la_dice_masked"])
+    close(O.mask_dice_loss(lg, la), g["la_dice_unmasked"])
+    x = lg.clone().requires_grad_(True)
+    l = O.mix_loss_la(x, la, lb, m, u_weight=0.5)
+    l.backward()
+    close(l.detach(), g["la_mix_loss"])
+    close(x.grad, g["la_mix_grad"], atol=1e-8)
+    x = lg.clone().requires_grad_(True)
+    l = O.mix_loss_la(x, lb, la, m, u_weight=0.5, unlab=True)
+    l.backward()
+    close(l.detach(), g["la_mix_loss_unlab"])
+    close(x.grad, g["la_mix_grad_unlab"], atol=1e-8)
+    close(O.mix_loss_la(lg, la, lb.long(), m).detach(), g["pan_mix_loss"])
+    x = lg.clone().requires_grad_(True)
+    lp = (F.cross_entropy(x, la) + O.mask_dice_loss(x, la)) / 2
+    lp.backward()
+    close(lp.detach(), g["la_pre_loss"])
+    close(x.grad, g["la_pre_grad"], atol=1e-8)
+
+    lg4, ta, tb, m2 = T(g["acdc_logits"]), T(g["acdc_lab_a"]), T(g["acdc_lab_b"]), T(g["acdc_mask"])
+    x = lg4.clone().requires_grad_(True)
+    d, c = O.mix_loss_acdc(x, ta, tb, m2, u_weight=0.5)
+    ((d + c) / 2).backward()
+    close(d.detach(), g["acdc_mix_dice"])
+    close(c.detach(), g["acdc_mix_ce"])
+    close(x.grad, g["acdc_mix_grad"], atol=1e-8)
+    d, c = O.mix_loss_acdc(lg4, tb, ta, m2, u_weight=0.5, unlab=True)
+    close(d, g["acdc_mix_dice_unlab"])
+    close(c, g["acdc_mix_ce_unlab"])
+
+
+def _bbox(mask):
+    return np.array([[int(i.min()), int(i.max()) + 1] for i in torch.nonzero(mask == 0, as_tuple=True)])
+
+
+def test_mask_vectors():
+    g = load("functions")
+    rs = np.random.RandomState(1337)
+    mk, lm, box = O.context_mask_la(torch.zeros(2, 1, 112, 112, 80), 2 / 3, rs)
+    assert (_bbox(mk) == g["la_ctx_mask_zero_bbox"]).all()
+    assert int(mk.sum()) == int(g["la_ctx_mask_sum"]) and int(lm.sum()) == int(g["la_ctx_lmask_sum"])
+    assert box[3:] == (74, 74, 53)
+    rs = np.random.RandomState(1337)
+    mk, lm, box = O.generate_mask_acdc(torch.zeros(6, 1, 256, 256), rs)
+    assert (_bbox(mk) == g["acdc_mask_zero_bbox"]).all() and int(mk.sum()) == int(g["acdc_mask_sum"])
+    rs = np.random.RandomState(2020)
+    mk, lm, box = O.generate_mask_pan(torch.zeros(2, 1, 96, 96, 96), 64, rs)
+    assert (_bbox(mk) == g["pan_mask_zero_bbox"]).all()
+    out = O.mask_mix(T(g["mix_a"]), T(g["mix_b"]), T(g["mix_mask"]))
+    assert out.numpy().tobytes() == g["mix_out"].tobytes()          # bit-exact incl. NaN payload / -0.0
+
+
+def test_pseudo_label_vectors():
+    g = load("functions")
+    assert (O.get_cut_mask(T(g["pl_logits"]), nms=0).numpy() == g["pl_cut"]).all()
+    assert (O.get_cut_mask(T(g["pl_logits2"]), nms=0).numpy() == g["pl_cut2"]).all()
+    assert (O.get_cut_mask(T(g["pl_logits2"]), nms=1).numpy() == g["pl_cc2"]).all()
+    assert (O.get_cut_mask(T(g["pl_logits2"]), nms=1, connectivity=2).numpy() == g["pl_cc2_conn2"]).all()
+    assert (O.get_cut_mask(T(g["pl_logits2"]), nms=1, connectivity=1).numpy() == g["pl_cc2_conn1"]).all()
+    e = torch.zeros(1, 2, 8, 8, 8)
+    e[:, 0] = 5
+    assert (O.get_cut_mask(e, nms=1).numpy() == g["pl_cc_empty"]).all()
+    assert (O.get_acdc_masks(T(g["acdc_pl_logits"]), nms=0).numpy() == g["acdc_pl_argmax"]).all()
+    assert (O.get_acdc_masks(T(g["acdc_pl_logits"]), nms=1).numpy() == g["acdc_pl_cc"]).all()
+
+
+def test_ema_vectors():
+    g = load("functions")
+    m1, m2 = O.OracleVNet(1, 2, 4, "batchnorm", True), O.OracleVNet(1, 2, 4, "batchnorm", True)
+    O.fill_state_dict_(m1, 3)
+    O.fill_state_dict_(m2, 4)
+    O.update_ema_variables(m1, m2, 0.99)
+    close(digest_named(m2.state_dict()), g["ema_la_digest"], rtol=1e-7, atol=0)
+    u1, u2 = O.OracleUNet2d(1, 4), O.OracleUNet2d(1, 4)
+    O.fill_state_dict_(u1, 5)
+    O.fill_state_dict_(u2, 6)
+    for k, v in u1.state_dict().items():
+        if k.endswith("num_batches_tracked"):
+            v.fill_(7)
+    for k, v in u2.state_dict().items():
+        if k.endswith("num_batches_tracked"):
+            v.fill_(3)
+    O.update_model_ema(u1, u2, 0.99)
+    close(digest_named(u2.state_dict()), g["ema_acdc_digest"], rtol=1e-7, atol=0)
+    assert int(u2.state_dict()["encoder.in_conv.conv_conv.1.num_batches_tracked"]) == int(g["ema_acdc_nbt"])
+
+
+def test_network_vectors():
+    g = load("networks")
+    net = O.OracleVNet(1, 2, 16, "batchnorm", False)
+    O.fill_state_dict_(net, 21)
+    net.eval()
+    with torch.no_grad():
+        lo, feat = net(O.synthetic_volume((1, 1, 48, 48, 48), 22))
+    close(lo, g["vnet_eval_logits"], rtol=1e-4, atol=1e-4)
+    close(feat, g["vnet_eval_feat"], rtol=1e-4, atol=1e-4)
+
+    net = O.net_factory("VNet", 1, 2, "train")
+    O.fill_state_dict_(net, 23)
+    net.train()
+    inject_dropout(net, seed=24)
+    lo, _ = net(O.synthetic_volume((2, 1, 48, 48, 48), 25))
+    close(lo.detach(), g["vnet_train_logits"], rtol=1e-4, atol=1e-4)
+    (lo * O.synthetic_volume(tuple(lo.shape), 26)).sum().backward()
+    digests_close(digest_named({n: p.grad for n, p in net.named_parameters() if p.grad is not None}), g["vnet_train_grad_digest"], rtol=1e-3)
+    close(net.encoder.block_one.conv[0].weight.grad, g["vnet_train_grad_first"], rtol=1e-3, atol=1e-3)
+
+    un = O.OracleUNet2d(1, 4)
+    O.fill_state_dict_(un, 31)
+    un.eval()
+    x = O.synthetic_volume((2, 1, 64, 48), 32, "rand")
+    with torch.no_grad():
+        close(un(x), g["unet_eval_logits"], rtol=1e-4, atol=1e-4)
+    un.train()
+    inject_dropout(un, seed=33)
+    lo = un(x)
+    close(lo.detach(), g["unet_train_logits"], rtol=1e-4, atol=1e-4)
+
+    pn = O.OraclePanVNet()
+    O.fill_state_dict_(pn, 41)
+    pn.train()
+    lo = pn(O.synthetic_volume((2, 1, 32, 16, 32), 42))[0]
+    close(lo.detach(), g["pan_train_logits"], rtol=1e-4, atol=1e-4)
+
+
+def _la_models(seed_w, seed_d1, seed_d2):
+    model, ema = O.net_factory("VNet", 1, 2, "train"), O.net_factory("VNet", 1, 2, "train")
+    for p in ema.parameters():
+        p.detach_()
+    O.fill_state_dict_(model, seed_w)
+    ema.load_state_dict(model.state_dict())
+    model.train()
+    ema.train()
+    inject_dropout(model, seed=seed_d1)
+    inject_dropout(ema, seed=seed_d2)
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=0.0001)
+    return model, ema, opt
+
+
+def _check_la_step(g, nsteps, shape, sub):
+    model, ema, opt = _la_models(51, 52, 53)
+    rs = np.random.RandomState(int(g["box_seed"]))
+    for it in range(nsteps):
+        vol = O.synthetic_volume((8, 1) + shape, 60 + it)
+        lab = O.synthetic_labels((8,) + shape, 70 + it)
+        r = O.la_self_train_step(model, ema, opt, vol, lab, rng=rs)
+        for k in ("loss", "loss_l", "loss_u"):
+            close(r[k], g[f"s{it}_{k}"], rtol=2e-5)
+        assert float(r["plab_a"].sum()) == float(g[f"s{it}_plab_a_sum"])
+        close(r["out_l"][..., ::sub, ::sub, ::sub], g[f"s{it}_out_l"], rtol=1e-3, atol=1e-3)
+        close(tensor_digest(r["mixl"]), g[f"s{it}_mixl_digest"], rtol=1e-9, atol=0)
+        digests_close(digest_named(model.state_dict()), g[f"s{it}_model_digest"])
+        digests_close(digest_named(ema.state_dict()), g[f"s{it}_ema_digest"])
+
+
+def test_la_step_small():
+    _check_la_step(load("la_step_small"), 2, (48, 48, 48), 2)
+
+
+def test_la_pre_step():
+    g = load("la_pre_step")
+    model = O.net_factory("VNet", 1, 2, "train")
+    O.fill_state_dict_(model, 81)
+    model.train()
+    inject_dropout(model, seed=82)
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=0.0001)
+    shape = (48, 48, 48)
+    r = O.la_pre_train_step(model, opt, O.synthetic_volume((4, 1) + shape, 83), O.synthetic_labels((4,) + shape, 84),
+                            rng=np.random.RandomState(int(g["box_seed"])))
+    close(r["loss"], g["loss"], rtol=2e-5)
+    close(r["out"], g["out"], rtol=1e-3, atol=1e-3)
+    digests_close(digest_named(model.state_dict()), g["model_digest"])
+
+
+def test_acdc_step():
+    g = load("acdc_step")
+    model, ema = O.BCP_net(1, 4), O.BCP_net(1, 4, ema=True)
+    O.fill_state_dict_(model, 91)
+    ema.load_state_dict(model.state_dict())
+    model.train()
+    ema.train()
+    inject_dropout(model, seed=92)
+    inject_dropout(ema, seed=93)
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=0.0001)
+    rs = np.random.RandomState(1337)
+    for it in range(2):
+        vol = O.synthetic_volume((8, 1, 64, 64), 100 + it, "rand")
+        lab = O.synthetic_labels((8, 64, 64), 110 + it, n_classes=4).to(torch.uint8)
+        r = O.acdc_self_train_step(model, ema, opt, vol, lab, labeled_bs=4, rng=rs)
+        close(r["loss"], g[f"s{it}_loss"], rtol=2e-5)
+        close(r["loss_dice"], g[f"s{it}_loss_dice"], rtol=2e-5)
+        assert (r["plab_a"].numpy() == g[f"s{it}_plab_a"]).all()
+        close(r["out_l"], g[f"s{it}_out_l"], rtol=1e-3, atol=1e-3)
+        digests_close(digest_named(model.state_dict()), g[f"s{it}_model_digest"])
+        digests_close(digest_named(ema.state_dict()), g[f"s{it}_ema_digest"])
+
+
+@pytest.mark.slow
+def test_la_step_full():
+    if not os.path.exists(os.path.join(G, "la_step_full.npz")):
+        pytest.skip("full-size fixture not generated")
+    _check_la_step(load("la_step_full"), 1, (112, 112, 80), 4)
+
+
+@pytest.mark.slow
+def test_pan_step():
+    if not os.path.exists(os.path.join(G, "pan_step.npz")):
+        pytest.skip("fixture not generated")
+    g = load("pan_step")
+    net, ema = O.OraclePanVNet(), O.OraclePanVNet()
+    for p in ema.parameters():
+        p.detach_()
+    O.fill_state_dict_(net, 121)
+    ema.load_state_dict(net.state_dict())
+    net.train()
+    ema.train()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    rs = np.random.RandomState(2020)
+    S = (96, 96, 96)
+    v = O.synthetic_volume((8, 1) + S, 130)
+    l = O.synthetic_labels((8,) + S, 140)
+    r = O.pan_self_train_step(net, ema, opt, v[0:2], l[0:2], v[2:4], l[2:4], v[4:6], v[6:8], rng=rs)
+    close(r["loss"], g["s0_loss"], rtol=2e-5)
+    assert float(r["plab_a"].sum()) == float(g["s0_plab_a_sum"])
+    close(r["out_1"][..., ::4, ::4, ::4], g["s0_out_1"], rtol=1e-3, atol=1e-3)
+    digests_close(digest_named(net.state_dict()), g["s0_model_digest"])
+    digests_close(digest_named(ema.state_dict()), g["s0_ema_digest"])
