@@ -1,0 +1,59 @@
+"""Builds bcp_b200/libbcp_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libbcp_b200.so")
+SOURCES = ["api.cu", "elementwise.cu", "norm.cu", "loss.cu", "conv_direct.cu", "conv_tc.cu", "pool.cu", "cc.cu"]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+
+
+def _stamp():
+    h = hashlib.sha256()
+    for root in (CSRC, os.path.join(HERE, "..", "include")):
+        for f in sorted(os.listdir(root)):
+            if f.endswith((".cu", ".cuh", ".h")):
+                h.update(open(os.path.join(root, f), "rb").read())
+    h.update(" ".join(FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force=False, verbose=False):
+    stamp_file = os.path.join(HERE, "build", "stamp")
+    stamp = _stamp()
+    if not force and os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
+        return LIB
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    objs = []
+    procs = []
+    for s in SOURCES:
+        obj = os.path.join(HERE, "build", s.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, s), "-o", obj]
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = []
+    failed = False
+    for s, p in procs:
+        out, _ = p.communicate()
+        log.append("== %s\n%s" % (s, out))
+        if p.returncode != 0:
+            failed = True
+            sys.stderr.write("nvcc failed for %s:\n%s\n" % (s, out))
+    open(os.path.join(HERE, "build", "nvcc.log"), "w").write("\n".join(log))
+    if failed:
+        raise RuntimeError("nvcc compilation failed (see bcp_b200/build/nvcc.log)")
+    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-lcudart"]
+    subprocess.check_call(cmd)
+    open(stamp_file, "w").write(stamp)
+    if verbose:
+        print("\n".join(log))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,159 @@
+// Largest-connected-component filter on the GPU (replaces the reference's per-sample
+// GPU->CPU->GPU round trip through skimage.measure.label: LA_BCP_train.py:65-77,
+// pancreas/pancreas_utils.py:284-296, ACDC_BCP_train.py:89-109).
+//   * label-equivalence union-find (atomicMin hooks, roots = smallest raster index of a component)
+//   * integer histogram of component sizes (atomicAdd on ints: order-independent result)
+//   * per (sample, class) arg-max with ties -> smallest root == first component in raster order,
+//     which is what np.argmax(np.bincount(labels.flat)[1:]) + 1 picks from skimage's raster labelling
+//   * classes 1..3 are handled in one pass (unions only between equal non-zero labels)
+// connectivity = max number of axes along which neighbours may differ (skimage semantics):
+// 3-D: 1 -> 6, 2 -> 18, 3 -> 26 neighbours; 2-D (X == 1): 1 -> 4, 2 -> 8.
+#include "common.cuh"
+#include "../../include/bcp_b200.h"
+
+namespace bcp {
+
+__device__ __forceinline__ int uf_find(int* L, int i) {
+  int r = i;
+  while (true) {
+    const int p = L[r];
+    if (p == r) break;
+    r = p;
+  }
+  // path compression (benign race: labels only decrease towards the root)
+  while (true) {
+    const int p = L[i];
+    if (p == r || p == i) break;
+    L[i] = r;
+    i = p;
+  }
+  return r;
+}
+
+__device__ __forceinline__ void uf_union(int* L, int a, int b) {
+  while (true) {
+    a = uf_find(L, a);
+    b = uf_find(L, b);
+    if (a == b) return;
+    if (a < b) { const int t = a; a = b; b = t; }   // a > b: hook the larger root under the smaller
+    const int old = atomicMin(&L[a], b);
+    if (old == a) return;
+    a = old;
+  }
+}
+
+__global__ void cc_init_kernel(const unsigned char* __restrict__ seg, int* __restrict__ L, int* __restrict__ cnt,
+                               unsigned long long* __restrict__ best, long long total, int V, int nbest) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    L[i] = seg[i] ? (int)(i % V) : -1;
+    cnt[i] = 0;
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nbest; i += stride) best[i] = 0ull;
+}
+
+__global__ void cc_merge_kernel(const unsigned char* __restrict__ seg, int* __restrict__ L, int N, int X, int Y, int Z, int conn) {
+  const int V = X * Y * Z;
+  const long long total = (long long)N * V;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < total; gi += stride) {
+    const unsigned char c = seg[gi];
+    if (!c) continue;
+    const int n = (int)(gi / V), i = (int)(gi - (long long)n * V);
+    const int z = i % Z, y = (i / Z) % Y, x = i / (Z * Y);
+    int* Ls = L + (long long)n * V;
+    const unsigned char* ss = seg + (long long)n * V;
+    for (int dx = -1; dx <= 0; ++dx) {
+      for (int dy = -1; dy <= 1; ++dy) {
+        for (int dz = -1; dz <= 1; ++dz) {
+          const int off = (dx * Y + dy) * Z + dz;
+          if (off >= 0) continue;                                   // visit each undirected pair once
+          if (abs(dx) + abs(dy) + abs(dz) > conn) continue;
+          const int xx = x + dx, yy = y + dy, zz = z + dz;
+          if (xx < 0 || yy < 0 || yy >= Y || zz < 0 || zz >= Z) continue;
+          const int j = i + off;
+          if (ss[j] == c) uf_union(Ls, i, j);
+        }
+      }
+    }
+  }
+}
+
+__global__ void cc_count_kernel(const unsigned char* __restrict__ seg, int* __restrict__ L, int* __restrict__ cnt, int N, int V) {
+  const long long total = (long long)N * V;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < total; gi += stride) {
+    if (!seg[gi]) continue;
+    const int n = (int)(gi / V), i = (int)(gi - (long long)n * V);
+    int* Ls = L + (long long)n * V;
+    const int r = uf_find(Ls, i);
+    Ls[i] = r;
+    atomicAdd(&cnt[(long long)n * V + r], 1);
+  }
+}
+
+__global__ void cc_best_kernel(const unsigned char* __restrict__ seg, const int* __restrict__ L, const int* __restrict__ cnt,
+                               unsigned long long* __restrict__ best, int N, int V) {
+  const long long total = (long long)N * V;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < total; gi += stride) {
+    const unsigned char c = seg[gi];
+    if (!c) continue;
+    const int n = (int)(gi / V), i = (int)(gi - (long long)n * V);
+    if (L[gi] != i) continue;   // roots only
+    const unsigned long long key = ((unsigned long long)(unsigned)cnt[gi] << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+    atomicMax(&best[n * 4 + (c & 3)], key);
+  }
+}
+
+__global__ void cc_select_kernel(const unsigned char* __restrict__ seg, const int* __restrict__ L,
+                                 const unsigned long long* __restrict__ best, unsigned char* __restrict__ out_u8,
+                                 float* __restrict__ out_f32, int N, int V) {
+  const long long total = (long long)N * V;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < total; gi += stride) {
+    const unsigned char c = seg[gi];
+    unsigned char o = 0;
+    if (c) {
+      const int n = (int)(gi / V);
+      const unsigned long long key = best[n * 4 + (c & 3)];
+      const int root = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+      o = (L[gi] == root) ? c : 0;
+    }
+    if (out_u8) out_u8[gi] = o;
+    if (out_f32) out_f32[gi] = (float)o;
+  }
+}
+
+}  // namespace bcp
+
+using namespace bcp;
+
+extern "C" {
+
+long long bcp_largest_cc_workspace_bytes(int n, long long v) { return (long long)n * v * 8 + (long long)n * 4 * 8 + 64; }
+
+int bcp_largest_cc(const unsigned char* seg, unsigned char* out_u8, float* out_f32, void* workspace, int n, int X, int Y, int Z,
+                   int connectivity, cudaStream_t stream) {
+  BCP_REQUIRE(seg && workspace && (out_u8 || out_f32), "largest_cc: null pointer");
+  BCP_REQUIRE(n > 0 && X > 0 && Y > 0 && Z > 0, "largest_cc: bad shape");
+  BCP_REQUIRE((long long)X * Y * Z < (1ll << 31), "largest_cc: volume too large");
+  BCP_REQUIRE(connectivity >= 1 && connectivity <= 3, "largest_cc: connectivity %d", connectivity);
+  const int V = X * Y * Z;
+  const long long total = (long long)n * V;
+  unsigned long long* best = (unsigned long long*)workspace;          // [n][4], 8-byte aligned at the front
+  int* L = (int*)((char*)workspace + (((long long)n * 4 * 8 + 63) / 64) * 64);
+  int* cnt = L + total;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  const int g = (int)blocks;
+  cc_init_kernel<<<g, 256, 0, stream>>>(seg, L, cnt, best, total, V, n * 4);
+  cc_merge_kernel<<<g, 256, 0, stream>>>(seg, L, n, X, Y, Z, connectivity);
+  cc_count_kernel<<<g, 256, 0, stream>>>(seg, L, cnt, n, V);
+  cc_best_kernel<<<g, 256, 0, stream>>>(seg, L, cnt, best, n, V);
+  cc_select_kernel<<<g, 256, 0, stream>>>(seg, L, best, out_u8, out_f32, n, V);
+  return check_launch("largest_cc");
+}
+
+}  // extern "C"

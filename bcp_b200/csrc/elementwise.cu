@@ -1,0 +1,325 @@
+// Bandwidth-bound step primitives: box mask-mix, pseudo-labels, fused SGD/Adam+EMA, weight repack,
+// layout converts.  All kernels: 128-bit vectorised where alignment allows, grid-stride, no atomics.
+#include "common.cuh"
+#include "../../include/bcp_b200.h"
+#include <math.h>
+
+namespace bcp {
+
+// ------------------------------------------------------------------------------------------
+// mask-mix:  out = a*M + b*(1-M), M = 0 inside the box, 1 outside (reference: LA_BCP_train.py:248-249,
+// ACDC_BCP_train.py:372-373, train_pancreas.py:155-156).  Computed literally with two multiplies and
+// one add (no select, no FMA) so -0.0 / inf / NaN behave like the reference's tensor expression.
+// ------------------------------------------------------------------------------------------
+__global__ void mask_mix_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                                long long total, int X, int Y, int Z, int bx0, int by0, int bz0, int bx1, int by1, int bz1) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    long long r = i;
+    const int z = (int)(r % Z); r /= Z;
+    const int y = (int)(r % Y); r /= Y;
+    const int x = (int)(r % X);
+    const bool inside = (x >= bx0) & (x < bx1) & (y >= by0) & (y < by1) & (z >= bz0) & (z < bz1);
+    const float m = inside ? 0.f : 1.f;
+    out[i] = __fadd_rn(__fmul_rn(a[i], m), __fmul_rn(b[i], 1.f - m));
+  }
+}
+
+__global__ void label_mix_kernel(const unsigned char* __restrict__ a, const unsigned char* __restrict__ b,
+                                 unsigned char* __restrict__ out, long long total, int X, int Y, int Z, int bx0, int by0,
+                                 int bz0, int bx1, int by1, int bz1) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    long long r = i;
+    const int z = (int)(r % Z); r /= Z;
+    const int y = (int)(r % Y); r /= Y;
+    const int x = (int)(r % X);
+    const bool inside = (x >= bx0) & (x < bx1) & (y >= by0) & (y < by1) & (z >= bz0) & (z < bz1);
+    out[i] = inside ? b[i] : a[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// pseudo labels.  thresh: (softmax(x,1) >= thr)[:,1]   (LA_BCP_train.py:57-60, pancreas_utils.py:275-278)
+//                 argmax: torch.max(softmax(x,1),1)[1] (ACDC_BCP_train.py:112-114)
+// fp32 softmax is replicated step by step (max, expf(x-max), sum, IEEE divide) because
+// "p1 >= 0.5" is not "x1 >= x0" once exp rounds to 1.0f.
+// ------------------------------------------------------------------------------------------
+template <int C>
+__global__ void pseudo_label_kernel(const float* __restrict__ logits, unsigned char* __restrict__ out,
+                                    int N, long long V, int mode, float thr) {
+  const long long total = (long long)N * V;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long n = i / V, v = i - n * V;
+    const float* p = logits + n * C * V + v;
+    float x[C];
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { x[c] = p[(long long)c * V]; m = fmaxf(m, x[c]); }
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { x[c] = expf(x[c] - m); s += x[c]; }
+    if (mode == 0) {
+      out[i] = (__fdiv_rn(x[1], s) >= thr) ? 1 : 0;
+    } else {
+      float best = __fdiv_rn(x[0], s);
+      int bi = 0;
+#pragma unroll
+      for (int c = 1; c < C; ++c) {
+        const float pc = __fdiv_rn(x[c], s);
+        if (pc > best) { best = pc; bi = c; }
+      }
+      out[i] = (unsigned char)bi;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fused SGD(momentum, weight decay) + EMA over a flat fp32 arena (optim.SGD semantics,
+// LA_BCP_train.py:218 + utils/BCP_utils.py:78-81).  hyper = {lr, momentum, wd, ema_alpha, grad_scale, 1-ema_alpha}
+// lives on the device so a captured CUDA graph survives LR decay.
+//   g = grad*grad_scale + wd*p ; buf = mom*buf + g ; p -= lr*buf ; e = e*alpha + (1-alpha)*p
+// elements [n_train, n_total) are EMA-only (never-trained MLP heads / BN buffers for ACDC).
+// ------------------------------------------------------------------------------------------
+__global__ void sgd_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
+                               float* __restrict__ e, const float* __restrict__ hyper, long long n_train, long long n_total) {
+  const float lr = hyper[0], mom = hyper[1], wd = hyper[2], alpha = hyper[3], gs = hyper[4];
+  const float one_m_alpha = hyper[5];   // float(1 - alpha) evaluated in double on the host, like the Python expression
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_total; i += stride) {
+    float pv = p[i];
+    if (i < n_train) {
+      const float gv = g[i] * gs + wd * pv;
+      const float bv = mom * buf[i] + gv;
+      buf[i] = bv;
+      pv = pv - lr * bv;
+      p[i] = pv;
+    }
+    if (e != nullptr) e[i] = __fadd_rn(__fmul_rn(e[i], alpha), __fmul_rn(one_m_alpha, pv));
+  }
+}
+
+// Adam (optim.Adam defaults, pancreas/dataloaders.py:182) + EMA.  hyper = {lr, beta1, beta2, eps, ema_alpha,
+// grad_scale, bias_corr1, bias_corr2_sqrt, 1-ema_alpha}; the two bias corrections are refreshed by the host each step.
+__global__ void adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, float* __restrict__ e, const float* __restrict__ hyper,
+                                long long n_train, long long n_total) {
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], alpha = hyper[4], gs = hyper[5];
+  const float bc1 = hyper[6], bc2s = hyper[7];
+  const float one_m_alpha = hyper[8];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_total; i += stride) {
+    float pv = p[i];
+    if (i < n_train) {
+      const float gv = g[i] * gs;
+      const float mv = b1 * m[i] + (1.f - b1) * gv;
+      const float vv = b2 * v[i] + (1.f - b2) * gv * gv;
+      m[i] = mv; v[i] = vv;
+      const float denom = sqrtf(vv) / bc2s + eps;
+      pv = pv - (lr / bc1) * (mv / denom);
+      p[i] = pv;
+    }
+    if (e != nullptr) e[i] = __fadd_rn(__fmul_rn(e[i], alpha), __fmul_rn(one_m_alpha, pv));
+  }
+}
+
+// ACDC's state_dict EMA also blends int64 num_batches_tracked through float and truncates
+// (ACDC_BCP_train.py:123-129).
+__global__ void ema_i64_kernel(long long* __restrict__ e, const long long* __restrict__ p, int n, float alpha,
+                               float one_m_alpha) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float r = __fadd_rn(__fmul_rn(alpha, (float)e[i]), __fmul_rn(one_m_alpha, (float)p[i]));
+    e[i] = (long long)r;  // truncation toward zero like tensor.copy_(float -> int64)
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// weight repack: fp32 master weights (PyTorch layouts) -> bf16 operand layouts used by the conv kernels.
+// One launch handles every layer of a network from a device-resident job table.
+//   source is always [A][B][T] fp32 (Conv3d/2d: A=Cout,B=Cin; Conv k2s2: A=Cout(half-res),B=Cin(full-res);
+//   ConvTranspose k2s2: A=Cin(half-res),B=Cout(full-res)).
+//   kind 0: [T][B/8][A][8]  inner = B index            -- conv fwd operand; stride-2 "gather" (full->half) operand
+//   kind 1: [T][A/8][B][8]  inner = A index, taps flipped (t -> T-1-t)   -- conv dgrad operand
+//   kind 2: [T][A/8][B][8]  inner = A index            -- stride-2 "scatter" (half->full) operand
+// Channel counts that are not multiples of 8 are zero-padded in the blocked dimension.
+// ------------------------------------------------------------------------------------------
+__global__ void repack_kernel(const float* __restrict__ arena, __nv_bfloat16* __restrict__ packed,
+                              const bcp_repack_job* __restrict__ jobs, int njobs) {
+  for (int j = blockIdx.y; j < njobs; j += gridDim.y) {
+    const bcp_repack_job job = jobs[j];
+    const float* src = arena + job.src_off;
+    __nv_bfloat16* dst = packed + job.dst_off;
+    const int A = job.dim_a, B = job.dim_b, T = job.taps;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    if (job.kind == 0) {
+      // dst [T][ceil(B/8)][A][8] with inner = B index; src [A][B][T]
+      const int Bb = (B + 7) / 8;
+      const long long total = (long long)T * Bb * A * 8;
+      for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        long long r = i;
+        const int b8 = (int)(r % 8); r /= 8;
+        const int a = (int)(r % A); r /= A;
+        const int bb = (int)(r % Bb); r /= Bb;
+        const int t = (int)r;
+        const int b = bb * 8 + b8;
+        const float v = (b < B) ? src[((long long)a * B + b) * T + t] : 0.f;
+        dst[i] = __float2bfloat16_rn(v);
+      }
+    } else {
+      // kind 1 / 2: dst [T][ceil(A/8)][B][8] with inner = A index; src [A][B][T]; kind 1 flips taps
+      const int Ab = (A + 7) / 8;
+      const long long total = (long long)T * Ab * B * 8;
+      for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        long long r = i;
+        const int a8 = (int)(r % 8); r /= 8;
+        const int b = (int)(r % B); r /= B;
+        const int ab = (int)(r % Ab); r /= Ab;
+        const int t = (int)r;
+        const int a = ab * 8 + a8;
+        const int ts = (job.kind == 1) ? (T - 1 - t) : t;
+        const float v = (a < A) ? src[((long long)a * B + b) * T + ts] : 0.f;
+        dst[i] = __float2bfloat16_rn(v);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// layout converts between planar fp32 NC(D)HW and channel-blocked bf16 CB8 [N][C/8][S][8]
+// ------------------------------------------------------------------------------------------
+__global__ void planar_to_cb8_kernel(const float* __restrict__ in, uint4* __restrict__ out, int N, int C, long long S) {
+  const int Cb = (C + 7) / 8;
+  const long long total = (long long)N * Cb * S;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long s = i % S;
+    const long long r = i / S;
+    const int cb = (int)(r % Cb);
+    const long long n = r / Cb;
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = cb * 8 + k;
+      f[k] = (c < C) ? in[(n * C + c) * S + s] : 0.f;
+    }
+    out[i] = pack8(f);
+  }
+}
+
+__global__ void cb8_to_planar_kernel(const uint4* __restrict__ in, float* __restrict__ out, int N, int C, long long S) {
+  const int Cb = (C + 7) / 8;
+  const long long total = (long long)N * Cb * S;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long s = i % S;
+    const long long r = i / S;
+    const int cb = (int)(r % Cb);
+    const long long n = r / Cb;
+    float f[8];
+    unpack8(in[i], f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = cb * 8 + k;
+      if (c < C) out[(n * C + c) * S + s] = f[k];
+    }
+  }
+}
+
+static inline int grid_for(long long total, int threads) {
+  long long b = (total + threads - 1) / threads;
+  const long long cap = (long long)sm_count() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace bcp
+
+using namespace bcp;
+
+extern "C" {
+
+int bcp_mask_mix(const float* a, const float* b, float* out, int n, int c, int X, int Y, int Z,
+                 int bx, int by, int bz, int px, int py, int pz, cudaStream_t stream) {
+  BCP_REQUIRE(a && b && out, "mask_mix: null pointer");
+  BCP_REQUIRE(n > 0 && c > 0 && X > 0 && Y > 0 && Z > 0, "mask_mix: bad shape");
+  const long long total = (long long)n * c * X * Y * Z;
+  // the reference slices mask[w:w+px,...]: python slicing clips at the volume edge
+  const int bx1 = min(bx + px, X), by1 = min(by + py, Y), bz1 = min(bz + pz, Z);
+  mask_mix_kernel<<<grid_for(total, 256), 256, 0, stream>>>(a, b, out, total, X, Y, Z, bx, by, bz, bx1, by1, bz1);
+  return check_launch("mask_mix");
+}
+
+int bcp_label_mix(const unsigned char* a, const unsigned char* b, unsigned char* out, int n, int X, int Y, int Z,
+                  int bx, int by, int bz, int px, int py, int pz, cudaStream_t stream) {
+  BCP_REQUIRE(a && b && out && n > 0 && X > 0 && Y > 0 && Z > 0, "label_mix: bad args");
+  const long long total = (long long)n * X * Y * Z;
+  const int bx1 = min(bx + px, X), by1 = min(by + py, Y), bz1 = min(bz + pz, Z);
+  label_mix_kernel<<<grid_for(total, 256), 256, 0, stream>>>(a, b, out, total, X, Y, Z, bx, by, bz, bx1, by1, bz1);
+  return check_launch("label_mix");
+}
+
+int bcp_pseudo_label(const float* logits, unsigned char* out, int n, int c, long long v, int mode, float thr,
+                     cudaStream_t stream) {
+  BCP_REQUIRE(logits && out, "pseudo_label: null pointer");
+  BCP_REQUIRE(c == 2 || c == 4, "pseudo_label: class count %d unsupported (2 or 4)", c);
+  BCP_REQUIRE(mode == 0 || mode == 1, "pseudo_label: mode");
+  BCP_REQUIRE(!(mode == 0 && c != 2), "pseudo_label: threshold mode takes channel 1 of 2");
+  const long long total = (long long)n * v;
+  if (c == 2)
+    pseudo_label_kernel<2><<<grid_for(total, 256), 256, 0, stream>>>(logits, out, n, v, mode, thr);
+  else
+    pseudo_label_kernel<4><<<grid_for(total, 256), 256, 0, stream>>>(logits, out, n, v, mode, thr);
+  return check_launch("pseudo_label");
+}
+
+int bcp_sgd_ema_step(float* params, const float* grads, float* momentum, float* ema, const float* hyper,
+                     long long n_train, long long n_total, cudaStream_t stream) {
+  BCP_REQUIRE(params && grads && momentum && hyper, "sgd_ema_step: null pointer");
+  BCP_REQUIRE(n_train >= 0 && n_total >= n_train, "sgd_ema_step: bad sizes");
+  if (n_total == 0) return BCP_OK;
+  sgd_ema_kernel<<<grid_for(n_total, 256), 256, 0, stream>>>(params, grads, momentum, ema, hyper, n_train, n_total);
+  return check_launch("sgd_ema_step");
+}
+
+int bcp_adam_ema_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* ema,
+                      const float* hyper, long long n_train, long long n_total, cudaStream_t stream) {
+  BCP_REQUIRE(params && grads && exp_avg && exp_avg_sq && hyper, "adam_ema_step: null pointer");
+  BCP_REQUIRE(n_train >= 0 && n_total >= n_train, "adam_ema_step: bad sizes");
+  if (n_total == 0) return BCP_OK;
+  adam_ema_kernel<<<grid_for(n_total, 256), 256, 0, stream>>>(params, grads, exp_avg, exp_avg_sq, ema, hyper, n_train, n_total);
+  return check_launch("adam_ema_step");
+}
+
+int bcp_ema_i64(long long* ema, const long long* model, int n, float alpha, float one_minus_alpha, cudaStream_t stream) {
+  BCP_REQUIRE(ema && model && n >= 0, "ema_i64: bad args");
+  if (n == 0) return BCP_OK;
+  ema_i64_kernel<<<(n + 127) / 128, 128, 0, stream>>>(ema, model, n, alpha, one_minus_alpha);
+  return check_launch("ema_i64");
+}
+
+int bcp_weights_repack(const float* arena, void* packed, const bcp_repack_job* jobs_dev, int njobs,
+                       cudaStream_t stream) {
+  BCP_REQUIRE(arena && packed && jobs_dev && njobs > 0, "weights_repack: bad args");
+  dim3 grid(32, njobs < 512 ? njobs : 512);
+  repack_kernel<<<grid, 256, 0, stream>>>(arena, (__nv_bfloat16*)packed, jobs_dev, njobs);
+  return check_launch("weights_repack");
+}
+
+int bcp_planar_to_cb8(const float* in, void* out, int n, int c, long long s, cudaStream_t stream) {
+  BCP_REQUIRE(in && out && n > 0 && c > 0 && s > 0, "planar_to_cb8: bad args");
+  const long long total = (long long)n * ((c + 7) / 8) * s;
+  planar_to_cb8_kernel<<<grid_for(total, 256), 256, 0, stream>>>(in, (uint4*)out, n, c, s);
+  return check_launch("planar_to_cb8");
+}
+
+int bcp_cb8_to_planar(const void* in, float* out, int n, int c, long long s, cudaStream_t stream) {
+  BCP_REQUIRE(in && out && n > 0 && c > 0 && s > 0, "cb8_to_planar: bad args");
+  const long long total = (long long)n * ((c + 7) / 8) * s;
+  cb8_to_planar_kernel<<<grid_for(total, 256), 256, 0, stream>>>((const uint4*)in, out, n, c, s);
+  return check_launch("cb8_to_planar");
+}
+
+}  // extern "C"

@@ -1,0 +1,506 @@
+"""torch.autograd.Function wrappers over the C-ABI kernels (bcp_b200/_native.py).
+
+Hidden activations travel as channel-blocked bf16 tensors of shape [N, C/8, X, Y, Z, 8] ("CB8");
+2-D networks use X == 1.  The network input and the logits are planar fp32 NC(D)HW exactly like
+the reference modules' tensors.  PyTorch is used for memory and autograd plumbing only: every
+arithmetic op on the path is a kernel of libbcp_b200.so, and a missing library is a hard error.
+"""
+from __future__ import annotations
+
+import torch
+from torch.autograd import Function
+
+from ._native import LIB, i3, i6, ptr, stream
+
+BF16 = torch.bfloat16
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"bcp_b200.{what}: tensor is on {t.device}; the sm_100a kernels need a CUDA device "
+                           "(there is no CPU fallback)")
+
+
+def cb8_shape(n, c, x, y, z):
+    return (n, (c + 7) // 8, x, y, z, 8)
+
+
+def act_dims(a: torch.Tensor):
+    n, cb, x, y, z, e = a.shape
+    assert e == 8 and a.dtype == BF16
+    return n, cb * 8, x, y, z
+
+
+def _f32(n, device):
+    return torch.empty(int(n), dtype=torch.float32, device=device)
+
+
+# ----------------------------------------------------------------------------------------------
+# layout converts
+# ----------------------------------------------------------------------------------------------
+class PlanarToCB8(Function):
+    @staticmethod
+    def forward(ctx, x):
+        _require_cuda(x, "planar_to_cb8")
+        x = x.contiguous().float()
+        n, c = x.shape[:2]
+        sp = tuple(x.shape[2:])
+        x3 = (1,) + sp if len(sp) == 2 else sp
+        s = x3[0] * x3[1] * x3[2]
+        out = torch.empty(cb8_shape(n, c, *x3), dtype=BF16, device=x.device)
+        LIB.call("bcp_planar_to_cb8", ptr(x), ptr(out), n, c, s, stream())
+        ctx.meta = (n, c, sp, s)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        n, c, sp, s = ctx.meta
+        g = g.contiguous()
+        out = torch.empty((n, c) + sp, dtype=torch.float32, device=g.device)
+        LIB.call("bcp_cb8_to_planar", ptr(g), ptr(out), n, c, s, stream())
+        return out
+
+
+class CB8ToPlanar(Function):
+    @staticmethod
+    def forward(ctx, a, c, two_d):
+        _require_cuda(a, "cb8_to_planar")
+        a = a.contiguous()
+        n, cc, x, y, z = act_dims(a)
+        sp = (y, z) if two_d else (x, y, z)
+        out = torch.empty((n, c) + sp, dtype=torch.float32, device=a.device)
+        LIB.call("bcp_cb8_to_planar", ptr(a), ptr(out), n, c, x * y * z, stream())
+        ctx.meta = (n, c, x, y, z)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        n, c, x, y, z = ctx.meta
+        g = g.contiguous().float()
+        out = torch.empty(cb8_shape(n, c, x, y, z), dtype=BF16, device=g.device)
+        LIB.call("bcp_planar_to_cb8", ptr(g), ptr(out), n, c, x * y * z, stream())
+        return out, None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# convolutions
+# ----------------------------------------------------------------------------------------------
+class ConvPack:
+    """bf16 operand packs of one conv layer: views into the owning network's packed buffer."""
+    __slots__ = ("fwd", "bwd")
+
+    def __init__(self, fwd=None, bwd=None):
+        self.fwd, self.bwd = fwd, bwd
+
+
+def _conv_same(a, wpack, bias, cout, kernel, allow_tc=True):
+    """kx*ky*kz stride-1 'same' conv on CB8; picks the tcgen05 kernel when the shape qualifies."""
+    n, cin, x, y, z = act_dims(a)
+    out = torch.empty(cb8_shape(n, cout, x, y, z), dtype=BF16, device=a.device)
+    dims, k = i3(x, y, z), i3(*kernel)
+    if allow_tc and LIB.query("bcp_conv_tc_supported", cin, cout, dims, k):
+        LIB.call("bcp_conv_tc_fwd", ptr(a), ptr(wpack), ptr(bias), ptr(out), n, cin, cout, dims, k, stream())
+    else:
+        LIB.call("bcp_conv_direct_fwd", ptr(a), ptr(wpack), ptr(bias), ptr(out), n, cin, cout, dims, k,
+                 i3(1, 1, 1), i3(kernel[0] // 2, kernel[1] // 2, kernel[2] // 2), 0, stream())
+    return out
+
+
+def _wgrad(inp, outgrad, cin, cout, in_dims, kernel, stride, pad, wshape):
+    n = inp.shape[0]
+    od = [(in_dims[i] + 2 * pad[i] - kernel[i]) // stride[i] + 1 for i in range(3)]
+    ws = _f32(LIB.query("bcp_conv_wgrad_workspace_floats", n, cin, cout, i3(*od), i3(*kernel)), inp.device)
+    dw = torch.empty(wshape, dtype=torch.float32, device=inp.device)
+    LIB.call("bcp_conv_direct_wgrad", ptr(inp), ptr(outgrad), ptr(dw), ptr(ws), n, cin, cout, i3(*in_dims), i3(*kernel),
+             i3(*stride), i3(*pad), stream())
+    return dw
+
+
+def _chan_sum(t, c):
+    n, _, x, y, z = act_dims(t)
+    s = x * y * z
+    ws = _f32(LIB.query("bcp_chan_sum_workspace_floats", n, c, s), t.device)
+    out = torch.empty(c, dtype=torch.float32, device=t.device)
+    LIB.call("bcp_chan_sum", ptr(t), ptr(out), ptr(ws), n, c, s, stream())
+    return out
+
+
+class ConvSame(Function):
+    """nn.Conv3d(k=3,p=1) / nn.Conv2d(k=3,p=1 | k=1) on CB8 (networks/VNet.py:17, networks/unet.py:20,24,49)."""
+
+    @staticmethod
+    def forward(ctx, a, weight, bias, pack: ConvPack, kernel):
+        _require_cuda(a, "conv")
+        a = a.contiguous()
+        cout = weight.shape[0]
+        ctx.save_for_backward(a, weight)
+        ctx.pack, ctx.kernel, ctx.has_bias = pack, tuple(kernel), bias is not None
+        return _conv_same(a, pack.fwd, bias, cout, kernel)
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        n, cin, x, y, z = act_dims(a)
+        cout, k = weight.shape[0], ctx.kernel
+        da = dw = db = None
+        if ctx.needs_input_grad[0]:
+            da = _conv_same(dy, ctx.pack.bwd, None, cin, k)
+        if ctx.needs_input_grad[1]:
+            dw = _wgrad(a, dy, cin, cout, (x, y, z), k, (1, 1, 1), (k[0] // 2, k[1] // 2, k[2] // 2), weight.shape)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = _chan_sum(dy, cout)
+        return da, dw, db, None, None
+
+
+class ConvDown2(Function):
+    """nn.Conv3d(k=2, s=2) (networks/VNet.py:74).  weight [Cout][Cin][2,2,2]; pack.fwd = kind 0, pack.bwd = kind 2."""
+
+    @staticmethod
+    def forward(ctx, a, weight, bias, pack: ConvPack):
+        _require_cuda(a, "conv_down2")
+        a = a.contiguous()
+        n, cin, x, y, z = act_dims(a)
+        cout = weight.shape[0]
+        out = torch.empty(cb8_shape(n, cout, x // 2, y // 2, z // 2), dtype=BF16, device=a.device)
+        LIB.call("bcp_conv_direct_fwd", ptr(a), ptr(pack.fwd), ptr(bias), ptr(out), n, cin, cout, i3(x, y, z), i3(2, 2, 2),
+                 i3(2, 2, 2), i3(0, 0, 0), 0, stream())
+        ctx.save_for_backward(a, weight)
+        ctx.pack, ctx.has_bias = pack, bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        n, cin, x, y, z = act_dims(a)
+        cout = weight.shape[0]
+        da = dw = db = None
+        if ctx.needs_input_grad[0]:
+            da = torch.empty_like(a)
+            LIB.call("bcp_conv_direct_fwd", ptr(dy), ptr(ctx.pack.bwd), None, ptr(da), n, cout, cin, i3(x // 2, y // 2, z // 2),
+                     i3(2, 2, 2), i3(2, 2, 2), i3(0, 0, 0), 1, stream())
+        if ctx.needs_input_grad[1]:
+            dw = _wgrad(a, dy, cin, cout, (x, y, z), (2, 2, 2), (2, 2, 2), (0, 0, 0), weight.shape)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = _chan_sum(dy, cout)
+        return da, dw, db, None
+
+
+class ConvUp2(Function):
+    """nn.ConvTranspose3d(k=2, s=2) (networks/VNet.py:101).  weight [Cin][Cout][2,2,2]; pack.fwd = kind 2, pack.bwd = kind 0."""
+
+    @staticmethod
+    def forward(ctx, a, weight, bias, pack: ConvPack):
+        _require_cuda(a, "conv_up2")
+        a = a.contiguous()
+        n, cin, x, y, z = act_dims(a)
+        cout = weight.shape[1]
+        out = torch.empty(cb8_shape(n, cout, 2 * x, 2 * y, 2 * z), dtype=BF16, device=a.device)
+        LIB.call("bcp_conv_direct_fwd", ptr(a), ptr(pack.fwd), ptr(bias), ptr(out), n, cin, cout, i3(x, y, z), i3(2, 2, 2),
+                 i3(2, 2, 2), i3(0, 0, 0), 1, stream())
+        ctx.save_for_backward(a, weight)
+        ctx.pack, ctx.has_bias = pack, bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        n, cin, x, y, z = act_dims(a)
+        cout = weight.shape[1]
+        da = dw = db = None
+        if ctx.needs_input_grad[0]:
+            da = torch.empty_like(a)
+            LIB.call("bcp_conv_direct_fwd", ptr(dy), ptr(ctx.pack.bwd), None, ptr(da), n, cout, cin, i3(2 * x, 2 * y, 2 * z),
+                     i3(2, 2, 2), i3(2, 2, 2), i3(0, 0, 0), 0, stream())
+        if ctx.needs_input_grad[1]:
+            # dW[ci][co][t] = sum_i a[i][ci] * dy[2i+t][co]: "in" = dy (full res, co), "outgrad" = a (half res, ci)
+            dw = _wgrad(dy, a, cout, cin, (2 * x, 2 * y, 2 * z), (2, 2, 2), (2, 2, 2), (0, 0, 0), weight.shape)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = _chan_sum(dy, cout)
+        return da, dw, db, None
+
+
+class ConvFirst(Function):
+    """First layer, Cin = 1, planar fp32 input (networks/VNet.py:151 block_one, networks/unet.py:72 in_conv)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        _require_cuda(x, "conv_first")
+        x = x.contiguous().float()
+        assert x.shape[1] == 1, "conv_first takes single-channel input"
+        n = x.shape[0]
+        sp = tuple(x.shape[2:])
+        dims = (1,) + sp if len(sp) == 2 else sp
+        kernel = (1,) + tuple(weight.shape[2:]) if len(sp) == 2 else tuple(weight.shape[2:])
+        cout = weight.shape[0]
+        w = weight.contiguous()
+        out = torch.empty(cb8_shape(n, cout, *dims), dtype=BF16, device=x.device)
+        LIB.call("bcp_conv_first_fwd", ptr(x), ptr(w), ptr(bias), ptr(out), n, cout, i3(*dims), i3(*kernel), stream())
+        ctx.save_for_backward(x, weight)
+        ctx.meta = (n, cout, dims, kernel, bias is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        n, cout, dims, kernel, has_bias = ctx.meta
+        dy = dy.contiguous()
+        dw = db = None
+        if ctx.needs_input_grad[1]:
+            ws = _f32(LIB.query("bcp_conv_first_wgrad_workspace_floats", n, cout, i3(*dims), i3(*kernel)), x.device)
+            dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)
+            LIB.call("bcp_conv_first_wgrad", ptr(x), ptr(dy), ptr(dw), ptr(ws), n, cout, i3(*dims), i3(*kernel), stream())
+        if has_bias and ctx.needs_input_grad[2]:
+            db = _chan_sum(dy, cout)
+        return None, dw, db
+
+
+class Head(Function):
+    """Classifier conv to planar fp32 logits: nn.Conv3d(16, 2, 1) (networks/VNet.py:210) / nn.Conv2d(16, 4, 3, p=1)
+    (networks/unet.py:102)."""
+
+    @staticmethod
+    def forward(ctx, a, weight, bias, two_d):
+        _require_cuda(a, "head")
+        a = a.contiguous()
+        n, cin, x, y, z = act_dims(a)
+        ncls = weight.shape[0]
+        kernel = (1,) + tuple(weight.shape[2:]) if two_d else tuple(weight.shape[2:])
+        w = weight.contiguous()
+        sp = (y, z) if two_d else (x, y, z)
+        out = torch.empty((n, ncls) + sp, dtype=torch.float32, device=a.device)
+        LIB.call("bcp_head_fwd", ptr(a), ptr(w), ptr(bias), ptr(out), n, cin, ncls, i3(x, y, z), i3(*kernel), stream())
+        ctx.save_for_backward(a, weight)
+        ctx.meta = (n, cin, ncls, (x, y, z), kernel, bias is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dlog):
+        a, weight = ctx.saved_tensors
+        n, cin, ncls, dims, kernel, has_bias = ctx.meta
+        dlog = dlog.contiguous().float()
+        w = weight.contiguous()
+        da = dw = db = None
+        if ctx.needs_input_grad[0]:
+            da = torch.empty_like(a)
+            LIB.call("bcp_head_dgrad", ptr(dlog), ptr(w), ptr(da), n, cin, ncls, i3(*dims), i3(*kernel), stream())
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            ws = _f32(LIB.query("bcp_head_wgrad_workspace_floats", n, cin, ncls, i3(*dims), i3(*kernel)), a.device)
+            dw = torch.empty(weight.shape, dtype=torch.float32, device=a.device)
+            db = torch.empty(ncls, dtype=torch.float32, device=a.device) if has_bias else None
+            LIB.call("bcp_head_wgrad", ptr(a), ptr(dlog), ptr(dw), ptr(db), ptr(ws), n, cin, ncls, i3(*dims), i3(*kernel), stream())
+        return da, dw, db, None
+
+
+# ----------------------------------------------------------------------------------------------
+# normalisation + activation (+ dropout) (+ residual)
+# ----------------------------------------------------------------------------------------------
+class NormAct(Function):
+    """act(norm(y)) [* dropout] [+ residual] on CB8.
+
+    mode 'batch': statistics over groups of `spg` samples (train-mode BatchNorm, InstanceNorm with spg=1);
+    running stats (if given) are updated once per group, in order.  mode 'eval': running statistics.
+    mode 'none': no normalisation (normalization='none' of networks/VNet.py:6)."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, running_mean, running_var, nbt, mode, spg, eps, momentum, slope,
+                chan_scale, elem_keep, elem_scale, residual):
+        _require_cuda(y, "norm_act")
+        y = y.contiguous()
+        n, c, x, yy, z = act_dims(y)
+        s = x * yy * z
+        dev = y.device
+        if mode != "batch":
+            spg = n
+        groups = n // spg
+        stat = torch.empty(groups, c, 2, dtype=torch.float32, device=dev)
+        coef = torch.empty(groups, c, 2, dtype=torch.float32, device=dev)
+        if mode == "batch":
+            ws = _f32(LIB.query("bcp_norm_workspace_floats", n, c, s), dev)
+            LIB.call("bcp_norm_stats", ptr(y), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), ptr(nbt),
+                     ptr(stat), ptr(coef), ptr(ws), n, c, s, spg, float(eps), float(momentum), stream())
+        elif mode == "eval":
+            LIB.call("bcp_norm_eval_coef", ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), ptr(stat), ptr(coef),
+                     c, groups, float(eps), stream())
+        else:
+            stat[..., 0] = 0.0
+            stat[..., 1] = 1.0
+            coef[..., 0] = 1.0
+            coef[..., 1] = 0.0
+        out = torch.empty_like(y)
+        if residual is not None:
+            residual = residual.contiguous()
+        LIB.call("bcp_norm_apply", ptr(y), ptr(out), ptr(coef), ptr(chan_scale), ptr(elem_keep), float(elem_scale),
+                 ptr(residual), n, c, s, spg, float(slope), stream())
+        ctx.save_for_backward(y, stat, coef, chan_scale, elem_keep)
+        ctx.meta = (n, c, s, spg, float(slope), float(elem_scale), mode, gamma is not None, beta is not None,
+                    residual is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, da):
+        y, stat, coef, chan_scale, elem_keep = ctx.saved_tensors
+        n, c, s, spg, slope, elem_scale, mode, has_g, has_b, has_res = ctx.meta
+        da = da.contiguous()
+        dev = y.device
+        dy = torch.empty_like(y)
+        need_affine = mode != "none" and (has_g or has_b)
+        dgamma = torch.empty(c, dtype=torch.float32, device=dev) if need_affine else None
+        dbeta = torch.empty(c, dtype=torch.float32, device=dev) if need_affine else None
+        sums = torch.empty(n // spg, c, 2, dtype=torch.float32, device=dev)
+        ws = _f32(LIB.query("bcp_norm_workspace_floats", n, c, s), dev)
+        LIB.call("bcp_norm_bwd", ptr(da), ptr(y), ptr(dy), ptr(stat), ptr(coef), ptr(chan_scale), ptr(elem_keep), elem_scale,
+                 ptr(dgamma), ptr(dbeta), ptr(sums), ptr(ws), n, c, s, spg, slope, 1 if mode == "batch" else 0, stream())
+        return (dy, dgamma if has_g else None, dbeta if has_b else None, None, None, None, None, None, None, None, None,
+                None, None, None, da if has_res else None)
+
+
+# ----------------------------------------------------------------------------------------------
+# resampling
+# ----------------------------------------------------------------------------------------------
+class MaxPool2(Function):
+    @staticmethod
+    def forward(ctx, a):
+        a = a.contiguous()
+        n, c, x, y, z = act_dims(a)
+        out = torch.empty(cb8_shape(n, c, x, y // 2, z // 2), dtype=BF16, device=a.device)
+        LIB.call("bcp_maxpool2_fwd", ptr(a), ptr(out), n * (c // 8) * x, y, z, stream())
+        ctx.save_for_backward(a)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (a,) = ctx.saved_tensors
+        n, c, x, y, z = act_dims(a)
+        din = torch.empty_like(a)
+        LIB.call("bcp_maxpool2_bwd", ptr(a), ptr(g.contiguous()), ptr(din), n * (c // 8) * x, y, z, stream())
+        return din
+
+
+class Upsample2(Function):
+    @staticmethod
+    def forward(ctx, a):
+        a = a.contiguous()
+        n, c, x, y, z = act_dims(a)
+        out = torch.empty(cb8_shape(n, c, x, 2 * y, 2 * z), dtype=BF16, device=a.device)
+        LIB.call("bcp_upsample2_fwd", ptr(a), ptr(out), n * (c // 8) * x, y, z, stream())
+        ctx.meta = (n, c, x, y, z)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        n, c, x, y, z = ctx.meta
+        din = torch.empty(cb8_shape(n, c, x, y, z), dtype=BF16, device=g.device)
+        LIB.call("bcp_upsample2_bwd", ptr(g.contiguous()), ptr(din), n * (c // 8) * x, y, z, stream())
+        return din
+
+
+def maxpool3d_k3s2(a, c):
+    n, _, x, y, z = act_dims(a)
+    out = torch.empty((n, c, (x - 3) // 2 + 1, (y - 3) // 2 + 1, (z - 3) // 2 + 1), dtype=torch.float32, device=a.device)
+    LIB.call("bcp_maxpool3d_k3s2", ptr(a.contiguous()), ptr(out), n, c, x, y, z, stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# step primitives
+# ----------------------------------------------------------------------------------------------
+def _dims3(t, lead):
+    sp = tuple(t.shape[lead:])
+    return (sp[0], sp[1], 1) if len(sp) == 2 else sp
+
+
+def mask_mix(a: torch.Tensor, b: torch.Tensor, box, out: torch.Tensor | None = None) -> torch.Tensor:
+    """out = a*M + b*(1-M) with the implicit box mask (LA_BCP_train.py:248-249).  a, b: fp32 [N,C,...]."""
+    _require_cuda(a, "mask_mix")
+    a, b = a.contiguous().float(), b.contiguous().float()
+    X, Y, Z = _dims3(a, 2)
+    box = tuple(box) if len(box) == 6 else (box[0], box[1], 0, box[2], box[3], 1)
+    if out is None:
+        out = torch.empty_like(a)
+    assert out.is_contiguous() and out.shape == a.shape and out.dtype == torch.float32
+    LIB.call("bcp_mask_mix", ptr(a), ptr(b), ptr(out), a.shape[0], a.shape[1], X, Y, Z, *[int(v) for v in box], stream())
+    return out
+
+
+def label_mix(a: torch.Tensor, b: torch.Tensor, box) -> torch.Tensor:
+    """uint8 label maps: a outside the box, b inside (label_batch = lab_a*M + lab_b*(1-M), LA_BCP_train.py:156)."""
+    _require_cuda(a, "label_mix")
+    a, b = to_u8_labels(a).contiguous(), to_u8_labels(b).contiguous()
+    X, Y, Z = _dims3(a, 1)
+    box = tuple(box) if len(box) == 6 else (box[0], box[1], 0, box[2], box[3], 1)
+    out = torch.empty_like(a)
+    LIB.call("bcp_label_mix", ptr(a), ptr(b), ptr(out), a.shape[0], X, Y, Z, *[int(v) for v in box], stream())
+    return out
+
+
+def pseudo_label(logits: torch.Tensor, mode: str = "thresh", thr: float = 0.5) -> torch.Tensor:
+    """uint8 pseudo labels from planar fp32 logits (LA_BCP_train.py:57-60 / ACDC_BCP_train.py:112-114)."""
+    _require_cuda(logits, "pseudo_label")
+    logits = logits.contiguous().float()
+    n, c = logits.shape[:2]
+    v = logits[0, 0].numel()
+    out = torch.empty((n,) + tuple(logits.shape[2:]), dtype=torch.uint8, device=logits.device)
+    LIB.call("bcp_pseudo_label", ptr(logits), ptr(out), n, c, v, 0 if mode == "thresh" else 1, float(thr), stream())
+    return out
+
+
+def largest_cc(seg_u8: torch.Tensor, connectivity: int | None = None, out_float: bool = False) -> torch.Tensor:
+    """Per-(sample, class) largest connected component on the GPU (LA_BCP_train.py:65-77, ACDC_BCP_train.py:89-109)."""
+    _require_cuda(seg_u8, "largest_cc")
+    seg = seg_u8.contiguous()
+    assert seg.dtype == torch.uint8
+    n = seg.shape[0]
+    sp = tuple(seg.shape[1:])
+    X, Y, Z = (1,) + sp if len(sp) == 2 else sp
+    conn = connectivity if connectivity is not None else len(sp)
+    ws = torch.empty(LIB.query("bcp_largest_cc_workspace_bytes", n, X * Y * Z), dtype=torch.uint8, device=seg.device)
+    out = torch.empty(seg.shape, dtype=torch.float32 if out_float else torch.uint8, device=seg.device)
+    LIB.call("bcp_largest_cc", ptr(seg), None if out_float else ptr(out), ptr(out) if out_float else None, ptr(ws),
+             n, X, Y, Z, conn, stream())
+    return out
+
+
+class MixLoss(Function):
+    """Returns a 3-vector [ (dice+ce)/2, dice, ce ] (device).  form 0 = LA/PAN, form 1 = ACDC."""
+
+    @staticmethod
+    def forward(ctx, logits, lab_img, lab_patch, box, mask_u8, form, w_img, w_patch):
+        _require_cuda(logits, "mix_loss")
+        logits = logits.contiguous().float()
+        n, c = logits.shape[:2]
+        X, Y, Z = _dims3(logits, 2)
+        if box is None:
+            box = (0, 0, 0, 0, 0, 0)
+        box6 = tuple(box) if len(box) == 6 else (box[0], box[1], 0, box[2], box[3], 1)
+        if mask_u8 is not None:
+            mask_u8 = mask_u8.contiguous()
+            assert mask_u8.dtype == torch.uint8 and mask_u8.numel() == n * X * Y * Z
+        li = lab_img.contiguous()
+        lp = lab_patch.contiguous()
+        assert li.dtype == torch.uint8 and lp.dtype == torch.uint8
+        dev = logits.device
+        cbuf = _f32(LIB.query("bcp_mix_loss_ctx_floats", n, c), dev)
+        ws = _f32(LIB.query("bcp_mix_loss_workspace_floats", n, c, X * Y * Z), dev)
+        LIB.call("bcp_mix_loss_fwd", ptr(logits), ptr(li), ptr(lp), ptr(mask_u8), ptr(cbuf), ptr(ws), n, c, X, Y, Z, i6(box6),
+                 int(form), float(w_img), float(w_patch), stream())
+        ctx.save_for_backward(logits, li, lp, cbuf, mask_u8)
+        ctx.meta = (n, c, X, Y, Z, box6)
+        return cbuf[:3].clone()
+
+    @staticmethod
+    def backward(ctx, g3):
+        logits, li, lp, cbuf, mask_u8 = ctx.saved_tensors
+        n, c, X, Y, Z, box6 = ctx.meta
+        g3 = g3.contiguous().float()
+        dlog = torch.empty_like(logits)
+        LIB.call("bcp_mix_loss_bwd", ptr(logits), ptr(li), ptr(lp), ptr(mask_u8), ptr(cbuf), ptr(g3), ptr(dlog), n, c, X, Y, Z,
+                 i6(box6), stream())
+        return dlog, None, None, None, None, None, None, None
+
+
+def to_u8_labels(t: torch.Tensor) -> torch.Tensor:
+    """int64 / float32 / uint8 label maps -> uint8 (the reference casts with .type(torch.int64), utils/BCP_utils.py:59)."""
+    return t if t.dtype == torch.uint8 else t.to(torch.uint8)

@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py -- LA V-Net BCP self-training step throughput (patches/s) on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --gpus N ...            # the reference algorithm's CPU path (oracle port)
+
+A "step" is one BCP self-training step (LA_BCP_train.py:234-270): teacher forward on 4 unlabeled volumes, pseudo
+labels + largest-CC, bidirectional copy-paste mix, student forward/backward on the 4 mixed 112x112x80 patches,
+masked Dice+CE, SGD and the EMA teacher update.  "patches" = mixed volumes through the student (4 per step per GPU).
+Prints ONE JSON line (rank 0).  See the task contract in DESIGN.md section "Measurement".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SHAPE = (112, 112, 80)
+FLOP_PER_STEP = 1280.0e9          # 4 teacher fwd + 4 student fwd+bwd, conv MACs x2
+PATCHES_PER_STEP = 4
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def synthetic_batch(rank, gen_device):
+    g = torch.Generator(device="cpu").manual_seed(1337 + rank)
+    vol = torch.randn((8, 1) + SHAPE, generator=g, dtype=torch.float32)
+    # blobby labels: threshold a box-filtered noise field
+    noise = torch.randn((8, 1) + SHAPE, generator=g)
+    sm = torch.nn.functional.avg_pool3d(noise, 5, stride=1, padding=2)
+    lab = (sm[:, 0] > sm.std()).to(torch.uint8)
+    return vol, lab
+
+
+def build_native(dev):
+    from bcp_b200.networks.net_factory import net_factory
+    from bcp_b200.optim import FusedSGD_EMA
+    torch.manual_seed(1337)
+    model = net_factory("VNet", 1, 2, "train")
+    ema = net_factory("VNet", 1, 2, "train")
+    for p in ema.parameters():
+        p.detach_()
+    ema.load_state_dict(model.state_dict())
+    model.train()
+    ema.train()
+    opt = FusedSGD_EMA(model, ema, lr=0.01, momentum=0.9, weight_decay=1e-4, ema_alpha=0.99, ema_mode="params")
+    return model, ema, opt
+
+
+def run_native(args):
+    import torch.distributed as dist
+    from bcp_b200._native import LIB
+    from bcp_b200.step import la_self_train_step
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    model, ema, opt = build_native(dev)
+    vol_h, lab_h = synthetic_batch(rank, dev)
+    vol_h, lab_h = vol_h.pin_memory(), lab_h.pin_memory()
+    vol_d, lab_d = vol_h.to(dev), lab_h.to(dev)
+    np.random.seed(1337 + rank)
+
+    def step_resident():
+        return la_self_train_step(model, ema, opt, vol_d, lab_d)
+
+    def step_e2e():
+        v = vol_h.to(dev, non_blocking=True)
+        l = lab_h.to(dev, non_blocking=True)
+        r = la_self_train_step(model, ema, opt, v, l)
+        return float(r["loss"].cpu())            # D2H read of the step's result
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        barrier()
+        return ms, out
+
+    for _ in range(max(args.warmup, 3)):
+        r = step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = LIB.launches
+    ms, r = timed(step_resident, args.steps)
+    launches = LIB.launches - l0
+    clocks = sampler.stop() if rank == 0 else None
+    loss = float(r["loss"])
+    ms_e2e, _ = timed(step_e2e, args.steps)
+
+    # roofline of the dominant kernel family (convolutions): one instrumented extra step with CUDA events around
+    # every conv launch on the launching stream; algorithmic FLOPs = 2*MACs of that launch.
+    roof = conv_roofline(LIB, step_resident)
+    pk, pk_src = peaks()
+    if roof is not None:
+        peak = pk["bf16_tflops_sustained"]
+        roof.update({"bound": "tensor", "peak": peak, "unit": "TFLOP/s", "frac": roof["achieved"] / peak, "peak_source": pk_src + " (sustained)"})
+    value = world * PATCHES_PER_STEP * args.steps / (ms / 1e3)
+    e2e = world * PATCHES_PER_STEP * args.steps / (ms_e2e / 1e3)
+    line = {
+        "metric": "LA V-Net BCP train-step patches/sec", "value": value, "unit": "patches/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "LA V-Net BCP self-train step: per GPU 8 loaded volumes 112x112x80 (4 labeled + 4 unlabeled), "
+                               "4 mixed student patches (BASELINE configs[1]); random-init weights",
+                   "parallelism": "dp%d" % world, "per_gpu_student_patches": 4,
+                   "l2": "per-step working set (>2 GB of activations) exceeds the 126 MB L2; no explicit flush"},
+        "loss": loss, "gpu_launches": launches, "clocks": clocks,
+        "e2e": {"value": e2e, "unit": "patches/s", "h2d_bytes_per_step": vol_h.numel() * 4 + lab_h.numel(),
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+        "step_flops": FLOP_PER_STEP, "step_tflops": world * FLOP_PER_STEP * args.steps / (ms / 1e3) / 1e12,
+        "roofline": roof,
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_sample()
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def conv_roofline(LIB, step_fn):
+    names = ("bcp_conv_tc_fwd", "bcp_conv_tc_wgrad")
+    recs = []
+    orig = LIB.call
+
+    def wrapped(name, *a):
+        if name in names:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            orig(name, *a)
+            e1.record()
+            # args: (in, wpack, bias, out, n, cin, cout, dims, kernel, stream) for fwd
+            n, cin, cout, dims, kernel = a[4], a[5], a[6], a[7], a[8]
+            vox = n * dims[0] * dims[1] * dims[2]
+            taps = kernel[0] * kernel[1] * kernel[2]
+            recs.append((name, e0, e1, 2.0 * vox * taps * cin * cout, cin, cout))
+        else:
+            orig(name, *a)
+    LIB.call = wrapped
+    try:
+        step_fn()
+        torch.cuda.synchronize()
+    finally:
+        LIB.call = orig
+    if not recs:
+        return None
+    tot_ms = sum(e0.elapsed_time(e1) for _, e0, e1, _, _, _ in recs)
+    tot_fl = sum(f for *_, f, _, _ in recs)
+    per = {}
+    for name, e0, e1, f, cin, cout in recs:
+        k = "%s_c%d_%d" % (name.replace("bcp_conv_", ""), cin, cout)
+        d = per.setdefault(k, [0.0, 0.0, 0])
+        d[0] += e0.elapsed_time(e1)
+        d[1] += f
+        d[2] += 1
+    return {"kernel": "conv_tc (tcgen05 implicit GEMM, fwd+dgrad)", "launches": len(recs), "avg_launch_ms": tot_ms / len(recs),
+            "achieved": tot_fl / (tot_ms / 1e3) / 1e12, "traffic": None,
+            "per_shape_tflops": {k: round(v[1] / (v[0] / 1e3) / 1e12, 1) for k, v in per.items()},
+            "kernel_ms_per_step": tot_ms}
+
+
+def oracle_step_runner():
+    """The reference algorithm's CPU path (oracle/bcp_oracle.py: fp32 PyTorch restatement pinned to the reference)."""
+    from oracle import bcp_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(1337)
+    model, ema = O.net_factory("VNet", 1, 2, "train"), O.net_factory("VNet", 1, 2, "train")
+    for p in ema.parameters():
+        p.detach_()
+    ema.load_state_dict(model.state_dict())
+    model.train()
+    ema.train()
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=0.0001)
+    vol, lab = synthetic_batch(0, None)
+    rs = np.random.RandomState(1337)
+
+    def step():
+        return O.la_self_train_step(model, ema, opt, vol, lab.long(), rng=rs)
+    return step
+
+
+def cpu_baseline_sample():
+    step = oracle_step_runner()
+    t0 = time.time()
+    step()
+    dt = time.time() - t0
+    return {"value": PATCHES_PER_STEP / dt, "unit": "patches/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "1 LA self-train step (8 volumes 112x112x80, 4 student patches), first call, fp32 PyTorch CPU, %.1f s" % dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    step = oracle_step_runner()
+    t0 = time.time()
+    step()                                      # warm-up (also sizes the sample)
+    t_first = time.time() - t0
+    budget = 150.0
+    n_eff = max(1, min(args.steps, int(budget / max(t_first, 1e-3))))
+    t0 = time.time()
+    for _ in range(n_eff):
+        step()
+    dt = (time.time() - t0) / n_eff
+    v = PATCHES_PER_STEP / dt
+    line = {"impl": "reference", "metric": "LA V-Net BCP train-step patches/sec", "value": v, "unit": "patches/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "LA V-Net BCP self-train step: 8 loaded volumes 112x112x80, 4 mixed student patches "
+                                   "(BASELINE configs[1]) on the host CPU", "parallelism": "cpu"},
+            "cpu_baseline": {"value": v, "unit": "patches/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": "%d timed step(s) after 1 warm-up (time-bounded to ~150 s of the requested %d)" % (n_eff, args.steps)},
+            "e2e": {"value": v, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_native(a)

@@ -1,0 +1,162 @@
+/* bcp_b200 -- C ABI of the B200-native BCP training-step kernels (libbcp_b200.so).
+ *
+ * The reference (DeepMed-Lab-ECNU/BCP) has no FFI seam: every operator on its hot path is a PyTorch
+ * library call made from Python.  The entry points below are what a binding for that
+ * path has to reach; each one names the reference call site(s) it replaces (paths relative to
+ * /root/reference/code).  Host code (bcp_b200/*.py) reaches them through ctypes; INTEGRATION.md shows the
+ * stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C symbols, POD arguments, no torch types; every call takes the cudaStream_t to enqueue on
+ *   - return 0 on success, <0 on error (-1 invalid argument, -2 unsupported shape, -3 CUDA error);
+ *     bcp_last_error() returns a thread-local message.  Never throws, never aborts, never synchronises.
+ *   - the CALLER owns all memory, including workspaces (query bcp_*_workspace_* first); no hidden allocation
+ *     and no global mutable state, so calls are re-entrant (autograd's backward thread, one process per GPU)
+ *   - activations: channel-blocked bf16 "CB8"  [N][ceil(C/8)][X][Y][Z][8]  (2-D nets use X = 1)
+ *     network input / logits: planar fp32 [N][C][X][Y][Z] (PyTorch NCDHW); labels: uint8 [N][X][Y][Z]
+ *     statistics, master weights, gradients of weights: fp32
+ */
+#ifndef BCP_B200_H_
+#define BCP_B200_H_
+
+#include <cuda_runtime_api.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BCP_B200_ABI_VERSION 1
+
+const char* bcp_last_error(void);
+int bcp_abi_version(void);
+int bcp_device_sm_count(void);
+
+/* ---- box mask-mix: out = a*M + b*(1-M), M = 0 inside box [b, b+p) else 1.  Bit-exact vs the tensor
+ * expression at LA_BCP_train.py:155,248-249; ACDC_BCP_train.py:244,372-373; pancreas/train_pancreas.py:86,155-156.
+ * a, b, out: fp32 [n][c][X][Y][Z].  The box is clipped to the volume like Python slicing. */
+int bcp_mask_mix(const float* a, const float* b, float* out, int n, int c, int X, int Y, int Z,
+                 int bx, int by, int bz, int px, int py, int pz, cudaStream_t stream);
+
+/* uint8 label maps mixed with the same box (label_batch at LA_BCP_train.py:156, ACDC_BCP_train.py:245). */
+int bcp_label_mix(const unsigned char* a, const unsigned char* b, unsigned char* out, int n, int X, int Y, int Z,
+                  int bx, int by, int bz, int px, int py, int pz, cudaStream_t stream);
+
+/* ---- pseudo labels from planar fp32 logits [n][c][v] -> uint8 [n][v].
+ * mode 0: (softmax(x,1) >= thr)[:,1]     LA_BCP_train.py:57-60, pancreas/pancreas_utils.py:275-278   (c == 2)
+ * mode 1: argmax_c softmax(x,1)          ACDC_BCP_train.py:112-114                                   (c == 2|4) */
+int bcp_pseudo_label(const float* logits, unsigned char* out, int n, int c, long long v, int mode, float thr,
+                     cudaStream_t stream);
+
+/* ---- largest connected component per (sample, class 1..3); LA_BCP_train.py:65-77, pancreas_utils.py:284-296,
+ * ACDC_BCP_train.py:89-109 (skimage.measure.label + bincount on the CPU in the reference).
+ * seg: uint8 [n][X][Y][Z] with values 0..3; outputs (either may be NULL): uint8 and/or float32 of the same shape
+ * holding class value where the voxel belongs to the largest component of its class, else 0. */
+long long bcp_largest_cc_workspace_bytes(int n, long long v);
+int bcp_largest_cc(const unsigned char* seg, unsigned char* out_u8, float* out_f32, void* workspace, int n, int X, int Y,
+                   int Z, int connectivity, cudaStream_t stream);
+
+/* ---- fused mask-weighted Dice + CE.  form 0: utils/BCP_utils.py:58-69 + utils/losses.py:47-77 (LA) and
+ * pancreas/losses.py:82-141; form 1: ACDC_BCP_train.py:167-179 + utils/losses.py:102-134.
+ * Pre-train losses (LA_BCP_train.py:159-161) are the empty-box case.  `mask` (optional uint8 [n][v], 1 = image
+ * region) overrides the box for callers that hold an explicit loss mask (utils/losses.py:47 mask_DiceLoss API).
+ * ctx (device, bcp_mix_loss_ctx_floats): [0]=(dice+ce)/2, [1]=dice, [2]=ce, rest = backward coefficients.
+ * bwd: grad3 (device) = upstream gradients of ctx[0..2]; dlogits = (g1+g0/2)*d(dice)/dx + (g2+g0/2)*d(ce)/dx. */
+long long bcp_mix_loss_ctx_floats(int n, int c);
+long long bcp_mix_loss_workspace_floats(int n, int c, long long v);
+int bcp_mix_loss_fwd(const float* logits, const unsigned char* lab_img, const unsigned char* lab_patch,
+                     const unsigned char* mask, float* ctx, float* workspace, int n, int c, int X, int Y, int Z, const int* box6, int form, float w_img,
+                     float w_patch, cudaStream_t stream);
+int bcp_mix_loss_bwd(const float* logits, const unsigned char* lab_img, const unsigned char* lab_patch,
+                     const unsigned char* mask, const float* ctx, const float* grad3, float* dlogits,
+                     int n, int c, int X, int Y, int Z, const int* box6, cudaStream_t stream);
+
+/* ---- optimiser + EMA over flat fp32 arenas.
+ * SGD: torch.optim.SGD(momentum, weight_decay) at LA_BCP_train.py:218 / ACDC_BCP_train.py:334 fused with
+ *      update_ema_variables (utils/BCP_utils.py:78-81) / update_model_ema (ACDC_BCP_train.py:123-129).
+ *      hyper (device) = {lr, momentum, weight_decay, ema_alpha, grad_scale, 1-ema_alpha}
+ * Adam: torch.optim.Adam(lr) at pancreas/dataloaders.py:182 + pancreas/pancreas_utils.py:299-302.
+ *      hyper (device) = {lr, beta1, beta2, eps, ema_alpha, grad_scale, 1-beta1^t, sqrt(1-beta2^t), 1-ema_alpha}
+ * elements [n_train, n_total) are EMA-only; ema may be NULL. */
+int bcp_sgd_ema_step(float* params, const float* grads, float* momentum, float* ema, const float* hyper,
+                     long long n_train, long long n_total, cudaStream_t stream);
+int bcp_adam_ema_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* ema,
+                      const float* hyper, long long n_train, long long n_total, cudaStream_t stream);
+int bcp_ema_i64(long long* ema, const long long* model, int n, float alpha, float one_minus_alpha, cudaStream_t stream);
+
+/* ---- weight repack: fp32 master weights -> bf16 operand layouts (one launch per network).
+ * source tensor is [dim_a][dim_b][taps] fp32 at arena + src_off (floats); destination at packed + dst_off (bf16 elems)
+ * kind 0: [T][dim_b/8][dim_a][8] (inner = b)          conv fwd / stride-2 gather operand
+ * kind 1: [T][dim_a/8][dim_b][8] (inner = a), taps reversed     conv dgrad operand
+ * kind 2: [T][dim_a/8][dim_b][8] (inner = a)          stride-2 scatter operand */
+typedef struct bcp_repack_job {
+  long long src_off;
+  long long dst_off;
+  int dim_a, dim_b, taps, kind;
+} bcp_repack_job;
+int bcp_weights_repack(const float* arena, void* packed, const bcp_repack_job* jobs_dev, int njobs, cudaStream_t stream);
+
+/* ---- layout converts planar fp32 <-> CB8 bf16 */
+int bcp_planar_to_cb8(const float* in, void* out, int n, int c, long long s, cudaStream_t stream);
+int bcp_cb8_to_planar(const void* in, float* out, int n, int c, long long s, cudaStream_t stream);
+
+/* ---- normalisation (train-mode nn.BatchNorm3d/2d: networks/VNet.py:19, networks/unet.py:21,25;
+ * nn.InstanceNorm3d: pancreas/Vnet.py:25,49,76) fused with ReLU/LeakyReLU, Dropout3d/Dropout and the skip add.
+ * groups of `spg` consecutive samples share statistics (BatchNorm of one reference forward call = one group;
+ * InstanceNorm: spg = 1).  stat/coef: fp32 [n/spg][c][2] = {mean, invstd} / {scale, shift}. */
+int bcp_norm_chunks(long long s);
+long long bcp_norm_workspace_floats(int n, int c, long long s);
+int bcp_norm_stats(const void* y, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                   long long* num_batches_tracked, float* stat, float* coef, float* workspace,
+                   int n, int c, long long s, int spg, float eps, float momentum, cudaStream_t stream);
+int bcp_norm_eval_coef(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                       float* stat, float* coef, int c, int groups, float eps, cudaStream_t stream);
+int bcp_norm_apply(const void* y, void* out, const float* coef, const float* chan_scale, const unsigned char* elem_keep,
+                   float elem_scale, const void* residual, int n, int c, long long s, int spg, float slope,
+                   cudaStream_t stream);
+int bcp_norm_bwd(const void* dact, const void* y, void* dy, const float* stat, const float* coef, const float* chan_scale,
+                 const unsigned char* elem_keep, float elem_scale, float* dgamma, float* dbeta, float* sums,
+                 float* workspace, int n, int c, long long s, int spg, float slope, int stats_grad, cudaStream_t stream);
+
+/* ---- convolutions (nn.Conv3d / nn.Conv2d / nn.ConvTranspose3d call sites: networks/VNet.py:17,74,101,210;
+ * networks/unet.py:20,24,49,102; pancreas/Vnet.py:19,43,70,128).  dims/kernel/stride/pad are int[3] (x,y,z).
+ * conv_tc_*: tcgen05 + TMA implicit GEMM for 3x3x3 / 1x3x3, stride 1, 'same' padding, channels % 16 == 0.
+ * conv_direct_*: CUDA-core kernels for everything else (see csrc/conv_direct.cu). */
+int bcp_conv_direct_fwd(const void* in, const void* wpack, const float* bias, void* out, int n, int cin, int cout,
+                        const int* in_dims, const int* kernel, const int* stride, const int* pad, int transposed,
+                        cudaStream_t stream);
+long long bcp_conv_wgrad_workspace_floats(int n, int cin, int cout, const int* out_dims, const int* kernel);
+int bcp_conv_direct_wgrad(const void* in, const void* outgrad, float* dw, float* workspace, int n, int cin, int cout,
+                          const int* in_dims, const int* kernel, const int* stride, const int* pad, cudaStream_t stream);
+long long bcp_chan_sum_workspace_floats(int n, int c, long long s);
+int bcp_chan_sum(const void* x, float* out, float* workspace, int n, int c, long long s, cudaStream_t stream);
+int bcp_conv_first_fwd(const float* in, const float* w, const float* bias, void* out, int n, int cout,
+                       const int* dims, const int* kernel, cudaStream_t stream);
+long long bcp_conv_first_wgrad_workspace_floats(int n, int cout, const int* dims, const int* kernel);
+int bcp_conv_first_wgrad(const float* in, const void* outgrad, float* dw, float* workspace, int n, int cout,
+                         const int* dims, const int* kernel, cudaStream_t stream);
+int bcp_head_fwd(const void* in, const float* w, const float* bias, float* logits, int n, int cin, int ncls,
+                 const int* dims, const int* kernel, cudaStream_t stream);
+int bcp_head_dgrad(const float* dlogits, const float* w, void* din, int n, int cin, int ncls, const int* dims,
+                   const int* kernel, cudaStream_t stream);
+long long bcp_head_wgrad_workspace_floats(int n, int cin, int ncls, const int* dims, const int* kernel);
+int bcp_head_wgrad(const void* in, const float* dlogits, float* dw, float* db, float* workspace, int n, int cin, int ncls,
+                   const int* dims, const int* kernel, cudaStream_t stream);
+
+/* tcgen05 implicit-GEMM convolution, stride 1, 'same' zero padding, kernel (kx,3,3) with kx in {1,3}.
+ * wpack is the kind-0 (forward) or kind-1 (dgrad) pack.  Returns -2 for shapes it does not take. */
+int bcp_conv_tc_supported(int cin, int cout, const int* dims, const int* kernel);
+int bcp_conv_tc_fwd(const void* in, const void* wpack, const float* bias, void* out, int n, int cin, int cout,
+                    const int* dims, const int* kernel, cudaStream_t stream);
+
+/* ---- resampling (networks/unet.py:37 MaxPool2d(2); :50 Upsample(bilinear, align_corners=True);
+ * networks/VNet.py:249 MaxPool3d(3, stride=2)).  planes = n * ceil(c/8) * X. */
+int bcp_maxpool2_fwd(const void* in, void* out, long long planes, int y, int z, cudaStream_t stream);
+int bcp_maxpool2_bwd(const void* in, const void* dout, void* din, long long planes, int y, int z, cudaStream_t stream);
+int bcp_upsample2_fwd(const void* in, void* out, long long planes, int y, int z, cudaStream_t stream);
+int bcp_upsample2_bwd(const void* dout, void* din, long long planes, int y, int z, cudaStream_t stream);
+int bcp_maxpool3d_k3s2(const void* in, float* out, int n, int c, int x, int y, int z, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BCP_B200_H_ */

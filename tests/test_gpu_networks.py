@@ -1,0 +1,249 @@
+"""GPU parity of whole networks and whole BCP steps against the golden vectors minted from the reference
+(tests/golden/*.npz) and the fp32 oracle.  Activations are bf16 on the B200 path, the reference is fp32, so logits
+carry bf16 rounding noise; the tolerances below are the stated bf16 budget (DESIGN.md section "Parity")."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import bcp_oracle as O
+from tests.golden.golden_common import inject_dropout, digest_named
+from tests.util import load_golden, T, rel_rms, record
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 3e-2       # relative RMS error of logits through 30 bf16 conv layers vs the fp32 reference
+LOSS_TOL = 1e-2        # relative error of the step loss (fp32 reference vs bf16 activations)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def _vnet(dev, seed, has_dropout, mode_train, drop_seed=None):
+    from bcp_b200.networks.VNet import VNet
+    net = VNet(1, 2, 16, "batchnorm", has_dropout)
+    O.fill_state_dict_(net, seed)
+    net = net.to(dev)
+    net.train(mode_train)
+    if drop_seed is not None:
+        inject_dropout(net, seed=drop_seed)
+    return net
+
+
+def test_vnet_eval_logits(dev):
+    g = load_golden("networks")
+    net = _vnet(dev, 21, False, False)
+    with torch.no_grad():
+        lo, feat = net(O.synthetic_volume((1, 1, 48, 48, 48), 22).to(dev))
+    e = rel_rms(lo.cpu(), T(g["vnet_eval_logits"]))
+    record("vnet_eval_logits_rel_rms", e)
+    assert e <= LOGIT_TOL
+    assert rel_rms(feat.cpu(), T(g["vnet_eval_feat"])) <= LOGIT_TOL
+
+
+def test_vnet_train_fwd_bwd(dev):
+    g = load_golden("networks")
+    net = _vnet(dev, 23, True, True, drop_seed=24)
+    lo, _ = net(O.synthetic_volume((2, 1, 48, 48, 48), 25).to(dev))
+    e = rel_rms(lo.detach().cpu(), T(g["vnet_train_logits"]))
+    record("vnet_train_logits_rel_rms", e)
+    assert e <= LOGIT_TOL
+    (lo * O.synthetic_volume(tuple(lo.shape), 26).to(dev)).sum().backward()
+    e1 = rel_rms(net.encoder.block_one.conv[0].weight.grad.cpu(), T(g["vnet_train_grad_first"]))
+    e2 = rel_rms(net.encoder.block_three.conv[3].weight.grad[:8, :8].cpu(), T(g["vnet_train_grad_mid"]))
+    record("vnet_train_grad_first_rel_rms", e1)
+    record("vnet_train_grad_mid_rel_rms", e2)
+    assert e1 <= 0.15 and e2 <= 0.15          # gradients through 60 bf16 layers: direction agrees, ~10% noise
+    d = digest_named({k: v for k, v in net.state_dict().items() if "running" in k})
+    ref = g["vnet_train_bn_state"]
+    assert np.allclose(d[:, 1], ref[:, 1], rtol=2e-2)
+
+
+def test_vnet_grouped_equals_two_calls(dev):
+    """Batching two reference forward calls as two BatchNorm groups is bit-identical to calling twice."""
+    x = O.synthetic_volume((4, 1, 32, 32, 16), 5).to(dev)
+    outs = []
+    for grouped in (False, True):
+        net = _vnet(dev, 7, False, True)
+        with torch.no_grad():
+            if grouped:
+                o = net(x, groups=2, with_features=False)[0]
+            else:
+                o = torch.cat([net(x[:2], with_features=False)[0], net(x[2:], with_features=False)[0]])
+        outs.append((o, {k: v.clone() for k, v in net.state_dict().items() if "running" in k or "num_batches" in k}))
+    assert torch.equal(outs[0][0], outs[1][0])
+    for k in outs[0][1]:
+        assert torch.equal(outs[0][1][k], outs[1][1][k]), k
+
+
+def test_unet_logits(dev):
+    from bcp_b200.networks.unet import UNet_2d
+    g = load_golden("networks")
+    net = UNet_2d(1, 4)
+    O.fill_state_dict_(net, 31)
+    net = net.to(dev).eval()
+    x = O.synthetic_volume((2, 1, 64, 48), 32, "rand").to(dev)
+    with torch.no_grad():
+        e = rel_rms(net(x).cpu(), T(g["unet_eval_logits"]))
+    record("unet_eval_logits_rel_rms", e)
+    assert e <= LOGIT_TOL
+    net.train()
+    inject_dropout(net, seed=33)
+    lo = net(x)
+    e = rel_rms(lo.detach().cpu(), T(g["unet_train_logits"]))
+    record("unet_train_logits_rel_rms", e)
+    assert e <= LOGIT_TOL
+    (lo * O.synthetic_volume(tuple(lo.shape), 34).to(dev)).sum().backward()
+    d = digest_named({n: p.grad for n, p in net.named_parameters() if p.grad is not None})
+    ref = g["unet_train_grad_digest"]
+    assert d.shape == ref.shape
+    big = ref[:, 1] > 1e-3 * ref[:, 1].max()
+    rel = np.abs(d[big, 1] - ref[big, 1]) / ref[big, 1]
+    record("unet_grad_abs_sum_rel_max", float(rel.max()))
+    assert rel.max() <= 0.2
+
+
+def test_pan_vnet_logits(dev):
+    from bcp_b200.pancreas.Vnet import VNet
+    g = load_golden("networks")
+    net = VNet()
+    O.fill_state_dict_(net, 41)
+    net = net.to(dev).train()
+    lo = net(O.synthetic_volume((2, 1, 32, 16, 32), 42).to(dev))[0]
+    e = rel_rms(lo.detach().cpu(), T(g["pan_train_logits"]))
+    record("pan_train_logits_rel_rms", e)
+    assert e <= LOGIT_TOL
+
+
+def _la_pair(dev):
+    from bcp_b200.networks.net_factory import net_factory
+    from bcp_b200.optim import FusedSGD_EMA
+    model, ema = net_factory("VNet", 1, 2, "train"), net_factory("VNet", 1, 2, "train")
+    for p in ema.parameters():
+        p.detach_()
+    O.fill_state_dict_(model, 51)
+    ema.load_state_dict(model.state_dict())
+    model.train()
+    ema.train()
+    inject_dropout(model, seed=52)
+    inject_dropout(ema, seed=53)
+    opt = FusedSGD_EMA(model, ema, lr=0.01, momentum=0.9, weight_decay=1e-4, ema_alpha=0.99, ema_mode="params")
+    return model, ema, opt
+
+
+def _la_step_check(dev, g, nsteps, shape, sub, tag):
+    from bcp_b200.step import la_self_train_step
+    model, ema, opt = _la_pair(dev)
+    np.random.seed(int(g["box_seed"]))
+    for it in range(nsteps):
+        vol = O.synthetic_volume((8, 1) + shape, 60 + it).to(dev)
+        lab = O.synthetic_labels((8,) + shape, 70 + it).to(torch.uint8).to(dev)
+        r = la_self_train_step(model, ema, opt, vol, lab)
+        for k in ("loss", "loss_l", "loss_u"):
+            rel = abs(float(r[k]) - float(g[f"s{it}_{k}"])) / abs(float(g[f"s{it}_{k}"]))
+            record(f"{tag}_s{it}_{k}_rel_err", rel)
+            assert rel <= LOSS_TOL, (k, rel)
+        pa = float(r["plab"][:2].float().sum())
+        record(f"{tag}_s{it}_plab_a_sum_rel", abs(pa - float(g[f"s{it}_plab_a_sum"])) / max(1.0, float(g[f"s{it}_plab_a_sum"])))
+        e = rel_rms(r["out"][:2][..., ::sub, ::sub, ::sub].cpu(), T(g[f"s{it}_out_l"]))
+        record(f"{tag}_s{it}_out_l_rel_rms", e)
+        assert e <= 2 * LOGIT_TOL
+        # mixed inputs are bit-exact (digest of the fp32 mix)
+        from tests.golden.golden_common import tensor_digest
+        assert np.allclose(tensor_digest(r["mixed"][:2]), g[f"s{it}_mixl_digest"], rtol=1e-9, atol=0)
+        dm = digest_named(model.state_dict())
+        ref = g[f"s{it}_model_digest"]
+        big = ref[:, 1] > 1e-6
+        rel = np.abs(dm[big, 1] - ref[big, 1]) / ref[big, 1]
+        record(f"{tag}_s{it}_model_abs_sum_rel_max", float(rel.max()))
+        assert rel.max() <= 2e-2
+        de = digest_named(ema.state_dict())
+        refe = g[f"s{it}_ema_digest"]
+        bige = refe[:, 1] > 1e-6
+        assert (np.abs(de[bige, 1] - refe[bige, 1]) / refe[bige, 1]).max() <= 2e-2
+
+
+def test_la_step_small(dev):
+    _la_step_check(dev, load_golden("la_step_small"), 2, (48, 48, 48), 2, "la_small")
+
+
+def test_la_step_full(dev):
+    _la_step_check(dev, load_golden("la_step_full"), 1, (112, 112, 80), 4, "la_full")
+
+
+def test_la_pre_step(dev):
+    from bcp_b200.networks.net_factory import net_factory
+    from bcp_b200.optim import FusedSGD_EMA
+    from bcp_b200.step import la_pre_train_step
+    g = load_golden("la_pre_step")
+    model = net_factory("VNet", 1, 2, "train")
+    O.fill_state_dict_(model, 81)
+    model.train()
+    inject_dropout(model, seed=82)
+    opt = FusedSGD_EMA(model, None, lr=0.01, momentum=0.9, weight_decay=1e-4)
+    shape = (48, 48, 48)
+    np.random.seed(int(g["box_seed"]))
+    r = la_pre_train_step(model, opt, O.synthetic_volume((4, 1) + shape, 83).to(dev),
+                          O.synthetic_labels((4,) + shape, 84).to(torch.uint8).to(dev))
+    rel = abs(float(r["loss"]) - float(g["loss"])) / abs(float(g["loss"]))
+    record("la_pre_loss_rel_err", rel)
+    assert rel <= LOSS_TOL
+    assert rel_rms(r["out"].cpu(), T(g["out"])) <= 2 * LOGIT_TOL
+
+
+def test_acdc_step(dev):
+    from bcp_b200.networks.net_factory import BCP_net
+    from bcp_b200.optim import FusedSGD_EMA
+    from bcp_b200.step import acdc_self_train_step
+    g = load_golden("acdc_step")
+    model, ema = BCP_net(1, 4), BCP_net(1, 4, ema=True)
+    O.fill_state_dict_(model, 91)
+    ema.load_state_dict(model.state_dict())
+    model.train()
+    ema.train()
+    inject_dropout(model, seed=92)
+    inject_dropout(ema, seed=93)
+    opt = FusedSGD_EMA(model, ema, lr=0.01, momentum=0.9, weight_decay=1e-4, ema_alpha=0.99, ema_mode="state_dict")
+    np.random.seed(1337)
+    for it in range(2):
+        vol = O.synthetic_volume((8, 1, 64, 64), 100 + it, "rand").to(dev)
+        lab = O.synthetic_labels((8, 64, 64), 110 + it, n_classes=4).to(torch.uint8).to(dev)
+        r = acdc_self_train_step(model, ema, opt, vol, lab, labeled_bs=4)
+        for k in ("loss", "loss_dice", "loss_ce"):
+            rel = abs(float(r[k]) - float(g[f"s{it}_{k}"])) / abs(float(g[f"s{it}_{k}"]))
+            record(f"acdc_s{it}_{k}_rel_err", rel)
+            assert rel <= 2e-2, (k, rel)
+        mism = float((r["plab"][:2].cpu().float().numpy() != g[f"s{it}_plab_a"]).mean())
+        record(f"acdc_s{it}_plab_mismatch_frac", mism)
+        e = rel_rms(r["out"][2:].cpu(), T(g[f"s{it}_out_l"]))
+        record(f"acdc_s{it}_out_l_rel_rms", e)
+        assert e <= 2 * LOGIT_TOL
+    nbt = ema.state_dict()["encoder.in_conv.conv_conv.1.num_batches_tracked"]
+    assert int(nbt) == 0            # trunc(0.99*ema + 0.01*model) with ema counters at 0..: reference quirk preserved
+
+
+def test_pan_step(dev):
+    from bcp_b200.pancreas.Vnet import VNet
+    from bcp_b200.optim import FusedAdam_EMA
+    from bcp_b200.step import pan_self_train_step
+    g = load_golden("pan_step")
+    net, ema = VNet().to(dev), VNet().to(dev)
+    for p in ema.parameters():
+        p.detach_()
+    O.fill_state_dict_(net, 121)
+    ema.load_state_dict(net.state_dict())
+    net.train()
+    ema.train()
+    opt = FusedAdam_EMA(net, ema, lr=1e-3, ema_alpha=0.99)
+    np.random.seed(2020)
+    S = (96, 96, 96)
+    v = O.synthetic_volume((8, 1) + S, 130).to(dev)
+    l = O.synthetic_labels((8,) + S, 140).to(torch.uint8).to(dev)
+    r = pan_self_train_step(net, ema, opt, v[0:2], l[0:2], v[2:4], l[2:4], v[4:6], v[6:8])
+    rel = abs(float(r["loss"]) - float(g["s0_loss"])) / abs(float(g["s0_loss"]))
+    record("pan_loss_rel_err", rel)
+    assert rel <= LOSS_TOL
+    e = rel_rms(r["out"][:2][..., ::4, ::4, ::4].cpu(), T(g["s0_out_1"]))
+    record("pan_out_rel_rms", e)
+    assert e <= 2 * LOGIT_TOL

@@ -1,0 +1,104 @@
+"""CPU-side tests: the C-ABI library loads and exports every symbol include/bcp_b200.h declares, the drop-in
+modules keep the reference's state_dict keys / parameter order, host logic (box drawing, arenas, packs)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bcp_oracle as O
+
+
+def test_library_exports_every_declared_symbol():
+    from bcp_b200._native import LIB, parse_header
+    protos = parse_header()
+    assert len(protos) >= 40
+    lib = LIB.load()
+    for name in protos:
+        assert hasattr(lib, name), name
+    assert lib.bcp_abi_version() == 1
+    assert isinstance(lib.bcp_last_error(), bytes)
+
+
+def test_argument_errors_do_not_abort():
+    from bcp_b200._native import LIB
+    lib = LIB.load()
+    rc = lib.bcp_mask_mix(None, None, None, 1, 1, 4, 4, 4, 0, 0, 0, 1, 1, 1, None)
+    assert rc == -1 and b"null" in lib.bcp_last_error()
+    assert lib.bcp_mix_loss_ctx_floats(2, 2) == 6 + 2 * 2 * 2 * 3
+    assert lib.bcp_norm_chunks(10) == 1
+
+
+def test_product_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from bcp_b200 import ops
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.mask_mix(torch.zeros(1, 1, 4, 4, 4), torch.zeros(1, 1, 4, 4, 4), (0, 0, 0, 1, 1, 1))
+    from bcp_b200.networks.VNet import VNet
+    net = VNet(1, 2, 16, "batchnorm", False)
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 1, 16, 16, 16))
+
+
+def test_state_dict_keys_match_reference_layout():
+    from bcp_b200.networks.VNet import VNet
+    from bcp_b200.networks.unet import UNet_2d, UNet
+    from bcp_b200.pancreas.Vnet import VNet as PanVNet
+    pairs = [(VNet(1, 2, 16, "batchnorm", True), O.OracleVNet(1, 2, 16, "batchnorm", True), 259),
+             (UNet_2d(1, 4), O.OracleUNet2d(1, 4), 226), (UNet(1, 4), O.OracleUNet2d(1, 4, True), 226),
+             (PanVNet(), O.OraclePanVNet(), 60)]
+    for a, b, nkeys in pairs:
+        sa, sb = a.state_dict(), b.state_dict()
+        assert list(sa.keys()) == list(sb.keys()) and len(sa) == nkeys
+        assert [tuple(v.shape) for v in sa.values()] == [tuple(v.shape) for v in sb.values()]
+        assert [v.dtype for v in sa.values()] == [v.dtype for v in sb.values()]
+        assert [n for n, _ in a.named_parameters()] == [n for n, _ in b.named_parameters()]
+
+
+def test_shipped_checkpoints_load():
+    root = "/root/reference/models"
+    if not os.path.isdir(root):
+        pytest.skip("reference checkpoints not present on this box")
+    from bcp_b200.networks.VNet import VNet
+    from bcp_b200.networks.unet import UNet_2d
+    for f in ("LA/LA_5.pth", "LA/LA_10.pth"):
+        VNet(1, 2, 16, "batchnorm", True).load_state_dict(torch.load(os.path.join(root, f), map_location="cpu"))
+    for f in ("ACDC/ACDC_5.pth", "ACDC/ACDC_10.pth"):
+        UNet_2d(1, 4).load_state_dict(torch.load(os.path.join(root, f), map_location="cpu"))
+
+
+def test_flat_arena_and_packs():
+    from bcp_b200.networks.VNet import VNet
+    net = VNet(1, 2, 16, "batchnorm", True)
+    ref = {k: v.clone() for k, v in net.state_dict().items()}
+    rt = net.runtime
+    rt.flatten_()
+    assert rt.is_flat()
+    assert rt.n_train == 9448866 and rt.n_param == 9457318            # SURVEY.md section 6 parameter counts
+    for k, v in net.state_dict().items():
+        assert torch.equal(v, ref[k])
+    # load_state_dict keeps the views; a parameter that was re-allocated is detected
+    net.load_state_dict(ref)
+    assert rt.is_flat()
+    net.encoder.block_one.conv[0].weight.data = net.encoder.block_one.conv[0].weight.data.clone()
+    assert not rt.is_flat()
+    rt.flatten_()
+    g = rt.ensure_grad_arena()
+    assert g.numel() == rt.n_train
+    assert net.decoder.out_conv.weight.grad.data_ptr() >= g.data_ptr()
+    assert rt.njobs == 56       # 28 packed conv layers x (fwd, bwd); block_one and out_conv read fp32 weights
+
+
+def test_box_draw_order_matches_reference():
+    from bcp_b200.utils.BCP_utils import context_box
+    from bcp_b200.step import _acdc_box, _pan_box
+    np.random.seed(1337)
+    box = context_box((2, 1, 112, 112, 80), 2 / 3)
+    _, _, obox = O.context_mask_la(torch.zeros(2, 1, 112, 112, 80), 2 / 3, np.random.RandomState(1337))
+    assert box == obox
+    np.random.seed(7)
+    b2 = _acdc_box((6, 1, 256, 256))
+    assert b2 == O.generate_mask_acdc(torch.zeros(6, 1, 256, 256), np.random.RandomState(7))[2]
+    np.random.seed(9)
+    assert _pan_box(64) == O.generate_mask_pan(torch.zeros(2, 1, 96, 96, 96), 64, np.random.RandomState(9))[2]
