@@ -1,10 +1,710 @@
-// placeholder until the tcgen05 kernel lands
+// tcgen05 + TMA implicit-GEMM convolution for sm_100a: 3x3x3 / 1x3x3, stride 1, zero 'same' padding, on
+// channel-blocked bf16 activations (CB8).  Serves nn.Conv3d(k=3,p=1) / nn.Conv2d(k=3,p=1) forward
+// (networks/VNet.py:17, networks/unet.py:20,24) and, with the flipped operand pack, their data gradient.
+//
+// Design ("halo brick + shifted views"):
+//   * The output volume is cut into bricks of BX x BY x BZ voxels.  For a 16-channel chunk of the input, ONE
+//     5-D TMA box load brings the brick plus its one-voxel halo into shared memory (out-of-bounds = zero fill =
+//     the convolution's zero padding) as two 8-channel planes of [HX*HY*HZ rows][8 ch] = 16 bytes per row.
+//   * That is exactly the UMMA "K-major, no swizzle" canonical layout with 16-byte rows (SBO = 128 B between
+//     8-row groups, LBO = plane stride between the two K chunks).  A filter tap (dx,dy,dz) is therefore nothing
+//     but a start-address offset of ((dx*HY+dy)*HZ+dz)*16 bytes in the A descriptor: all 27 taps are MMAs over
+//     the SAME shared-memory bytes -- the halo is read from L2/HBM once, not 27 times.
+//   * Output rows are the linearised halo'd brick; rows that fall on halo positions are computed and dropped
+//     (efficiency BY*BZ/((BY+2)*(BZ+2)) per x-slab, chosen per layer by a small cost model).
+//   * M = 128 rows per MMA, N = Cout (16..256), K = 16; accumulators live in TMEM (MT tiles of N columns,
+//     double-buffered when 2*MT*N <= 512) and are drained by four epilogue warps with tcgen05.ld.
+//   * Warp roles: warp 0 = TMA producer (A bricks through a ring of 16-channel slots, per-tap weight tiles
+//     through a second ring via cp.async.bulk), warp 1 = MMA issuer (one elected lane), warps 2..5 = epilogue
+//     (TMEM -> registers -> +bias -> bf16 -> 16-byte coalesced stores).  All hand-offs are mbarriers.
+//   * Persistent grid: one CTA per SM, bricks assigned round-robin (static => deterministic).
 #include "common.cuh"
 #include "../../include/bcp_b200.h"
+#include <cuda.h>
+#include <mutex>
+
+namespace bcp {
+
+struct TcParams {
+  int N, X, Y, Z, Cin, Cout, kx;
+  int BX, BY, BZ, HX, HY, HZ;
+  int nbx, nby, nbz, nbricks;
+  int rows_h;          // HX*HY*HZ rows delivered by TMA per 8-channel plane
+  int MT;              // 128-row MMA tiles per brick
+  int nchunks;         // Cin / 16
+  int T;               // taps
+  int SA, SB;          // ring depths
+  int AS;              // accumulator stages in TMEM (1 or 2)
+  int tmem_cols;       // power of two >= AS*MT*Cout
+  unsigned slotA_bytes, stageB_bytes;
+  unsigned offA, offB, offBar;   // shared-memory carve-up (bytes from the 128B-aligned base)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (1ull << 46);
+}
+
+constexpr int TC_THREADS = 192;
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16* __restrict__ wpack, const float* __restrict__ bias,
+               uint4* __restrict__ out, const TcParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t a_base = sbase + p.offA, b_base = sbase + p.offB, bar_base = sbase + p.offBar;
+  // barrier slots (8 bytes each): full_a[SA], empty_a[SA], full_b[SB], empty_b[SB], tmem_full[AS], tmem_empty[AS]
+  const uint32_t full_a = bar_base, empty_a = full_a + 8 * p.SA, full_b = empty_a + 8 * p.SA, empty_b = full_b + 8 * p.SB;
+  const uint32_t tmem_full = empty_b + 8 * p.SB, tmem_empty = tmem_full + 8 * p.AS;
+  volatile uint32_t* tmem_slot = (volatile uint32_t*)(smem + p.offBar + 8 * (2 * p.SA + 2 * p.SB + 2 * p.AS));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p.SA; ++i) { mbar_init(full_a + 8 * i, 1); mbar_init(empty_a + 8 * i, 1); }
+    for (int i = 0; i < p.SB; ++i) { mbar_init(full_b + 8 * i, 1); mbar_init(empty_b + 8 * i, 1); }
+    for (int i = 0; i < p.AS; ++i) { mbar_init(tmem_full + 8 * i, 1); mbar_init(tmem_empty + 8 * i, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int Cib = p.Cin >> 3, Cob = p.Cout >> 3;
+  const int bricks_per_n = p.nbx * p.nby * p.nbz;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t ia = 0, ib = 0;                       // running item counters -> slot = i % S, phase = (i / S) & 1
+      const uint32_t a_bytes = (uint32_t)p.rows_h * 32u;
+      for (int brick = blockIdx.x; brick < p.nbricks; brick += gridDim.x) {
+        const int n = brick / bricks_per_n;
+        int r = brick - n * bricks_per_n;
+        const int bz = r % p.nbz; r /= p.nbz;
+        const int by = r % p.nby;
+        const int bx = r / p.nby;
+        const int x0 = bx * p.BX - (p.kx >> 1), y0 = by * p.BY - 1, z0 = bz * p.BZ - 1;
+        for (int c = 0; c < p.nchunks; ++c) {
+          const uint32_t sa = ia % p.SA, pa = (ia / p.SA) & 1;
+          mbar_wait(empty_a + 8 * sa, pa ^ 1);
+          mbar_expect_tx(full_a + 8 * sa, a_bytes);
+          tma_load_5d(a_base + sa * p.slotA_bytes, &tmap, full_a + 8 * sa, 0, z0, y0, x0, n * Cib + 2 * c);
+          ++ia;
+          for (int t = 0; t < p.T; ++t) {
+            const uint32_t sb = ib % p.SB, pb = (ib / p.SB) & 1;
+            mbar_wait(empty_b + 8 * sb, pb ^ 1);
+            mbar_expect_tx(full_b + 8 * sb, p.stageB_bytes);
+            const __nv_bfloat16* src = wpack + ((size_t)t * Cib + 2 * c) * (size_t)p.Cout * 8;
+            bulk_load(b_base + sb * p.stageB_bytes, src, p.stageB_bytes, full_b + 8 * sb);
+            ++ib;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Cout >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t lboA = (uint32_t)p.rows_h * 16u, lboB = (uint32_t)p.Cout * 16u;
+      uint32_t ia = 0, ib = 0, it = 0;
+      for (int brick = blockIdx.x; brick < p.nbricks; brick += gridDim.x, ++it) {
+        const uint32_t as = it % p.AS, ap = (it / p.AS) & 1;
+        mbar_wait(tmem_empty + 8 * as, ap ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + as * (uint32_t)(p.MT * p.Cout);
+        for (int c = 0; c < p.nchunks; ++c) {
+          const uint32_t sa = ia % p.SA, pa = (ia / p.SA) & 1;
+          mbar_wait(full_a + 8 * sa, pa);
+          tc_fence_after();
+          const uint32_t a_slot = a_base + sa * p.slotA_bytes;
+          for (int t = 0; t < p.T; ++t) {
+            const uint32_t sb = ib % p.SB, pb = (ib / p.SB) & 1;
+            mbar_wait(full_b + 8 * sb, pb);
+            tc_fence_after();
+            const int tz = t % 3, ty = (t / 3) % 3, tx = t / 9;
+            const uint32_t tapoff = (uint32_t)((tx * p.HY + ty) * p.HZ + tz) * 16u;
+            const uint64_t bdesc = make_desc(b_base + sb * p.stageB_bytes, lboB, 128u);
+            const uint32_t acc = (c | t) ? 1u : 0u;
+            for (int mt = 0; mt < p.MT; ++mt) {
+              const uint64_t adesc = make_desc(a_slot + tapoff + (uint32_t)mt * 2048u, lboA, 128u);
+              umma_bf16(d0 + (uint32_t)(mt * p.Cout), adesc, bdesc, idesc, acc);
+            }
+            umma_commit(empty_b + 8 * sb);
+            ++ib;
+          }
+          umma_commit(empty_a + 8 * sa);
+          ++ia;
+        }
+        umma_commit(tmem_full + 8 * as);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (TMEM lane quarter = warp % 4)
+    const int q = warp & 3;
+    uint32_t it = 0;
+    const long long S = (long long)p.X * p.Y * p.Z;
+    for (int brick = blockIdx.x; brick < p.nbricks; brick += gridDim.x, ++it) {
+      const int n = brick / bricks_per_n;
+      int r = brick - n * bricks_per_n;
+      const int bz = r % p.nbz; r /= p.nbz;
+      const int by = r % p.nby;
+      const int bx = r / p.nby;
+      const uint32_t as = it % p.AS, ap = (it / p.AS) & 1;
+      mbar_wait(tmem_full + 8 * as, ap);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + as * (uint32_t)(p.MT * p.Cout) + ((uint32_t)(q * 32) << 16);
+      for (int mt = 0; mt < p.MT; ++mt) {
+        const int L = mt * 128 + q * 32 + lane;
+        const int iz = L % p.HZ;
+        const int ry = L / p.HZ;
+        const int iy = ry % p.HY, ix = ry / p.HY;
+        const int x = bx * p.BX + ix, y = by * p.BY + iy, z = bz * p.BZ + iz;
+        const bool valid = (ix < p.BX) && (iy < p.BY) && (iz < p.BZ) && (x < p.X) && (y < p.Y) && (z < p.Z);
+        const long long sp = ((long long)x * p.Y + y) * p.Z + z;
+        for (int c16 = 0; c16 < p.Cout; c16 += 16) {
+          uint32_t v[16];
+          tmem_ld16(d0 + (uint32_t)(mt * p.Cout + c16), v);
+          tmem_ld_wait();
+          if (valid) {
+            float f[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v[k]) + (bias ? __ldg(bias + c16 + k) : 0.f);
+            uint4* dst = out + ((long long)n * Cob + (c16 >> 3)) * S + sp;
+            dst[0] = pack8(f);
+            dst[S] = pack8(f + 8);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + 8 * as);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// =========================================================================================================
+// weight gradient on tensor cores:  dW[t][co][ci] = sum_rows dy[row][co] * a[row + tap(t)][ci]
+//   D[M = co (128 lanes)][N = ci] += A[M][K] * B[N][K],  K = 16 voxels along z per MMA, both operands "MN-major,
+//   no swizzle" views of the same CB8 bricks the forward kernel uses (channels contiguous, voxels strided 16 B):
+//   A = dy brick (compact [BX][BY][ZP] rows, ZP = Z rounded up to 16, tail rows zero-filled by TMA OOB),
+//   B = halo'd a brick shifted by the tap offset -- again only a start-address change.
+//   Each CTA owns a group of taps (TP*Cin <= 512 TMEM columns) and one 128-channel half of Cout, streams its
+//   share of the bricks through a TMA ring and accumulates in TMEM across ALL of them; partial results go to a
+//   workspace [split][T][Cout][Cin] and are summed in fixed order by a finalize kernel (deterministic).
+// =========================================================================================================
+struct WgParams {
+  int N, X, Y, Z, Cin, Cout, kx;
+  int BX, BY, HX, HY, HZ, ZP;
+  int nbx, nby, nbricks;
+  int rows_a, rows_dy;
+  int T, TP, npass_t, MH, PL;     // taps, taps per pass, tap passes, M halves, dy planes loaded per brick
+  int S, splits, tmem_cols;
+  unsigned a_tx_bytes, dy_tx_bytes, a_alloc_bytes, dy_alloc_bytes, slot_bytes, offBar;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_dy,
+                     float* __restrict__ partial, const WgParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar_base = sbase + p.offBar;
+  const uint32_t full = bar_base, empty = full + 8 * p.S, tmem_full = empty + 8 * p.S;
+  volatile uint32_t* tmem_slot = (volatile uint32_t*)(smem + p.offBar + 8 * (2 * p.S + 1));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x, pass = blockIdx.y;
+  const int mh = pass % p.MH, tg = pass / p.MH;
+  const int t0 = tg * p.TP;
+  const int ntap = min(p.TP, p.T - t0);
+  const int Cib = p.Cin >> 3, Cob = p.Cout >> 3;
+
+  // zero the regions TMA never writes (unused dy planes, slack rows after the a planes): they feed MMAs
+  {
+    uint4 z = make_uint4(0, 0, 0, 0);
+    for (int s = 0; s < p.S; ++s) {
+      uint4* slot = reinterpret_cast<uint4*>(smem + (size_t)s * p.slot_bytes);
+      const unsigned a0 = p.a_tx_bytes / 16, a1 = p.a_alloc_bytes / 16;
+      for (unsigned i = a0 + threadIdx.x; i < a1; i += TC_THREADS) slot[i] = z;
+      const unsigned d0 = (p.a_alloc_bytes + p.dy_tx_bytes) / 16, d1 = (p.a_alloc_bytes + p.dy_alloc_bytes) / 16;
+      for (unsigned i = d0 + threadIdx.x; i < d1; i += TC_THREADS) slot[i] = z;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p.S; ++i) { mbar_init(full + 8 * i, 1); mbar_init(empty + 8 * i, 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dy) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int bricks_per_n = p.nbx * p.nby;
+  const bool has_work = split < p.nbricks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int brick = split; brick < p.nbricks; brick += p.splits, ++it) {
+        const int n = brick / bricks_per_n;
+        const int r = brick - n * bricks_per_n;
+        const int by = r % p.nby, bx = r / p.nby;
+        const uint32_t s = it % p.S, ph = (it / p.S) & 1;
+        mbar_wait(empty + 8 * s, ph ^ 1);
+        mbar_expect_tx(full + 8 * s, p.a_tx_bytes + p.dy_tx_bytes);
+        const uint32_t slot = sbase + s * p.slot_bytes;
+        tma_load_5d(slot, &map_a, full + 8 * s, 0, -1, by * p.BY - 1, bx * p.BX - (p.kx >> 1), n * Cib);
+        tma_load_5d(slot + p.a_alloc_bytes, &map_dy, full + 8 * s, 0, 0, by * p.BY, bx * p.BX, n * Cob + mh * 16);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && has_work) {
+      // M = 128, N = Cin, both operands MN-major (bits 15, 16)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.Cin >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t sboA = (uint32_t)p.rows_dy * 16u, sboB = (uint32_t)p.rows_a * 16u;
+      uint32_t it = 0;
+      uint32_t acc = 0;
+      for (int brick = split; brick < p.nbricks; brick += p.splits, ++it) {
+        const uint32_t s = it % p.S, ph = (it / p.S) & 1;
+        mbar_wait(full + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t a_slot = sbase + s * p.slot_bytes, dy_slot = a_slot + p.a_alloc_bytes;
+        for (int ix = 0; ix < p.BX; ++ix) {
+          for (int iy = 0; iy < p.BY; ++iy) {
+            for (int zc = 0; zc < p.ZP; zc += 16) {
+              const uint32_t dy_row = (uint32_t)((ix * p.BY + iy) * p.ZP + zc);
+              const uint64_t adesc = make_desc(dy_slot + dy_row * 16u, 128u, sboA);
+              for (int tl = 0; tl < ntap; ++tl) {
+                const int t = t0 + tl;
+                const int tz = t % 3, ty = (t / 3) % 3, tx = t / 9;
+                const uint32_t a_row = (uint32_t)(((ix + tx) * p.HY + iy + ty) * p.HZ + tz + zc);
+                const uint64_t bdesc = make_desc(a_slot + a_row * 16u, 128u, sboB);
+                umma_bf16(tmem_base + (uint32_t)(tl * p.Cin), adesc, bdesc, idesc, acc);
+              }
+              acc = 1;
+            }
+          }
+        }
+        umma_commit(empty + 8 * s);
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    const int q = warp & 3;
+    const int co = mh * 128 + q * 32 + lane;
+    if (has_work) {
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+    }
+    for (int tl = 0; tl < ntap; ++tl) {
+      const int t = t0 + tl;
+      float* dst = partial + (((size_t)split * p.T + t) * p.Cout + co) * p.Cin;
+      for (int c16 = 0; c16 < p.Cin; c16 += 16) {
+        uint32_t v[16];
+        if (has_work) {
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tl * p.Cin + c16), v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) v[k] = 0u;
+        }
+        if (co < p.Cout) {
+          float4* d4 = reinterpret_cast<float4*>(dst + c16);
+          d4[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+          d4[1] = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+          d4[2] = make_float4(__uint_as_float(v[8]), __uint_as_float(v[9]), __uint_as_float(v[10]), __uint_as_float(v[11]));
+          d4[3] = make_float4(__uint_as_float(v[12]), __uint_as_float(v[13]), __uint_as_float(v[14]), __uint_as_float(v[15]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// dw[co][ci][t] = sum_split partial[split][t][co][ci]   (fixed order)
+__global__ void conv_tc_wgrad_finalize_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int T,
+                                              int Cout, int Cin) {
+  const long long per = (long long)T * Cout * Cin;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= per) return;
+  const int ci = (int)(i % Cin);
+  const int co = (int)((i / Cin) % Cout);
+  const int t = (int)(i / ((long long)Cin * Cout));
+  float s = 0.f;
+  for (int k = 0; k < splits; ++k) s += partial[(long long)k * per + i];
+  dw[((long long)co * Cin + ci) * T + t] = s;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side: brick-shape selection, tensor map, launch
+// ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)f;
+  });
+  return fn;
+}
+
+constexpr unsigned SMEM_BUDGET = 220 * 1024;   // of the 227 KB a CTA may opt into
+
+static bool plan(TcParams& p, int nsm) {
+  const int T = p.kx * 9;
+  p.T = T;
+  p.nchunks = p.Cin / 16;
+  p.stageB_bytes = (unsigned)p.Cout * 32u;
+  double best = 1e300;
+  TcParams bestp = p;
+  bool found = false;
+  const double per_mma = (p.Cout / 2.0 > 32.0 + p.Cout / 4.0) ? p.Cout / 2.0 : 32.0 + p.Cout / 4.0;
+  int bz_opts[4];
+  int nz = 0;
+  for (int d = 1; d <= 8 && nz < 4; d *= 2) {
+    const int bz = (p.Z + d - 1) / d;
+    if (bz + 2 <= 256 && (nz == 0 || bz_opts[nz - 1] != bz)) bz_opts[nz++] = bz;
+  }
+  for (int zi = 0; zi < nz; ++zi) {
+    const int BZ = bz_opts[zi], HZ = BZ + 2;
+    for (int BY = 1; BY <= p.Y && BY + 2 <= 256; ++BY) {
+      const int HY = BY + 2;
+      const int bxmax = (p.kx == 1) ? 1 : p.X;
+      for (int BX = 1; BX <= bxmax; ++BX) {
+        const int HX = BX + p.kx - 1;
+        if (HX > 256) break;
+        const long long rows_h = (long long)HX * HY * HZ;
+        const long long lmax = ((long long)(BX - 1) * HY + (BY - 1)) * HZ + BZ;
+        const int MT = (int)((lmax + 127) / 128);
+        if (MT * p.Cout > 512) break;
+        const long long rows_alloc = (long long)MT * 128 + ((long long)(p.kx - 1) * HY + 2) * HZ + 2;
+        const long long slotA = ((rows_h + (rows_alloc > rows_h ? rows_alloc : rows_h)) * 16 + 127) / 128 * 128;
+        // ring depths: at least 2 A slots (3 preferred), 4 B stages
+        int SB = 4;
+        long long avail = (long long)SMEM_BUDGET - 1024 - (long long)SB * p.stageB_bytes;
+        int SA = (int)(avail / slotA);
+        if (SA < 2) break;
+        if (SA > 4) SA = 4;
+        const int nbx = (p.X + BX - 1) / BX, nby = (p.Y + BY - 1) / BY, nbz = (p.Z + BZ - 1) / BZ;
+        const long long nb = (long long)p.N * nbx * nby * nbz;
+        const long long waves = (nb + nsm - 1) / nsm;
+        const double mma_cyc = (double)MT * T * p.nchunks * per_mma;
+        const double load_cyc = (double)rows_h * p.Cin * 2.0 / 40.0 + (double)T * p.nchunks * p.stageB_bytes / 40.0;
+        const double epi_cyc = (double)MT * p.Cout * 12.0;
+        const int AS = (2 * MT * p.Cout <= 512) ? 2 : 1;
+        double brick = (mma_cyc > load_cyc ? mma_cyc : load_cyc) + (AS == 2 ? 0.0 : epi_cyc) + 1500.0;
+        const double cost = (double)waves * brick;
+        if (cost < best) {
+          best = cost;
+          found = true;
+          bestp = p;
+          bestp.BX = BX; bestp.BY = BY; bestp.BZ = BZ; bestp.HX = HX; bestp.HY = HY; bestp.HZ = HZ;
+          bestp.nbx = nbx; bestp.nby = nby; bestp.nbz = nbz; bestp.nbricks = (int)nb;
+          bestp.rows_h = (int)rows_h; bestp.MT = MT; bestp.SA = SA; bestp.SB = SB; bestp.AS = AS;
+          bestp.slotA_bytes = (unsigned)slotA;
+        }
+      }
+    }
+  }
+  if (!found) return false;
+  p = bestp;
+  int cols = 32;
+  while (cols < p.AS * p.MT * p.Cout) cols *= 2;
+  p.tmem_cols = cols;
+  p.offA = 0;
+  p.offB = p.SA * p.slotA_bytes;
+  p.offBar = p.offB + p.SB * p.stageB_bytes;
+  return true;
+}
+
+struct PlanKey {
+  int v[7];
+  bool operator==(const PlanKey& o) const { for (int i = 0; i < 7; ++i) if (v[i] != o.v[i]) return false; return true; }
+};
+// immutable plans memoised per shape (pure function of the key; guarded by a mutex)
+static bool plan_cached(TcParams& p, int nsm) {
+  static std::mutex mu;
+  static PlanKey keys[256];
+  static TcParams vals[256];
+  static int count = 0;
+  const PlanKey k = {{p.N, p.X, p.Y, p.Z, p.Cin, p.Cout, p.kx}};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    for (int i = 0; i < count; ++i) if (keys[i] == k) { p = vals[i]; return true; }
+  }
+  if (!plan(p, nsm)) return false;
+  std::lock_guard<std::mutex> g(mu);
+  if (count < 256) { keys[count] = k; vals[count] = p; ++count; }
+  return true;
+}
+
+static bool shape_ok(int cin, int cout, const int* dims, const int* kernel) {
+  if (cin % 16 || cout % 16 || cin < 16 || cout < 16 || cout > 256) return false;
+  if (!((kernel[0] == 3 || kernel[0] == 1) && kernel[1] == 3 && kernel[2] == 3)) return false;
+  if (kernel[0] == 1 && dims[0] != 1) return false;
+  if (dims[0] < 1 || dims[1] < 1 || dims[2] < 1) return false;
+  return true;
+}
+
+
+static bool wg_shape_ok(int cin, int cout, const int* dims, const int* kernel) {
+  if (!shape_ok(cin, cout, dims, kernel)) return false;
+  if (dims[2] + 2 > 256) return false;                 // one z-line (+halo) must fit a TMA box
+  return true;
+}
+
+static bool wg_plan(WgParams& p, int nsm) {
+  p.T = p.kx * 9;
+  p.TP = 512 / p.Cin;
+  if (p.TP > p.T) p.TP = p.T;
+  if (p.TP < 1) return false;
+  p.npass_t = (p.T + p.TP - 1) / p.TP;
+  p.MH = (p.Cout > 128) ? 2 : 1;
+  p.PL = (p.Cout / 8 < 16) ? p.Cout / 8 : 16;
+  p.HZ = p.Z + 2;
+  p.ZP = (p.Z + 15) / 16 * 16;
+  const int npass = p.npass_t * p.MH;
+  int cols = 32;
+  while (cols < p.TP * p.Cin) cols *= 2;
+  p.tmem_cols = cols;
+  double best = 1e300;
+  bool found = false;
+  WgParams bp = p;
+  const int Cib = p.Cin / 8;
+  const int bxmax = (p.kx == 1) ? 1 : p.X;
+  for (int BY = 1; BY <= p.Y && BY + 2 <= 256; ++BY) {
+    for (int BX = 1; BX <= bxmax; ++BX) {
+      const int HX = BX + p.kx - 1, HY = BY + 2;
+      if (HX > 256) break;
+      const long long rows_a = (long long)HX * HY * p.HZ, rows_dy = (long long)BX * BY * p.ZP;
+      if (rows_a >= 16384 || rows_dy >= 16384) break;
+      const long long a_tx = rows_a * 16 * Cib, dy_tx = rows_dy * 16 * p.PL;
+      const long long a_alloc = (a_tx + 256 + 127) / 128 * 128, dy_alloc = (rows_dy * 16 * 16 + 127) / 128 * 128;
+      const long long slot = a_alloc + dy_alloc;
+      int S = (int)((SMEM_BUDGET - 1024) / slot);
+      if (S < 2) break;
+      if (S > 4) S = 4;
+      const int nbx = (p.X + BX - 1) / BX, nby = (p.Y + BY - 1) / BY;
+      const long long nb = (long long)p.N * nbx * nby;
+      long long splits = nsm / npass;
+      if (splits < 1) splits = 1;
+      if (splits > nb) splits = nb;
+      const long long per_cta = (nb + splits - 1) / splits;
+      const double per_mma = (p.Cin / 2.0 > 32.0 + p.Cin / 4.0) ? p.Cin / 2.0 : 32.0 + p.Cin / 4.0;
+      const double mma_cyc = (double)BX * BY * (p.ZP / 16) * p.TP * per_mma;
+      const double load_cyc = (double)(a_tx + dy_tx) / 40.0;
+      const double cost = (double)per_cta * ((mma_cyc > load_cyc ? mma_cyc : load_cyc) + 1200.0);
+      if (cost < best) {
+        best = cost; found = true; bp = p;
+        bp.BX = BX; bp.BY = BY; bp.HX = HX; bp.HY = HY; bp.nbx = nbx; bp.nby = nby; bp.nbricks = (int)nb;
+        bp.rows_a = (int)rows_a; bp.rows_dy = (int)rows_dy; bp.S = S; bp.splits = (int)splits;
+        bp.a_tx_bytes = (unsigned)a_tx; bp.dy_tx_bytes = (unsigned)dy_tx; bp.a_alloc_bytes = (unsigned)a_alloc;
+        bp.dy_alloc_bytes = (unsigned)dy_alloc; bp.slot_bytes = (unsigned)slot;
+      }
+    }
+  }
+  if (!found) return false;
+  p = bp;
+  p.offBar = p.S * p.slot_bytes;
+  return true;
+}
+
+}  // namespace bcp
+
+using namespace bcp;
+
 extern "C" {
-int bcp_conv_tc_supported(int, int, const int*, const int*) { return 0; }
-int bcp_conv_tc_fwd(const void*, const void*, const float*, void*, int, int, int, const int*, const int*, cudaStream_t) {
-  bcp::set_last_error("conv_tc_fwd: not built");
-  return BCP_ERR_UNSUPPORTED;
+
+int bcp_conv_tc_supported(int cin, int cout, const int* dims, const int* kernel) {
+  if (!dims || !kernel) return 0;
+  if (!shape_ok(cin, cout, dims, kernel)) return 0;
+  return get_encode() != nullptr ? 1 : 0;
 }
+
+// writes the chosen plan for inspection/tests: {BX,BY,BZ,MT,SA,SB,AS,nbricks,tmem_cols,smem_bytes}
+int bcp_conv_tc_plan(int n, int cin, int cout, const int* dims, const int* kernel, int* plan10) {
+  BCP_REQUIRE(dims && kernel && plan10, "conv_tc_plan: null pointer");
+  if (!shape_ok(cin, cout, dims, kernel)) { set_last_error("conv_tc_plan: unsupported shape"); return BCP_ERR_UNSUPPORTED; }
+  TcParams p{};
+  p.N = n; p.X = dims[0]; p.Y = dims[1]; p.Z = dims[2]; p.Cin = cin; p.Cout = cout; p.kx = kernel[0];
+  if (!plan(p, sm_count())) { set_last_error("conv_tc_plan: no brick shape fits"); return BCP_ERR_UNSUPPORTED; }
+  const int v[10] = {p.BX, p.BY, p.BZ, p.MT, p.SA, p.SB, p.AS, p.nbricks, p.tmem_cols, (int)(p.offBar + 8 * (2 * p.SA + 2 * p.SB + 2 * p.AS) + 16 + 128)};
+  for (int i = 0; i < 10; ++i) plan10[i] = v[i];
+  return BCP_OK;
 }
+
+int bcp_conv_tc_fwd(const void* in, const void* wpack, const float* bias, void* out, int n, int cin, int cout,
+                    const int* dims, const int* kernel, cudaStream_t stream) {
+  BCP_REQUIRE(in && wpack && out && dims && kernel, "conv_tc_fwd: null pointer");
+  if (!shape_ok(cin, cout, dims, kernel)) { set_last_error("conv_tc_fwd: unsupported shape cin=%d cout=%d", cin, cout); return BCP_ERR_UNSUPPORTED; }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_last_error("conv_tc_fwd: cuTensorMapEncodeTiled unavailable"); return BCP_ERR_CUDA; }
+  TcParams p{};
+  p.N = n; p.X = dims[0]; p.Y = dims[1]; p.Z = dims[2]; p.Cin = cin; p.Cout = cout; p.kx = kernel[0];
+  const int nsm = sm_count();
+  if (!plan_cached(p, nsm)) { set_last_error("conv_tc_fwd: no brick shape fits shared memory / TMEM"); return BCP_ERR_UNSUPPORTED; }
+
+  CUtensorMap tmap;
+  const cuuint64_t gdim[5] = {8, (cuuint64_t)p.Z, (cuuint64_t)p.Y, (cuuint64_t)p.X, (cuuint64_t)n * (cin / 8)};
+  const cuuint64_t gstr[4] = {16, (cuuint64_t)p.Z * 16, (cuuint64_t)p.Z * p.Y * 16, (cuuint64_t)p.Z * p.Y * p.X * 16};
+  const cuuint32_t box[5] = {8, (cuuint32_t)p.HZ, (cuuint32_t)p.HY, (cuuint32_t)p.HX, 2};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(in), gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) { set_last_error("conv_tc_fwd: cuTensorMapEncodeTiled failed (%d)", (int)cr); return BCP_ERR_CUDA; }
+
+  const size_t smem = (size_t)p.offBar + 8 * (2 * p.SA + 2 * p.SB + 2 * p.AS) + 16 + 128;
+  static std::once_flag attr_once;
+  std::call_once(attr_once, [] { cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  const int grid = p.nbricks < nsm ? p.nbricks : nsm;
+  conv_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(tmap, (const __nv_bfloat16*)wpack, bias, (uint4*)out, p);
+  return check_launch("conv_tc_fwd");
+}
+
+int bcp_conv_tc_wgrad_supported(int cin, int cout, const int* dims, const int* kernel) {
+  if (!dims || !kernel) return 0;
+  if (!wg_shape_ok(cin, cout, dims, kernel)) return 0;
+  return get_encode() != nullptr ? 1 : 0;
+}
+
+static int wg_setup(WgParams& p, int n, int cin, int cout, const int* dims, const int* kernel) {
+  p = WgParams{};
+  p.N = n; p.X = dims[0]; p.Y = dims[1]; p.Z = dims[2]; p.Cin = cin; p.Cout = cout; p.kx = kernel[0];
+  return wg_plan(p, sm_count()) ? 0 : -1;
+}
+
+long long bcp_conv_tc_wgrad_workspace_floats(int n, int cin, int cout, const int* dims, const int* kernel) {
+  if (!dims || !kernel || !wg_shape_ok(cin, cout, dims, kernel)) return 0;
+  WgParams p;
+  if (wg_setup(p, n, cin, cout, dims, kernel) != 0) return 0;
+  return (long long)p.splits * p.T * cout * cin;
+}
+
+// dw[cout][cin][T] fp32; `a` = layer input (cin channels), `dy` = output gradient (cout channels), both CB8 at `dims`
+int bcp_conv_tc_wgrad(const void* a, const void* dy, float* dw, float* workspace, int n, int cin, int cout,
+                      const int* dims, const int* kernel, cudaStream_t stream) {
+  BCP_REQUIRE(a && dy && dw && workspace && dims && kernel, "conv_tc_wgrad: null pointer");
+  if (!wg_shape_ok(cin, cout, dims, kernel)) { set_last_error("conv_tc_wgrad: unsupported shape"); return BCP_ERR_UNSUPPORTED; }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_last_error("conv_tc_wgrad: cuTensorMapEncodeTiled unavailable"); return BCP_ERR_CUDA; }
+  WgParams p;
+  if (wg_setup(p, n, cin, cout, dims, kernel) != 0) { set_last_error("conv_tc_wgrad: no brick shape fits"); return BCP_ERR_UNSUPPORTED; }
+  CUtensorMap map_a, map_dy;
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const cuuint64_t gstr[4] = {16, (cuuint64_t)p.Z * 16, (cuuint64_t)p.Z * p.Y * 16, (cuuint64_t)p.Z * p.Y * p.X * 16};
+  {
+    const cuuint64_t gdim[5] = {8, (cuuint64_t)p.Z, (cuuint64_t)p.Y, (cuuint64_t)p.X, (cuuint64_t)n * (cin / 8)};
+    const cuuint32_t box[5] = {8, (cuuint32_t)p.HZ, (cuuint32_t)p.HY, (cuuint32_t)p.HX, (cuuint32_t)(cin / 8)};
+    const CUresult cr = enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(a), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { set_last_error("conv_tc_wgrad: tensor map (a) failed (%d)", (int)cr); return BCP_ERR_CUDA; }
+  }
+  {
+    const cuuint64_t gdim[5] = {8, (cuuint64_t)p.Z, (cuuint64_t)p.Y, (cuuint64_t)p.X, (cuuint64_t)n * (cout / 8)};
+    const cuuint32_t box[5] = {8, (cuuint32_t)p.ZP, (cuuint32_t)p.BY, (cuuint32_t)p.BX, (cuuint32_t)p.PL};
+    const CUresult cr = enc(&map_dy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(dy), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { set_last_error("conv_tc_wgrad: tensor map (dy) failed (%d)", (int)cr); return BCP_ERR_CUDA; }
+  }
+  const size_t smem = (size_t)p.offBar + 8 * (2 * p.S + 1) + 16 + 128;
+  static std::once_flag attr_once;
+  std::call_once(attr_once, [] { cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  dim3 grid(p.splits, p.npass_t * p.MH);
+  conv_tc_wgrad_kernel<<<grid, TC_THREADS, smem, stream>>>(map_a, map_dy, workspace, p);
+  const long long per = (long long)p.T * cout * cin;
+  conv_tc_wgrad_finalize_kernel<<<(unsigned)((per + 255) / 256), 256, 0, stream>>>(workspace, dw, p.splits, p.T, cout, cin);
+  return check_launch("conv_tc_wgrad");
+}
+
+}  // extern "C"

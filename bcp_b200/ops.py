@@ -7,12 +7,17 @@ arithmetic op on the path is a kernel of libbcp_b200.so, and a missing library i
 """
 from __future__ import annotations
 
+import os
+
 import torch
 from torch.autograd import Function
 
 from ._native import LIB, i3, i6, ptr, stream
 
 BF16 = torch.bfloat16
+# debugging switches (kernel selection only -- both settings run hand-written sm_100a kernels)
+_TC_FWD = os.environ.get("BCP_DISABLE_TC", "0") != "1"
+_TC_WGRAD = _TC_FWD and os.environ.get("BCP_DISABLE_TC_WGRAD", "0") != "1"
 
 
 def _require_cuda(t: torch.Tensor, what: str):
@@ -98,7 +103,7 @@ def _conv_same(a, wpack, bias, cout, kernel, allow_tc=True):
     n, cin, x, y, z = act_dims(a)
     out = torch.empty(cb8_shape(n, cout, x, y, z), dtype=BF16, device=a.device)
     dims, k = i3(x, y, z), i3(*kernel)
-    if allow_tc and LIB.query("bcp_conv_tc_supported", cin, cout, dims, k):
+    if allow_tc and _TC_FWD and LIB.query("bcp_conv_tc_supported", cin, cout, dims, k):
         LIB.call("bcp_conv_tc_fwd", ptr(a), ptr(wpack), ptr(bias), ptr(out), n, cin, cout, dims, k, stream())
     else:
         LIB.call("bcp_conv_direct_fwd", ptr(a), ptr(wpack), ptr(bias), ptr(out), n, cin, cout, dims, k,
@@ -106,8 +111,14 @@ def _conv_same(a, wpack, bias, cout, kernel, allow_tc=True):
     return out
 
 
-def _wgrad(inp, outgrad, cin, cout, in_dims, kernel, stride, pad, wshape):
+def _wgrad(inp, outgrad, cin, cout, in_dims, kernel, stride, pad, wshape, allow_tc=True):
     n = inp.shape[0]
+    same = tuple(stride) == (1, 1, 1) and tuple(pad) == tuple(k // 2 for k in kernel)
+    if allow_tc and _TC_WGRAD and same and LIB.query("bcp_conv_tc_wgrad_supported", cin, cout, i3(*in_dims), i3(*kernel)):
+        ws = _f32(LIB.query("bcp_conv_tc_wgrad_workspace_floats", n, cin, cout, i3(*in_dims), i3(*kernel)), inp.device)
+        dw = torch.empty(wshape, dtype=torch.float32, device=inp.device)
+        LIB.call("bcp_conv_tc_wgrad", ptr(inp), ptr(outgrad), ptr(dw), ptr(ws), n, cin, cout, i3(*in_dims), i3(*kernel), stream())
+        return dw
     od = [(in_dims[i] + 2 * pad[i] - kernel[i]) // stride[i] + 1 for i in range(3)]
     ws = _f32(LIB.query("bcp_conv_wgrad_workspace_floats", n, cin, cout, i3(*od), i3(*kernel)), inp.device)
     dw = torch.empty(wshape, dtype=torch.float32, device=inp.device)

@@ -145,8 +145,16 @@ int bcp_head_wgrad(const void* in, const float* dlogits, float* dw, float* db, f
 /* tcgen05 implicit-GEMM convolution, stride 1, 'same' zero padding, kernel (kx,3,3) with kx in {1,3}.
  * wpack is the kind-0 (forward) or kind-1 (dgrad) pack.  Returns -2 for shapes it does not take. */
 int bcp_conv_tc_supported(int cin, int cout, const int* dims, const int* kernel);
+/* chosen tiling for inspection: {BX,BY,BZ,MT,SA,SB,AS,nbricks,tmem_cols,smem_bytes} */
+int bcp_conv_tc_plan(int n, int cin, int cout, const int* dims, const int* kernel, int* plan10);
 int bcp_conv_tc_fwd(const void* in, const void* wpack, const float* bias, void* out, int n, int cin, int cout,
                     const int* dims, const int* kernel, cudaStream_t stream);
+
+/* tcgen05 weight gradient for the same family: dw[cout][cin][taps] fp32 (PyTorch layout), deterministic. */
+int bcp_conv_tc_wgrad_supported(int cin, int cout, const int* dims, const int* kernel);
+long long bcp_conv_tc_wgrad_workspace_floats(int n, int cin, int cout, const int* dims, const int* kernel);
+int bcp_conv_tc_wgrad(const void* a, const void* dy, float* dw, float* workspace, int n, int cin, int cout,
+                      const int* dims, const int* kernel, cudaStream_t stream);
 
 /* ---- resampling (networks/unet.py:37 MaxPool2d(2); :50 Upsample(bilinear, align_corners=True);
  * networks/VNet.py:249 MaxPool3d(3, stride=2)).  planes = n * ceil(c/8) * X. */

@@ -1,0 +1,103 @@
+"""Diagnostic harness for the tcgen05 conv kernel: compares against the CUDA-core kernel and torch on structured
+inputs and prints where (which rows / channels / taps) they differ.  Run under `timeout` on the GPU box."""
+import ctypes
+import sys
+import os
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+from bcp_b200 import ops
+from bcp_b200._native import LIB, i3
+from tests.util import cb8_from_planar, planar_from_cb8, rel_rms
+from tests.test_gpu_primitives import _packs
+
+dev = torch.device("cuda:0")
+
+
+def plan(n, cin, cout, dims, kernel):
+    out = (ctypes.c_int * 10)()
+    rc = LIB.query("bcp_conv_tc_plan", n, cin, cout, i3(*dims), i3(*kernel), out)
+    return rc, list(out)
+
+
+def run(n, cin, cout, dims, kernel, mode="rand", verbose=True):
+    torch.manual_seed(0)
+    if mode == "ones":
+        x = torch.ones(n, cin, *dims, device=dev)
+        w = torch.zeros(cout, cin, *kernel, device=dev)
+        w[:, :, kernel[0] // 2, 1, 1] = 1.0 / cin
+    elif mode == "tap":
+        x = torch.randn(n, cin, *dims, device=dev).to(torch.bfloat16).float()
+        w = torch.zeros(cout, cin, *kernel, device=dev)
+        for co in range(cout):
+            w[co, co % cin, (co // 9) % kernel[0], (co // 3) % 3, co % 3] = 1.0
+    else:
+        x = torch.randn(n, cin, *dims, device=dev).to(torch.bfloat16).float()
+        w = (torch.randn(cout, cin, *kernel, device=dev) / np.sqrt(cin * np.prod(kernel))).to(torch.bfloat16).float()
+    b = 0.1 * torch.randn(cout, device=dev)
+    pack = _packs(ops, dev, w, (0, 1))
+    a = cb8_from_planar(x)
+    rc, pl = plan(n, cin, cout, dims, kernel)
+    ref = F.conv3d(x, w, b, padding=tuple(k // 2 for k in kernel))
+    y_d = planar_from_cb8(ops._conv_same(a, pack.fwd, b, cout, kernel, allow_tc=False), cout)
+    y_t = planar_from_cb8(ops._conv_same(a, pack.fwd, b, cout, kernel, allow_tc=True), cout)
+    torch.cuda.synchronize()
+    e_d, e_t, e_td = rel_rms(y_d, ref), rel_rms(y_t, ref), rel_rms(y_t, y_d)
+    print(f"[{mode}] n={n} cin={cin} cout={cout} dims={dims} k={kernel} plan(BX,BY,BZ,MT,SA,SB,AS,nb,cols,smem)={pl} "
+          f"direct_vs_torch={e_d:.2e} tc_vs_torch={e_t:.2e} tc_vs_direct={e_td:.2e}", flush=True)
+    if e_t > 1e-2 and verbose:
+        bad = (y_t - ref).abs() > 0.05 * ref.abs().max()
+        print("   bad fraction", float(bad.float().mean()))
+        print("   bad by channel", bad.float().mean(dim=(0, 2, 3, 4)).cpu().numpy().round(2))
+        print("   bad by x", bad.float().mean(dim=(0, 1, 3, 4)).cpu().numpy().round(2))
+        print("   bad by y", bad.float().mean(dim=(0, 1, 2, 4)).cpu().numpy().round(2))
+        print("   bad by z", bad.float().mean(dim=(0, 1, 2, 3)).cpu().numpy().round(2))
+        print("   sample got", y_t[0, :4, 0, 0, :6].cpu().numpy().round(3))
+        print("   sample ref", ref[0, :4, 0, 0, :6].cpu().numpy().round(3))
+    return e_t
+
+
+def run_wgrad(n, cin, cout, dims, kernel):
+    torch.manual_seed(1)
+    x = torch.randn(n, cin, *dims, device=dev).to(torch.bfloat16).float()
+    g = torch.randn(n, cout, *dims, device=dev).to(torch.bfloat16).float()
+    a, dy = cb8_from_planar(x), cb8_from_planar(g)
+    w = torch.zeros(cout, cin, *kernel, device=dev, requires_grad=True)
+    F.conv3d(x, w, None, padding=tuple(k // 2 for k in kernel)).backward(g)
+    pad = tuple(k // 2 for k in kernel)
+    d_d = ops._wgrad(a, dy, cin, cout, dims, kernel, (1, 1, 1), pad, w.shape, allow_tc=False)
+    d_t = ops._wgrad(a, dy, cin, cout, dims, kernel, (1, 1, 1), pad, w.shape, allow_tc=True)
+    torch.cuda.synchronize()
+    e_d, e_t = rel_rms(d_d, w.grad), rel_rms(d_t, w.grad)
+    print(f"[wgrad] n={n} cin={cin} cout={cout} dims={dims} k={kernel} direct_vs_torch={e_d:.2e} tc_vs_torch={e_t:.2e}", flush=True)
+    if e_t > 1e-2:
+        bad = (d_t - w.grad).abs() > 0.05 * w.grad.abs().max()
+        print("   bad frac", float(bad.float().mean()), "by tap", bad.float().mean(dim=(0, 1)).flatten().cpu().numpy().round(2))
+        print("   by co", bad.float().mean(dim=(1, 2, 3, 4)).cpu().numpy().round(2)[:32])
+        print("   by ci", bad.float().mean(dim=(0, 2, 3, 4)).cpu().numpy().round(2)[:32])
+        print("   got", d_t[0, 0].flatten()[:9].cpu().numpy().round(2), "ref", w.grad[0, 0].flatten()[:9].cpu().numpy().round(2))
+    return e_t
+
+
+if __name__ == "__main__":
+    print(torch.cuda.get_device_name(0), flush=True)
+    worst = 0.0
+    worst = max(worst, run(1, 16, 16, (4, 6, 8), (3, 3, 3), "ones"))
+    worst = max(worst, run(1, 16, 16, (4, 6, 8), (3, 3, 3), "tap"))
+    for cfg in [(1, 16, 16, (4, 6, 8), (3, 3, 3)), (2, 16, 16, (8, 12, 20), (3, 3, 3)), (2, 32, 32, (6, 10, 12), (3, 3, 3)),
+                (2, 64, 64, (28, 28, 20), (3, 3, 3)), (2, 128, 128, (14, 14, 10), (3, 3, 3)), (2, 256, 256, (7, 7, 5), (3, 3, 3)),
+                (2, 32, 16, (9, 7, 11), (3, 3, 3)), (2, 16, 64, (5, 5, 5), (3, 3, 3)), (1, 16, 16, (112, 112, 80), (3, 3, 3)),
+                (2, 32, 32, (56, 56, 40), (3, 3, 3)), (3, 16, 16, (1, 64, 64), (1, 3, 3)), (2, 32, 64, (1, 32, 32), (1, 3, 3)),
+                (6, 16, 16, (1, 256, 256), (1, 3, 3)), (2, 256, 128, (1, 16, 16), (1, 3, 3))]:
+        worst = max(worst, run(*cfg))
+    print("WORST tc_vs_torch", worst, flush=True)
+    if "--wgrad" in sys.argv:
+        ww = 0.0
+        for cfg in [(1, 16, 16, (4, 6, 8), (3, 3, 3)), (2, 16, 16, (8, 12, 20), (3, 3, 3)), (2, 32, 32, (6, 10, 12), (3, 3, 3)),
+                    (2, 64, 64, (28, 28, 20), (3, 3, 3)), (2, 128, 128, (14, 14, 10), (3, 3, 3)), (2, 256, 256, (7, 7, 5), (3, 3, 3)),
+                    (2, 32, 16, (9, 7, 11), (3, 3, 3)), (2, 16, 64, (5, 5, 5), (3, 3, 3)), (1, 16, 16, (112, 112, 80), (3, 3, 3)),
+                    (3, 16, 16, (1, 64, 64), (1, 3, 3)), (2, 256, 128, (1, 16, 16), (1, 3, 3))]:
+            ww = max(ww, run_wgrad(*cfg))
+        print("WORST wgrad tc_vs_torch", ww, flush=True)
