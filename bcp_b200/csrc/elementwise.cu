@@ -45,6 +45,13 @@ __global__ void label_mix_kernel(const unsigned char* __restrict__ a, const unsi
 // fp32 softmax is replicated step by step (max, expf(x-max), sum, IEEE divide) because
 // "p1 >= 0.5" is not "x1 >= x0" once exp rounds to 1.0f.
 // ------------------------------------------------------------------------------------------
+// exp(d) for d <= 0 rounded like a <=1-ulp libm (the reference's CPU path) where it matters: for |d| < 2^-10 the
+// result is 1 + d + d^2/2 to well below half an ulp, so evaluate that directly; elsewhere p is far from any tie.
+__device__ __forceinline__ float exp_near_one(float d) {
+  if (fabsf(d) < 9.765625e-4f) return __fadd_rn(1.0f, __fadd_rn(d, __fmul_rn(__fmul_rn(d, d), 0.5f)));
+  return expf(d);
+}
+
 template <int C>
 __global__ void pseudo_label_kernel(const float* __restrict__ logits, unsigned char* __restrict__ out,
                                     int N, long long V, int mode, float thr) {
@@ -59,7 +66,7 @@ __global__ void pseudo_label_kernel(const float* __restrict__ logits, unsigned c
     for (int c = 0; c < C; ++c) { x[c] = p[(long long)c * V]; m = fmaxf(m, x[c]); }
     float s = 0.f;
 #pragma unroll
-    for (int c = 0; c < C; ++c) { x[c] = expf(x[c] - m); s += x[c]; }
+    for (int c = 0; c < C; ++c) { x[c] = exp_near_one(x[c] - m); s += x[c]; }
     if (mode == 0) {
       out[i] = (__fdiv_rn(x[1], s) >= thr) ? 1 : 0;
     } else {
