@@ -13,32 +13,28 @@
 
 namespace bcp {
 
-__device__ __forceinline__ int uf_find(int* L, int i) {
-  int r = i;
-  while (true) {
-    const int p = L[r];
-    if (p == r) break;
-    r = p;
+// Union-find in the style of ECL-CC (Jaiganesh & Burtscher): find with intermediate pointer jumping, hooking by
+// atomicCAS on ROOTS only (larger root under the smaller), so parent links always decrease and are never lost.
+__device__ __forceinline__ int uf_find(volatile int* L, int v) {
+  int curr = L[v];
+  if (curr != v) {
+    int prev = v, next;
+    while (curr > (next = L[curr])) {
+      L[prev] = next;          // pointer jumping; racy by design, values only move towards the root
+      prev = curr;
+      curr = next;
+    }
   }
-  // path compression (benign race: labels only decrease towards the root)
-  while (true) {
-    const int p = L[i];
-    if (p == r || p == i) break;
-    L[i] = r;
-    i = p;
-  }
-  return r;
+  return curr;
 }
 
 __device__ __forceinline__ void uf_union(int* L, int a, int b) {
-  while (true) {
-    a = uf_find(L, a);
-    b = uf_find(L, b);
-    if (a == b) return;
-    if (a < b) { const int t = a; a = b; b = t; }   // a > b: hook the larger root under the smaller
-    const int old = atomicMin(&L[a], b);
-    if (old == a) return;
-    a = old;
+  int ra = uf_find(L, a), rb = uf_find(L, b);
+  while (ra != rb) {
+    if (ra < rb) { const int t = ra; ra = rb; rb = t; }       // ra > rb: hook ra under rb if ra is still a root
+    const int seen = atomicCAS(&L[ra], ra, rb);
+    if (seen == ra) return;
+    ra = seen;                                                // somebody hooked ra meanwhile: continue from its parent
   }
 }
 

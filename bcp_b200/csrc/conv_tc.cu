@@ -255,6 +255,183 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16* __
 }
 
 // =========================================================================================================
+// stride-2 family on tensor cores ("tap GEMM"): 2x2x2 stride-2 conv (gather) and transposed conv (scatter).
+//   rows = voxels of the HALF-resolution grid, compact per brick (no halo, no dropped rows except tile padding)
+//   gather : out_half[o][co]        = sum_t sum_ci in_full[2o+t][ci] * W[t][ci][co]
+//            A item = (16-ch chunk, tap): ONE TMA box load with elementStrides (1,2,2,2,1) starting at tap t picks
+//            exactly the 2o+t voxels -> every input byte is read once; B item = W[t] chunk (kind-0 pack)
+//   scatter: out_full[2i+t][co]     = sum_ci in_half[i][ci] * W[ci][t][co]
+//            one GEMM with N = taps*Cout, cut into pieces of TPc taps; A item = 16-ch chunk; B item = 2 planes of the
+//            kind-3 pack [Cin/8][T][Cout][8]; the epilogue scatters column group tl to voxel 2i + tap(t0+tl)
+// Same warp roles / barriers as conv_tc_kernel.  Used for nn.Conv3d(k=2,s=2) fwd + nn.ConvTranspose3d dgrad (gather)
+// and nn.ConvTranspose3d fwd + nn.Conv3d(k=2,s=2) dgrad (scatter)  (networks/VNet.py:74,101).
+// =========================================================================================================
+struct S2Params {
+  int N, Cin, Cout, mode;          // mode 1 = gather, 2 = scatter
+  int Xh, Yh, Zh;                  // half-resolution grid
+  int BX, BY, BZ, nbx, nby, nbz, nbricks;
+  int rows, MT, nchunks;
+  int TPc, npieces, Npiece;        // taps per piece, pieces, MMA N
+  int SA, SB, AS, tmem_cols;
+  unsigned slotA_bytes, stageB_bytes, offA, offB, offBar;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_s2_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16* __restrict__ wpack, const float* __restrict__ bias,
+                  uint4* __restrict__ out, const S2Params p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t a_base = sbase + p.offA, b_base = sbase + p.offB, bar_base = sbase + p.offBar;
+  const uint32_t full_a = bar_base, empty_a = full_a + 8 * p.SA, full_b = empty_a + 8 * p.SA, empty_b = full_b + 8 * p.SB;
+  const uint32_t tmem_full = empty_b + 8 * p.SB, tmem_empty = tmem_full + 8 * p.AS;
+  volatile uint32_t* tmem_slot = (volatile uint32_t*)(smem + p.offBar + 8 * (2 * p.SA + 2 * p.SB + 2 * p.AS));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p.SA; ++i) { mbar_init(full_a + 8 * i, 1); mbar_init(empty_a + 8 * i, 1); }
+    for (int i = 0; i < p.SB; ++i) { mbar_init(full_b + 8 * i, 1); mbar_init(empty_b + 8 * i, 1); }
+    for (int i = 0; i < p.AS; ++i) { mbar_init(tmem_full + 8 * i, 1); mbar_init(tmem_empty + 8 * i, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int Cib = p.Cin >> 3, Cob = p.Cout >> 3;
+  const int bricks_per_n = p.nbx * p.nby * p.nbz;
+  const int kitems = (p.mode == 1) ? p.nchunks * 8 : p.nchunks;     // A/B items per (brick, piece)
+  const int ntiles = p.nbricks * p.npieces;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t ia = 0, ib = 0;
+      const uint32_t a_bytes = (uint32_t)p.rows * 32u;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int brick = tile / p.npieces, piece = tile - brick * p.npieces;
+        const int n = brick / bricks_per_n;
+        int r = brick - n * bricks_per_n;
+        const int bz = r % p.nbz; r /= p.nbz;
+        const int by = r % p.nby;
+        const int bx = r / p.nby;
+        for (int k = 0; k < kitems; ++k) {
+          const int c = (p.mode == 1) ? (k >> 3) : k;
+          const int t = (p.mode == 1) ? (k & 7) : 0;
+          const uint32_t sa = ia % p.SA, pa = (ia / p.SA) & 1;
+          mbar_wait(empty_a + 8 * sa, pa ^ 1);
+          mbar_expect_tx(full_a + 8 * sa, a_bytes);
+          if (p.mode == 1)
+            tma_load_5d(a_base + sa * p.slotA_bytes, &tmap, full_a + 8 * sa, 0, 2 * bz * p.BZ + (t & 1), 2 * by * p.BY + ((t >> 1) & 1),
+                        2 * bx * p.BX + (t >> 2), n * Cib + 2 * c);
+          else
+            tma_load_5d(a_base + sa * p.slotA_bytes, &tmap, full_a + 8 * sa, 0, bz * p.BZ, by * p.BY, bx * p.BX, n * Cib + 2 * c);
+          ++ia;
+          const uint32_t sb = ib % p.SB, pb = (ib / p.SB) & 1;
+          mbar_wait(empty_b + 8 * sb, pb ^ 1);
+          mbar_expect_tx(full_b + 8 * sb, p.stageB_bytes);
+          if (p.mode == 1) {
+            bulk_load(b_base + sb * p.stageB_bytes, wpack + ((size_t)t * Cib + 2 * c) * (size_t)p.Cout * 8, p.stageB_bytes, full_b + 8 * sb);
+          } else {
+            const uint32_t half = p.stageB_bytes / 2;
+            const size_t t0 = (size_t)piece * p.TPc;
+            bulk_load(b_base + sb * p.stageB_bytes, wpack + (((size_t)(2 * c) * 8 + t0) * p.Cout) * 8, half, full_b + 8 * sb);
+            bulk_load(b_base + sb * p.stageB_bytes + half, wpack + (((size_t)(2 * c + 1) * 8 + t0) * p.Cout) * 8, half, full_b + 8 * sb);
+          }
+          ++ib;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Npiece >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t lboA = (uint32_t)p.rows * 16u, lboB = (uint32_t)p.Npiece * 16u;
+      uint32_t ia = 0, ib = 0, it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const uint32_t as = it % p.AS, ap = (it / p.AS) & 1;
+        mbar_wait(tmem_empty + 8 * as, ap ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + as * (uint32_t)(p.MT * p.Npiece);
+        for (int k = 0; k < kitems; ++k) {
+          const uint32_t sa = ia % p.SA, pa = (ia / p.SA) & 1;
+          const uint32_t sb = ib % p.SB, pb = (ib / p.SB) & 1;
+          mbar_wait(full_a + 8 * sa, pa);
+          mbar_wait(full_b + 8 * sb, pb);
+          tc_fence_after();
+          const uint64_t bdesc = make_desc(b_base + sb * p.stageB_bytes, lboB, 128u);
+          for (int mt = 0; mt < p.MT; ++mt) {
+            const uint64_t adesc = make_desc(a_base + sa * p.slotA_bytes + (uint32_t)mt * 2048u, lboA, 128u);
+            umma_bf16(d0 + (uint32_t)(mt * p.Npiece), adesc, bdesc, idesc, k ? 1u : 0u);
+          }
+          umma_commit(empty_a + 8 * sa);
+          umma_commit(empty_b + 8 * sb);
+          ++ia; ++ib;
+        }
+        umma_commit(tmem_full + 8 * as);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    uint32_t it = 0;
+    const int Xo = (p.mode == 1) ? p.Xh : 2 * p.Xh, Yo = (p.mode == 1) ? p.Yh : 2 * p.Yh, Zo = (p.mode == 1) ? p.Zh : 2 * p.Zh;
+    const long long So = (long long)Xo * Yo * Zo;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int brick = tile / p.npieces, piece = tile - brick * p.npieces;
+      const int n = brick / bricks_per_n;
+      int r = brick - n * bricks_per_n;
+      const int bz = r % p.nbz; r /= p.nbz;
+      const int by = r % p.nby;
+      const int bx = r / p.nby;
+      const uint32_t as = it % p.AS, ap = (it / p.AS) & 1;
+      mbar_wait(tmem_full + 8 * as, ap);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + as * (uint32_t)(p.MT * p.Npiece) + ((uint32_t)(q * 32) << 16);
+      for (int mt = 0; mt < p.MT; ++mt) {
+        const int L = mt * 128 + q * 32 + lane;
+        const int iz = L % p.BZ;
+        const int ry = L / p.BZ;
+        const int iy = ry % p.BY, ix = ry / p.BY;
+        const int x = bx * p.BX + ix, y = by * p.BY + iy, z = bz * p.BZ + iz;
+        const bool valid = (L < p.rows) && (x < p.Xh) && (y < p.Yh) && (z < p.Zh);
+        for (int c16 = 0; c16 < p.Npiece; c16 += 16) {
+          uint32_t v[16];
+          tmem_ld16(d0 + (uint32_t)(mt * p.Npiece + c16), v);
+          tmem_ld_wait();
+          if (valid) {
+            int co = c16, ox = x, oy = y, oz = z;
+            if (p.mode == 2) {
+              const int tl = c16 / p.Cout;
+              co = c16 - tl * p.Cout;
+              const int t = piece * p.TPc + tl;
+              ox = 2 * x + (t >> 2); oy = 2 * y + ((t >> 1) & 1); oz = 2 * z + (t & 1);
+            }
+            float f[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v[k]) + (bias ? __ldg(bias + co + k) : 0.f);
+            uint4* dst = out + ((long long)n * Cob + (co >> 3)) * So + ((long long)ox * Yo + oy) * Zo + oz;
+            dst[0] = pack8(f);
+            dst[So] = pack8(f + 8);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + 8 * as);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// =========================================================================================================
 // weight gradient on tensor cores:  dW[t][co][ci] = sum_rows dy[row][co] * a[row + tap(t)][ci]
 //   D[M = co (128 lanes)][N = ci] += A[M][K] * B[N][K],  K = 16 voxels along z per MMA, both operands "MN-major,
 //   no swizzle" views of the same CB8 bricks the forward kernel uses (channels contiguous, voxels strided 16 B):
@@ -271,7 +448,8 @@ struct WgParams {
   int rows_a, rows_dy;
   int T, TP, npass_t, MH, PL;     // taps, taps per pass, tap passes, M halves, dy planes loaded per brick
   int S, splits, tmem_cols;
-  unsigned a_tx_bytes, dy_tx_bytes, a_alloc_bytes, dy_alloc_bytes, slot_bytes, offBar;
+  int s2;                         // 1: stride-2 family (B bricks are per-tap strided gathers of the full-res tensor)
+  unsigned a_tx_bytes, dy_tx_bytes, a_alloc_bytes, dy_alloc_bytes, slot_bytes, offBar, tap_bytes;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -329,9 +507,18 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         const int by = r % p.nby, bx = r / p.nby;
         const uint32_t s = it % p.S, ph = (it / p.S) & 1;
         mbar_wait(empty + 8 * s, ph ^ 1);
-        mbar_expect_tx(full + 8 * s, p.a_tx_bytes + p.dy_tx_bytes);
         const uint32_t slot = sbase + s * p.slot_bytes;
-        tma_load_5d(slot, &map_a, full + 8 * s, 0, -1, by * p.BY - 1, bx * p.BX - (p.kx >> 1), n * Cib);
+        if (p.s2) {
+          mbar_expect_tx(full + 8 * s, (uint32_t)ntap * p.tap_bytes + p.dy_tx_bytes);
+          for (int tl = 0; tl < ntap; ++tl) {
+            const int t = t0 + tl;
+            tma_load_5d(slot + (uint32_t)tl * p.tap_bytes, &map_a, full + 8 * s, 0, (t & 1), 2 * by * p.BY + ((t >> 1) & 1),
+                        2 * bx * p.BX + (t >> 2), n * Cib);
+          }
+        } else {
+          mbar_expect_tx(full + 8 * s, p.a_tx_bytes + p.dy_tx_bytes);
+          tma_load_5d(slot, &map_a, full + 8 * s, 0, -1, by * p.BY - 1, bx * p.BX - (p.kx >> 1), n * Cib);
+        }
         tma_load_5d(slot + p.a_alloc_bytes, &map_dy, full + 8 * s, 0, 0, by * p.BY, bx * p.BX, n * Cob + mh * 16);
       }
     }
@@ -355,8 +542,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
               for (int tl = 0; tl < ntap; ++tl) {
                 const int t = t0 + tl;
                 const int tz = t % 3, ty = (t / 3) % 3, tx = t / 9;
-                const uint32_t a_row = (uint32_t)(((ix + tx) * p.HY + iy + ty) * p.HZ + tz + zc);
-                const uint64_t bdesc = make_desc(a_slot + a_row * 16u, 128u, sboB);
+                const uint32_t a_row = p.s2 ? dy_row : (uint32_t)(((ix + tx) * p.HY + iy + ty) * p.HZ + tz + zc);
+                const uint64_t bdesc = make_desc(a_slot + (p.s2 ? (uint32_t)tl * p.tap_bytes : 0u) + a_row * 16u, 128u, sboB);
                 umma_bf16(tmem_base + (uint32_t)(tl * p.Cin), adesc, bdesc, idesc, acc);
               }
               acc = 1;
@@ -535,6 +722,51 @@ static bool shape_ok(int cin, int cout, const int* dims, const int* kernel) {
 }
 
 
+
+static bool s2_shape_ok(int cin, int cout, const int* half_dims) {
+  if (cin % 16 || cout % 16 || cin < 16 || cout < 16 || cin > 256 || cout > 256) return false;
+  if (half_dims[0] < 1 || half_dims[1] < 1 || half_dims[2] < 1) return false;
+  return true;
+}
+
+static bool s2_plan(S2Params& p) {
+  p.nchunks = p.Cin / 16;
+  if (p.mode == 1) { p.TPc = 8; p.npieces = 1; p.Npiece = p.Cout; }
+  else {
+    int tp = 8;
+    while (tp > 1 && tp * p.Cout > 256) tp >>= 1;
+    if (tp * p.Cout > 256) return false;
+    p.TPc = tp; p.npieces = 8 / tp; p.Npiece = tp * p.Cout;
+  }
+  int mtmax = 512 / (2 * p.Npiece);
+  if (mtmax < 1) mtmax = 1;
+  if (mtmax > 4) mtmax = 4;
+  const int target = mtmax * 128;
+  p.BZ = p.Zh < 128 ? p.Zh : 128;
+  int by = target / p.BZ; if (by < 1) by = 1; if (by > p.Yh) by = p.Yh; if (by > 128) by = 128;
+  p.BY = by;
+  int bx = target / (p.BZ * p.BY); if (bx < 1) bx = 1; if (bx > p.Xh) bx = p.Xh; if (bx > 128) bx = 128;
+  p.BX = bx;
+  p.rows = p.BX * p.BY * p.BZ;
+  p.MT = (p.rows + 127) / 128;
+  if (p.MT * p.Npiece > 512) return false;
+  p.AS = (2 * p.MT * p.Npiece <= 512) ? 2 : 1;
+  int cols = 32;
+  while (cols < p.AS * p.MT * p.Npiece) cols *= 2;
+  p.tmem_cols = cols;
+  p.nbx = (p.Xh + p.BX - 1) / p.BX; p.nby = (p.Yh + p.BY - 1) / p.BY; p.nbz = (p.Zh + p.BZ - 1) / p.BZ;
+  p.nbricks = p.N * p.nbx * p.nby * p.nbz;
+  p.slotA_bytes = (unsigned)(((long long)(p.rows + p.MT * 128) * 16 + 127) / 128 * 128);
+  p.stageB_bytes = (unsigned)p.Npiece * 32u;
+  p.SB = 4;
+  long long avail = (long long)SMEM_BUDGET - 1024 - (long long)p.SB * p.stageB_bytes;
+  int sa = (int)(avail / p.slotA_bytes);
+  if (sa < 2) return false;
+  p.SA = sa > 8 ? 8 : sa;
+  p.offA = 0; p.offB = p.SA * p.slotA_bytes; p.offBar = p.offB + p.SB * p.stageB_bytes;
+  return true;
+}
+
 static bool wg_shape_ok(int cin, int cout, const int* dims, const int* kernel) {
   if (!shape_ok(cin, cout, dims, kernel)) return false;
   if (dims[2] + 2 > 256) return false;                 // one z-line (+halo) must fit a TMA box
@@ -705,6 +937,157 @@ int bcp_conv_tc_wgrad(const void* a, const void* dy, float* dw, float* workspace
   const long long per = (long long)p.T * cout * cin;
   conv_tc_wgrad_finalize_kernel<<<(unsigned)((per + 255) / 256), 256, 0, stream>>>(workspace, dw, p.splits, p.T, cout, cin);
   return check_launch("conv_tc_wgrad");
+}
+
+// ---- stride-2 family.  half_dims = dims of the half-resolution grid (full = 2x).  mode 1 (gather): `in` is full-res with
+// cin channels, wpack = kind-0 pack, out half-res cout channels.  mode 2 (scatter): `in` is half-res with cin channels,
+// wpack = kind-3 pack [cin/8][8][cout][8], out full-res cout channels.
+int bcp_conv_tc_s2_supported(int cin, int cout, const int* half_dims, int mode) {
+  if (!half_dims || (mode != 1 && mode != 2)) return 0;
+  if (!s2_shape_ok(cin, cout, half_dims)) return 0;
+  S2Params p{};
+  p.N = 1; p.Cin = cin; p.Cout = cout; p.mode = mode; p.Xh = half_dims[0]; p.Yh = half_dims[1]; p.Zh = half_dims[2];
+  if (!s2_plan(p)) return 0;
+  return get_encode() != nullptr ? 1 : 0;
+}
+
+int bcp_conv_tc_s2_fwd(const void* in, const void* wpack, const float* bias, void* out, int n, int cin, int cout,
+                       const int* half_dims, int mode, cudaStream_t stream) {
+  BCP_REQUIRE(in && wpack && out && half_dims, "conv_tc_s2_fwd: null pointer");
+  BCP_REQUIRE(mode == 1 || mode == 2, "conv_tc_s2_fwd: mode");
+  if (!s2_shape_ok(cin, cout, half_dims)) { set_last_error("conv_tc_s2_fwd: unsupported shape"); return BCP_ERR_UNSUPPORTED; }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_last_error("conv_tc_s2_fwd: cuTensorMapEncodeTiled unavailable"); return BCP_ERR_CUDA; }
+  S2Params p{};
+  p.N = n; p.Cin = cin; p.Cout = cout; p.mode = mode; p.Xh = half_dims[0]; p.Yh = half_dims[1]; p.Zh = half_dims[2];
+  if (!s2_plan(p)) { set_last_error("conv_tc_s2_fwd: no tiling fits"); return BCP_ERR_UNSUPPORTED; }
+  const int f = (mode == 1) ? 2 : 1;      // input resolution factor
+  const cuuint64_t X = (cuuint64_t)p.Xh * f, Y = (cuuint64_t)p.Yh * f, Z = (cuuint64_t)p.Zh * f;
+  CUtensorMap tmap;
+  const cuuint64_t gdim[5] = {8, Z, Y, X, (cuuint64_t)n * (cin / 8)};
+  const cuuint64_t gstr[4] = {16, Z * 16, Z * Y * 16, Z * Y * X * 16};
+  const cuuint32_t box[5] = {8, (cuuint32_t)(p.BZ * f), (cuuint32_t)(p.BY * f), (cuuint32_t)(p.BX * f), 2};
+  const cuuint32_t estr[5] = {1, (cuuint32_t)f, (cuuint32_t)f, (cuuint32_t)f, 1};
+  const CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(in), gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) { set_last_error("conv_tc_s2_fwd: cuTensorMapEncodeTiled failed (%d)", (int)cr); return BCP_ERR_CUDA; }
+  const size_t smem = (size_t)p.offBar + 8 * (2 * p.SA + 2 * p.SB + 2 * p.AS) + 16 + 128;
+  static std::once_flag attr_once;
+  std::call_once(attr_once, [] { cudaFuncSetAttribute(conv_tc_s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  const int nsm = sm_count();
+  const int ntiles = p.nbricks * p.npieces;
+  conv_tc_s2_kernel<<<ntiles < nsm ? ntiles : nsm, TC_THREADS, smem, stream>>>(tmap, (const __nv_bfloat16*)wpack, bias, (uint4*)out, p);
+  return check_launch("conv_tc_s2_fwd");
+}
+
+// dw[c_half][c_full][8] = sum_i half[i][c_half] * full[2i+t][c_full]   (Conv3d k2s2: half = dy, full = input;
+// ConvTranspose3d k2s2: half = input, full = dy)
+static bool wg_s2_plan(WgParams& p, int nsm) {
+  p.T = 8;
+  p.TP = 512 / p.Cin; if (p.TP > 8) p.TP = 8; if (p.TP < 1) return false;
+  p.npass_t = (8 + p.TP - 1) / p.TP;
+  p.MH = (p.Cout > 128) ? 2 : 1;
+  p.PL = (p.Cout / 8 < 16) ? p.Cout / 8 : 16;
+  p.ZP = (p.Z + 15) / 16 * 16;
+  if (p.ZP > 128) return false;
+  p.HX = p.HY = p.HZ = 0; p.s2 = 1; p.kx = 2;
+  int cols = 32;
+  while (cols < p.TP * p.Cin) cols *= 2;
+  p.tmem_cols = cols;
+  const int npass = p.npass_t * p.MH, Cib = p.Cin / 8;
+  double best = 1e300; bool found = false; WgParams bp = p;
+  for (int BY = 1; BY <= p.Y && BY <= 128; ++BY) {
+    for (int BX = 1; BX <= p.X && BX <= 128; ++BX) {
+      const long long rows = (long long)BX * BY * p.ZP;
+      if (rows >= 16384) break;
+      const long long tap_bytes = rows * 16 * Cib, a_alloc = ((long long)p.TP * tap_bytes + 127) / 128 * 128;
+      const long long dy_tx = rows * 16 * p.PL, dy_alloc = (rows * 256 + 127) / 128 * 128;
+      const long long slot = a_alloc + dy_alloc;
+      int S = (int)((SMEM_BUDGET - 1024) / slot);
+      if (S < 2) break;
+      if (S > 4) S = 4;
+      const int nbx = (p.X + BX - 1) / BX, nby = (p.Y + BY - 1) / BY;
+      const long long nb = (long long)p.N * nbx * nby;
+      long long splits = nsm / npass; if (splits < 1) splits = 1; if (splits > nb) splits = nb;
+      const long long per_cta = (nb + splits - 1) / splits;
+      const double per_mma = (p.Cin / 2.0 > 32.0 + p.Cin / 4.0) ? p.Cin / 2.0 : 32.0 + p.Cin / 4.0;
+      const double mma_cyc = (double)BX * BY * (p.ZP / 16) * p.TP * per_mma;
+      const double load_cyc = (double)(p.TP * tap_bytes + dy_tx) / 40.0;
+      const double cost = (double)per_cta * ((mma_cyc > load_cyc ? mma_cyc : load_cyc) + 1200.0);
+      if (cost < best) {
+        best = cost; found = true; bp = p;
+        bp.BX = BX; bp.BY = BY; bp.nbx = nbx; bp.nby = nby; bp.nbricks = (int)nb;
+        bp.rows_a = (int)rows; bp.rows_dy = (int)rows; bp.S = S; bp.splits = (int)splits;
+        bp.tap_bytes = (unsigned)tap_bytes; bp.a_tx_bytes = (unsigned)a_alloc; bp.a_alloc_bytes = (unsigned)a_alloc;
+        bp.dy_tx_bytes = (unsigned)dy_tx; bp.dy_alloc_bytes = (unsigned)dy_alloc; bp.slot_bytes = (unsigned)slot;
+      }
+    }
+  }
+  if (!found) return false;
+  p = bp;
+  p.offBar = p.S * p.slot_bytes;
+  return true;
+}
+
+static int wg_s2_setup(WgParams& p, int n, int c_half, int c_full, const int* half_dims) {
+  p = WgParams{};
+  p.N = n; p.X = half_dims[0]; p.Y = half_dims[1]; p.Z = half_dims[2]; p.Cin = c_full; p.Cout = c_half;
+  return wg_s2_plan(p, sm_count()) ? 0 : -1;
+}
+
+int bcp_conv_tc_s2_wgrad_supported(int c_half, int c_full, const int* half_dims) {
+  if (!half_dims || !s2_shape_ok(c_full, c_half, half_dims)) return 0;
+  WgParams p;
+  if (wg_s2_setup(p, 1, c_half, c_full, half_dims) != 0) return 0;
+  return get_encode() != nullptr ? 1 : 0;
+}
+
+long long bcp_conv_tc_s2_wgrad_workspace_floats(int n, int c_half, int c_full, const int* half_dims) {
+  if (!half_dims || !s2_shape_ok(c_full, c_half, half_dims)) return 0;
+  WgParams p;
+  if (wg_s2_setup(p, n, c_half, c_full, half_dims) != 0) return 0;
+  return (long long)p.splits * 8 * c_half * c_full;
+}
+
+int bcp_conv_tc_s2_wgrad(const void* full, const void* half, float* dw, float* workspace, int n, int c_half, int c_full,
+                         const int* half_dims, cudaStream_t stream) {
+  BCP_REQUIRE(full && half && dw && workspace && half_dims, "conv_tc_s2_wgrad: null pointer");
+  if (!s2_shape_ok(c_full, c_half, half_dims)) { set_last_error("conv_tc_s2_wgrad: unsupported shape"); return BCP_ERR_UNSUPPORTED; }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_last_error("conv_tc_s2_wgrad: cuTensorMapEncodeTiled unavailable"); return BCP_ERR_CUDA; }
+  WgParams p;
+  if (wg_s2_setup(p, n, c_half, c_full, half_dims) != 0) { set_last_error("conv_tc_s2_wgrad: no tiling fits"); return BCP_ERR_UNSUPPORTED; }
+  CUtensorMap map_a, map_dy;
+  {
+    const cuuint64_t X = 2ull * p.X, Y = 2ull * p.Y, Z = 2ull * p.Z;
+    const cuuint64_t gdim[5] = {8, Z, Y, X, (cuuint64_t)n * (c_full / 8)};
+    const cuuint64_t gstr[4] = {16, Z * 16, Z * Y * 16, Z * Y * X * 16};
+    const cuuint32_t box[5] = {8, (cuuint32_t)(2 * p.ZP), (cuuint32_t)(2 * p.BY), (cuuint32_t)(2 * p.BX), (cuuint32_t)(c_full / 8)};
+    const cuuint32_t estr[5] = {1, 2, 2, 2, 1};
+    const CUresult cr = enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(full), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { set_last_error("conv_tc_s2_wgrad: tensor map (full) failed (%d)", (int)cr); return BCP_ERR_CUDA; }
+  }
+  {
+    const cuuint64_t gdim[5] = {8, (cuuint64_t)p.Z, (cuuint64_t)p.Y, (cuuint64_t)p.X, (cuuint64_t)n * (c_half / 8)};
+    const cuuint64_t gstr[4] = {16, (cuuint64_t)p.Z * 16, (cuuint64_t)p.Z * p.Y * 16, (cuuint64_t)p.Z * p.Y * p.X * 16};
+    const cuuint32_t box[5] = {8, (cuuint32_t)p.ZP, (cuuint32_t)p.BY, (cuuint32_t)p.BX, (cuuint32_t)p.PL};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUresult cr = enc(&map_dy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(half), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { set_last_error("conv_tc_s2_wgrad: tensor map (half) failed (%d)", (int)cr); return BCP_ERR_CUDA; }
+  }
+  const size_t smem = (size_t)p.offBar + 8 * (2 * p.S + 1) + 16 + 128;
+  static std::once_flag attr_once;
+  std::call_once(attr_once, [] { cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  dim3 grid(p.splits, p.npass_t * p.MH);
+  conv_tc_wgrad_kernel<<<grid, TC_THREADS, smem, stream>>>(map_a, map_dy, workspace, p);
+  const long long per = 8ll * c_half * c_full;
+  conv_tc_wgrad_finalize_kernel<<<(unsigned)((per + 255) / 256), 256, 0, stream>>>(workspace, dw, p.splits, 8, c_half, c_full);
+  return check_launch("conv_tc_s2_wgrad");
 }
 
 }  // extern "C"

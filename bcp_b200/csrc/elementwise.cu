@@ -149,7 +149,8 @@ __global__ void ema_i64_kernel(long long* __restrict__ e, const long long* __res
 //   ConvTranspose k2s2: A=Cin(half-res),B=Cout(full-res)).
 //   kind 0: [T][B/8][A][8]  inner = B index            -- conv fwd operand; stride-2 "gather" (full->half) operand
 //   kind 1: [T][A/8][B][8]  inner = A index, taps flipped (t -> T-1-t)   -- conv dgrad operand
-//   kind 2: [T][A/8][B][8]  inner = A index            -- stride-2 "scatter" (half->full) operand
+//   kind 2: [T][A/8][B][8]  inner = A index            -- stride-2 "scatter" (half->full) operand, CUDA-core kernel
+//   kind 3: [A/8][T][B][8]  inner = A index            -- stride-2 "scatter" operand of the tcgen05 kernel
 // Channel counts that are not multiples of 8 are zero-padded in the blocked dimension.
 // ------------------------------------------------------------------------------------------
 __global__ void repack_kernel(const float* __restrict__ arena, __nv_bfloat16* __restrict__ packed,
@@ -172,6 +173,19 @@ __global__ void repack_kernel(const float* __restrict__ arena, __nv_bfloat16* __
         const int t = (int)r;
         const int b = bb * 8 + b8;
         const float v = (b < B) ? src[((long long)a * B + b) * T + t] : 0.f;
+        dst[i] = __float2bfloat16_rn(v);
+      }
+    } else if (job.kind == 3) {
+      // dst [ceil(A/8)][T][B][8] with inner = A index; src [A][B][T]
+      const int Ab = (A + 7) / 8;
+      const long long total = (long long)Ab * T * B * 8;
+      for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        long long r = i;
+        const int a8 = (int)(r % 8); r /= 8;
+        const int b = (int)(r % B); r /= B;
+        const int t = (int)(r % T); r /= T;
+        const int a = (int)r * 8 + a8;
+        const float v = (a < A) ? src[((long long)a * B + b) * T + t] : 0.f;
         dst[i] = __float2bfloat16_rn(v);
       }
     } else {

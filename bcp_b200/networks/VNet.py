@@ -59,10 +59,8 @@ class _Stage3d(nn.Module):
             conv = self.conv[i * self._per]
             if self.kind == "same":
                 rt.register_conv(conv, None if conv.in_channels % 8 else (0, 1))
-            elif self.kind == "down":
-                rt.register_conv(conv, (0, 2))
             else:
-                rt.register_conv(conv, (2, 0))
+                rt.register_conv(conv, (0, 2, 3))
 
     def _norm_act(self, y, norm, chan_scale=None, residual=None):
         rt = self._rt

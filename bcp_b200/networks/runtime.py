@@ -123,7 +123,7 @@ class NetRuntime:
                 else:
                     n = taps * ((a + 7) // 8) * b * 8
                 jobs.append((src, dst, a, b, taps, kind))
-                views.append((dst, n))
+                views.append((kind, dst, n))
                 dst += (n + 127) // 128 * 128          # keep every pack 256-byte aligned
             slots.append((conv, views))
         self.packed = torch.empty(max(dst, 128), dtype=torch.bfloat16, device=dev)
@@ -132,8 +132,7 @@ class NetRuntime:
         self.jobs = torch.from_numpy(arr.view(np.uint8).copy()).to(dev) if jobs else None
         self.packs = {}
         for conv, views in slots:
-            t = [self.packed[o:o + n] for o, n in views]
-            self.packs[id(conv)] = ConvPack(t[0], t[1] if len(t) > 1 else None)
+            self.packs[id(conv)] = ConvPack({kind: self.packed[o:o + n] for kind, o, n in views})
 
     def pack(self, conv) -> ConvPack:
         return self.packs[id(conv)]

@@ -91,11 +91,12 @@ class CB8ToPlanar(Function):
 # convolutions
 # ----------------------------------------------------------------------------------------------
 class ConvPack:
-    """bf16 operand packs of one conv layer: views into the owning network's packed buffer."""
-    __slots__ = ("fwd", "bwd")
+    """bf16 operand packs of one conv layer, keyed by repack kind (include/bcp_b200.h): views into the owning
+    network's packed buffer."""
+    __slots__ = ("k",)
 
-    def __init__(self, fwd=None, bwd=None):
-        self.fwd, self.bwd = fwd, bwd
+    def __init__(self, by_kind):
+        self.k = dict(by_kind)
 
 
 def _conv_same(a, wpack, bias, cout, kernel, allow_tc=True):
@@ -146,7 +147,7 @@ class ConvSame(Function):
         cout = weight.shape[0]
         ctx.save_for_backward(a, weight)
         ctx.pack, ctx.kernel, ctx.has_bias = pack, tuple(kernel), bias is not None
-        return _conv_same(a, pack.fwd, bias, cout, kernel)
+        return _conv_same(a, pack.k[0], bias, cout, kernel)
 
     @staticmethod
     def backward(ctx, dy):
@@ -156,7 +157,7 @@ class ConvSame(Function):
         cout, k = weight.shape[0], ctx.kernel
         da = dw = db = None
         if ctx.needs_input_grad[0]:
-            da = _conv_same(dy, ctx.pack.bwd, None, cin, k)
+            da = _conv_same(dy, ctx.pack.k[1], None, cin, k)
         if ctx.needs_input_grad[1]:
             dw = _wgrad(a, dy, cin, cout, (x, y, z), k, (1, 1, 1), (k[0] // 2, k[1] // 2, k[2] // 2), weight.shape)
         if ctx.has_bias and ctx.needs_input_grad[2]:
@@ -164,8 +165,36 @@ class ConvSame(Function):
         return da, dw, db, None, None
 
 
+def _s2_fwd(inp, pack: ConvPack, bias, cin, cout, half_dims, mode):
+    """stride-2 conv (mode 1: full->half) / transposed conv (mode 2: half->full) on CB8; tcgen05 when the shape qualifies."""
+    n = inp.shape[0]
+    hx, hy, hz = half_dims
+    od = (hx, hy, hz) if mode == 1 else (2 * hx, 2 * hy, 2 * hz)
+    out = torch.empty(cb8_shape(n, cout, *od), dtype=BF16, device=inp.device)
+    if _TC_FWD and 3 in pack.k and LIB.query("bcp_conv_tc_s2_supported", cin, cout, i3(*half_dims), mode):
+        LIB.call("bcp_conv_tc_s2_fwd", ptr(inp), ptr(pack.k[0] if mode == 1 else pack.k[3]), ptr(bias), ptr(out), n, cin, cout,
+                 i3(*half_dims), mode, stream())
+    else:
+        ind = (2 * hx, 2 * hy, 2 * hz) if mode == 1 else (hx, hy, hz)
+        LIB.call("bcp_conv_direct_fwd", ptr(inp), ptr(pack.k[0] if mode == 1 else pack.k[2]), ptr(bias), ptr(out), n, cin, cout,
+                 i3(*ind), i3(2, 2, 2), i3(2, 2, 2), i3(0, 0, 0), 0 if mode == 1 else 1, stream())
+    return out
+
+
+def _s2_wgrad(full, half, c_full, c_half, half_dims, wshape):
+    """dW[c_half][c_full][8] = sum_i half[i] (x) full[2i+t]."""
+    n = full.shape[0]
+    hx, hy, hz = half_dims
+    if _TC_WGRAD and LIB.query("bcp_conv_tc_s2_wgrad_supported", c_half, c_full, i3(*half_dims)):
+        ws = _f32(LIB.query("bcp_conv_tc_s2_wgrad_workspace_floats", n, c_half, c_full, i3(*half_dims)), full.device)
+        dw = torch.empty(wshape, dtype=torch.float32, device=full.device)
+        LIB.call("bcp_conv_tc_s2_wgrad", ptr(full), ptr(half), ptr(dw), ptr(ws), n, c_half, c_full, i3(*half_dims), stream())
+        return dw
+    return _wgrad(full, half, c_full, c_half, (2 * hx, 2 * hy, 2 * hz), (2, 2, 2), (2, 2, 2), (0, 0, 0), wshape, allow_tc=False)
+
+
 class ConvDown2(Function):
-    """nn.Conv3d(k=2, s=2) (networks/VNet.py:74).  weight [Cout][Cin][2,2,2]; pack.fwd = kind 0, pack.bwd = kind 2."""
+    """nn.Conv3d(k=2, s=2) (networks/VNet.py:74).  weight [Cout][Cin][2,2,2]; packs: kind 0 (fwd), kinds 2/3 (dgrad)."""
 
     @staticmethod
     def forward(ctx, a, weight, bias, pack: ConvPack):
@@ -173,12 +202,9 @@ class ConvDown2(Function):
         a = a.contiguous()
         n, cin, x, y, z = act_dims(a)
         cout = weight.shape[0]
-        out = torch.empty(cb8_shape(n, cout, x // 2, y // 2, z // 2), dtype=BF16, device=a.device)
-        LIB.call("bcp_conv_direct_fwd", ptr(a), ptr(pack.fwd), ptr(bias), ptr(out), n, cin, cout, i3(x, y, z), i3(2, 2, 2),
-                 i3(2, 2, 2), i3(0, 0, 0), 0, stream())
         ctx.save_for_backward(a, weight)
         ctx.pack, ctx.has_bias = pack, bias is not None
-        return out
+        return _s2_fwd(a, pack, bias, cin, cout, (x // 2, y // 2, z // 2), 1)
 
     @staticmethod
     def backward(ctx, dy):
@@ -186,20 +212,19 @@ class ConvDown2(Function):
         dy = dy.contiguous()
         n, cin, x, y, z = act_dims(a)
         cout = weight.shape[0]
+        half = (x // 2, y // 2, z // 2)
         da = dw = db = None
         if ctx.needs_input_grad[0]:
-            da = torch.empty_like(a)
-            LIB.call("bcp_conv_direct_fwd", ptr(dy), ptr(ctx.pack.bwd), None, ptr(da), n, cout, cin, i3(x // 2, y // 2, z // 2),
-                     i3(2, 2, 2), i3(2, 2, 2), i3(0, 0, 0), 1, stream())
+            da = _s2_fwd(dy, ctx.pack, None, cout, cin, half, 2)
         if ctx.needs_input_grad[1]:
-            dw = _wgrad(a, dy, cin, cout, (x, y, z), (2, 2, 2), (2, 2, 2), (0, 0, 0), weight.shape)
+            dw = _s2_wgrad(a, dy, cin, cout, half, weight.shape)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = _chan_sum(dy, cout)
         return da, dw, db, None
 
 
 class ConvUp2(Function):
-    """nn.ConvTranspose3d(k=2, s=2) (networks/VNet.py:101).  weight [Cin][Cout][2,2,2]; pack.fwd = kind 2, pack.bwd = kind 0."""
+    """nn.ConvTranspose3d(k=2, s=2) (networks/VNet.py:101).  weight [Cin][Cout][2,2,2]; packs: kinds 2/3 (fwd), kind 0 (dgrad)."""
 
     @staticmethod
     def forward(ctx, a, weight, bias, pack: ConvPack):
@@ -207,12 +232,9 @@ class ConvUp2(Function):
         a = a.contiguous()
         n, cin, x, y, z = act_dims(a)
         cout = weight.shape[1]
-        out = torch.empty(cb8_shape(n, cout, 2 * x, 2 * y, 2 * z), dtype=BF16, device=a.device)
-        LIB.call("bcp_conv_direct_fwd", ptr(a), ptr(pack.fwd), ptr(bias), ptr(out), n, cin, cout, i3(x, y, z), i3(2, 2, 2),
-                 i3(2, 2, 2), i3(0, 0, 0), 1, stream())
         ctx.save_for_backward(a, weight)
         ctx.pack, ctx.has_bias = pack, bias is not None
-        return out
+        return _s2_fwd(a, pack, bias, cin, cout, (x, y, z), 2)
 
     @staticmethod
     def backward(ctx, dy):
@@ -222,12 +244,9 @@ class ConvUp2(Function):
         cout = weight.shape[1]
         da = dw = db = None
         if ctx.needs_input_grad[0]:
-            da = torch.empty_like(a)
-            LIB.call("bcp_conv_direct_fwd", ptr(dy), ptr(ctx.pack.bwd), None, ptr(da), n, cout, cin, i3(2 * x, 2 * y, 2 * z),
-                     i3(2, 2, 2), i3(2, 2, 2), i3(0, 0, 0), 0, stream())
+            da = _s2_fwd(dy, ctx.pack, None, cout, cin, (x, y, z), 1)
         if ctx.needs_input_grad[1]:
-            # dW[ci][co][t] = sum_i a[i][ci] * dy[2i+t][co]: "in" = dy (full res, co), "outgrad" = a (half res, ci)
-            dw = _wgrad(dy, a, cout, cin, (2 * x, 2 * y, 2 * z), (2, 2, 2), (2, 2, 2), (0, 0, 0), weight.shape)
+            dw = _s2_wgrad(dy, a, cout, cin, (x, y, z), weight.shape)     # half = layer input, full = dy
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = _chan_sum(dy, cout)
         return da, dw, db, None

@@ -87,7 +87,8 @@ int bcp_ema_i64(long long* ema, const long long* model, int n, float alpha, floa
  * source tensor is [dim_a][dim_b][taps] fp32 at arena + src_off (floats); destination at packed + dst_off (bf16 elems)
  * kind 0: [T][dim_b/8][dim_a][8] (inner = b)          conv fwd / stride-2 gather operand
  * kind 1: [T][dim_a/8][dim_b][8] (inner = a), taps reversed     conv dgrad operand
- * kind 2: [T][dim_a/8][dim_b][8] (inner = a)          stride-2 scatter operand */
+ * kind 2: [T][dim_a/8][dim_b][8] (inner = a)          stride-2 scatter operand (CUDA-core kernel)
+ * kind 3: [dim_a/8][T][dim_b][8] (inner = a)          stride-2 scatter operand (tcgen05 kernel) */
 typedef struct bcp_repack_job {
   long long src_off;
   long long dst_off;
@@ -155,6 +156,18 @@ int bcp_conv_tc_wgrad_supported(int cin, int cout, const int* dims, const int* k
 long long bcp_conv_tc_wgrad_workspace_floats(int n, int cin, int cout, const int* dims, const int* kernel);
 int bcp_conv_tc_wgrad(const void* a, const void* dy, float* dw, float* workspace, int n, int cin, int cout,
                       const int* dims, const int* kernel, cudaStream_t stream);
+
+/* tcgen05 stride-2 family (nn.Conv3d(k=2,s=2) networks/VNet.py:74, nn.ConvTranspose3d(k=2,s=2) networks/VNet.py:101).
+ * half_dims = half-resolution grid.  mode 1 gather: in = full-res [cin], wpack kind 0, out = half-res [cout].
+ * mode 2 scatter: in = half-res [cin], wpack kind 3 ([cin/8][8][cout][8]), out = full-res [cout].
+ * wgrad: dw[c_half][c_full][8] = sum_i half[i][c_half] * full[2i+t][c_full]. */
+int bcp_conv_tc_s2_supported(int cin, int cout, const int* half_dims, int mode);
+int bcp_conv_tc_s2_fwd(const void* in, const void* wpack, const float* bias, void* out, int n, int cin, int cout,
+                       const int* half_dims, int mode, cudaStream_t stream);
+int bcp_conv_tc_s2_wgrad_supported(int c_half, int c_full, const int* half_dims);
+long long bcp_conv_tc_s2_wgrad_workspace_floats(int n, int c_half, int c_full, const int* half_dims);
+int bcp_conv_tc_s2_wgrad(const void* full, const void* half, float* dw, float* workspace, int n, int c_half, int c_full,
+                         const int* half_dims, cudaStream_t stream);
 
 /* ---- resampling (networks/unet.py:37 MaxPool2d(2); :50 Upsample(bilinear, align_corners=True);
  * networks/VNet.py:249 MaxPool3d(3, stride=2)).  planes = n * ceil(c/8) * X. */

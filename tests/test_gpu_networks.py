@@ -61,6 +61,43 @@ def test_vnet_train_fwd_bwd(dev):
     assert np.allclose(d[:, 1], ref[:, 1], rtol=2e-2)
 
 
+def test_vnet_grads_vs_fp32_oracle_full_size(dev):
+    """All parameter gradients of one train-mode forward/backward at the LA size (batch 2) against the fp32 oracle run
+    on the same GPU (cuDNN, TF32 off).  Full-size statistics (>= 490 values per channel) keep bf16 noise from being
+    amplified the way it is on the tiny golden volumes."""
+    import json
+    import os
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    shape = (2, 1, 112, 112, 80)
+    x = O.synthetic_volume(shape, 77).to(dev)
+    w = O.synthetic_volume((2, 2) + shape[2:], 78).to(dev)
+    net = _vnet(dev, 23, True, True, drop_seed=24)
+    lo, _ = net(x, with_features=False)
+    (lo * w).sum().backward()
+    ref = O.OracleVNet(1, 2, 16, "batchnorm", True)
+    O.fill_state_dict_(ref, 23)
+    ref = ref.to(dev).train()
+    inject_dropout(ref, seed=24)
+    lr, _ = ref(x)
+    (lr * w).sum().backward()
+    e_logits = rel_rms(lo.detach(), lr.detach())
+    record("vnet_full_train_logits_rel_rms", e_logits)
+    table = {}
+    rp = dict(ref.named_parameters())
+    for n, p in net.named_parameters():
+        if p.grad is None:
+            continue
+        table[n] = rel_rms(p.grad, rp[n].grad)
+    os.makedirs(os.path.join(os.path.dirname(__file__), "..", "gpurun_out"), exist_ok=True)
+    json.dump(table, open(os.path.join(os.path.dirname(__file__), "..", "gpurun_out", "vnet_grad_table.json"), "w"), indent=1)
+    conv_w = [v for k, v in table.items() if k.endswith("conv.0.weight") or ".conv.3.weight" in k or ".conv.6.weight" in k or "out_conv.weight" in k]
+    record("vnet_full_grad_conv_weight_rel_rms_median", float(np.median(conv_w)))
+    record("vnet_full_grad_conv_weight_rel_rms_max", float(np.max(conv_w)))
+    assert e_logits <= LOGIT_TOL
+    assert np.median(conv_w) <= 5e-2 and np.max(conv_w) <= 0.25
+
+
 def test_vnet_grouped_equals_two_calls(dev):
     """Batching two reference forward calls as two BatchNorm groups is bit-identical to calling twice."""
     x = O.synthetic_volume((4, 1, 32, 32, 16), 5).to(dev)

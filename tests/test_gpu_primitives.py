@@ -288,7 +288,7 @@ def _packs(ops, dev, weight, kinds):
     jt = torch.from_numpy(np.array(jobs, dtype=_JOB).view(np.uint8).copy()).to(dev)
     w = weight.detach().contiguous()
     LIB.call("bcp_weights_repack", ptr(w), ptr(packed), ptr(jt), len(jobs), stream())
-    return ops.ConvPack(*[packed[o:o + n] for o, n in views])
+    return ops.ConvPack({kind: packed[o:o + n] for kind, (o, n) in zip(kinds, views)})
 
 
 def _check_conv(got_y, ref_y, grads_got, grads_ref, tol_fwd=6e-3, tol_bwd=1e-2):
@@ -328,7 +328,7 @@ def test_conv_stride2_family(ops, dev):
     w = (torch.randn(cout, cin, 2, 2, 2, device=dev) / np.sqrt(cin * 8)).to(torch.bfloat16).float().requires_grad_(True)
     b = (0.1 * torch.randn(cout, device=dev)).requires_grad_(True)
     xcb = cb8_from_planar(x).requires_grad_(True)
-    y = ops.ConvDown2.apply(xcb, w, b, _packs(ops, dev, w, (0, 2)))
+    y = ops.ConvDown2.apply(xcb, w, b, _packs(ops, dev, w, (0, 2, 3)))
     xr, wr, br = x.clone().requires_grad_(True), w.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
     yr = F.conv3d(xr, wr, br, stride=2)
     g = torch.randn_like(yr).to(torch.bfloat16).float()
@@ -342,7 +342,7 @@ def test_conv_stride2_family(ops, dev):
     w = (torch.randn(cin, cout, 2, 2, 2, device=dev) / np.sqrt(cin)).to(torch.bfloat16).float().requires_grad_(True)
     b = (0.1 * torch.randn(cout, device=dev)).requires_grad_(True)
     xcb = cb8_from_planar(x).requires_grad_(True)
-    y = ops.ConvUp2.apply(xcb, w, b, _packs(ops, dev, w, (2, 0)))
+    y = ops.ConvUp2.apply(xcb, w, b, _packs(ops, dev, w, (0, 2, 3)))
     xr, wr, br = x.clone().requires_grad_(True), w.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
     yr = F.conv_transpose3d(xr, wr, br, stride=2)
     g = torch.randn_like(yr).to(torch.bfloat16).float()

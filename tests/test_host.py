@@ -87,7 +87,7 @@ def test_flat_arena_and_packs():
     g = rt.ensure_grad_arena()
     assert g.numel() == rt.n_train
     assert net.decoder.out_conv.weight.grad.data_ptr() >= g.data_ptr()
-    assert rt.njobs == 56       # 28 packed conv layers x (fwd, bwd); block_one and out_conv read fp32 weights
+    assert rt.njobs == 64       # 20 'same' convs x (fwd, dgrad) + 8 stride-2 convs x 3 packs; block_one/out_conv read fp32
 
 
 def test_box_draw_order_matches_reference():

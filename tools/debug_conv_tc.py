@@ -41,8 +41,8 @@ def run(n, cin, cout, dims, kernel, mode="rand", verbose=True):
     a = cb8_from_planar(x)
     rc, pl = plan(n, cin, cout, dims, kernel)
     ref = F.conv3d(x, w, b, padding=tuple(k // 2 for k in kernel))
-    y_d = planar_from_cb8(ops._conv_same(a, pack.fwd, b, cout, kernel, allow_tc=False), cout)
-    y_t = planar_from_cb8(ops._conv_same(a, pack.fwd, b, cout, kernel, allow_tc=True), cout)
+    y_d = planar_from_cb8(ops._conv_same(a, pack.k[0], b, cout, kernel, allow_tc=False), cout)
+    y_t = planar_from_cb8(ops._conv_same(a, pack.k[0], b, cout, kernel, allow_tc=True), cout)
     torch.cuda.synchronize()
     e_d, e_t, e_td = rel_rms(y_d, ref), rel_rms(y_t, ref), rel_rms(y_t, y_d)
     print(f"[{mode}] n={n} cin={cin} cout={cout} dims={dims} k={kernel} plan(BX,BY,BZ,MT,SA,SB,AS,nb,cols,smem)={pl} "
@@ -57,6 +57,48 @@ def run(n, cin, cout, dims, kernel, mode="rand", verbose=True):
         print("   sample got", y_t[0, :4, 0, 0, :6].cpu().numpy().round(3))
         print("   sample ref", ref[0, :4, 0, 0, :6].cpu().numpy().round(3))
     return e_t
+
+
+def run_s2(n, c_full, c_half, half):
+    """down conv (c_full -> c_half) and transposed conv (c_half -> c_full), fwd + all gradients, tc vs direct vs torch."""
+    torch.manual_seed(2)
+    full = tuple(2 * h for h in half)
+    res = {}
+    for tc in (False, True):
+        ops._TC_FWD, ops._TC_WGRAD = tc, tc
+        # down
+        x = torch.randn(n, c_full, *full, device=dev).to(torch.bfloat16).float()
+        w = (torch.randn(c_half, c_full, 2, 2, 2, device=dev) / np.sqrt(8 * c_full)).to(torch.bfloat16).float().requires_grad_(True)
+        b = (0.1 * torch.randn(c_half, device=dev)).requires_grad_(True)
+        xcb = cb8_from_planar(x).requires_grad_(True)
+        y = ops.ConvDown2.apply(xcb, w, b, _packs(ops, dev, w, (0, 2, 3)))
+        xr, wr, br = x.clone().requires_grad_(True), w.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+        yr = F.conv3d(xr, wr, br, stride=2)
+        g = torch.randn_like(yr).to(torch.bfloat16).float()
+        yr.backward(g)
+        y.backward(cb8_from_planar(g))
+        torch.cuda.synchronize()
+        res[("down", tc)] = (rel_rms(planar_from_cb8(y.detach(), c_half), yr.detach()), rel_rms(planar_from_cb8(xcb.grad, c_full), xr.grad),
+                             rel_rms(w.grad, wr.grad))
+        # up
+        x = torch.randn(n, c_half, *half, device=dev).to(torch.bfloat16).float()
+        w = (torch.randn(c_half, c_full, 2, 2, 2, device=dev) / np.sqrt(c_half)).to(torch.bfloat16).float().requires_grad_(True)
+        b = (0.1 * torch.randn(c_full, device=dev)).requires_grad_(True)
+        xcb = cb8_from_planar(x).requires_grad_(True)
+        y = ops.ConvUp2.apply(xcb, w, b, _packs(ops, dev, w, (0, 2, 3)))
+        xr, wr, br = x.clone().requires_grad_(True), w.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+        yr = F.conv_transpose3d(xr, wr, br, stride=2)
+        g = torch.randn_like(yr).to(torch.bfloat16).float()
+        yr.backward(g)
+        y.backward(cb8_from_planar(g))
+        torch.cuda.synchronize()
+        res[("up", tc)] = (rel_rms(planar_from_cb8(y.detach(), c_full), yr.detach()), rel_rms(planar_from_cb8(xcb.grad, c_half), xr.grad),
+                           rel_rms(w.grad, wr.grad))
+    ops._TC_FWD, ops._TC_WGRAD = True, True
+    fmt = lambda t: "(y %.1e dx %.1e dw %.1e)" % t
+    print(f"[s2] n={n} full_c={c_full} half_c={c_half} half={half} down direct{fmt(res[('down', False)])} tc{fmt(res[('down', True)])} "
+          f"| up direct{fmt(res[('up', False)])} tc{fmt(res[('up', True)])}", flush=True)
+    return max(max(res[("down", True)]), max(res[("up", True)]))
 
 
 def run_wgrad(n, cin, cout, dims, kernel):
@@ -93,6 +135,12 @@ if __name__ == "__main__":
                 (6, 16, 16, (1, 256, 256), (1, 3, 3)), (2, 256, 128, (1, 16, 16), (1, 3, 3))]:
         worst = max(worst, run(*cfg))
     print("WORST tc_vs_torch", worst, flush=True)
+    if "--s2" in sys.argv:
+        ws = 0.0
+        for cfg in [(1, 16, 32, (4, 6, 8)), (2, 16, 32, (8, 6, 20)), (2, 32, 64, (14, 14, 10)), (2, 64, 128, (7, 7, 5)),
+                    (2, 128, 256, (3, 4, 2)), (4, 16, 32, (56, 56, 40)), (4, 128, 256, (7, 7, 5))]:
+            ws = max(ws, run_s2(*cfg))
+        print("WORST s2 tc_vs_torch", ws, flush=True)
     if "--wgrad" in sys.argv:
         ww = 0.0
         for cfg in [(1, 16, 16, (4, 6, 8), (3, 3, 3)), (2, 16, 16, (8, 12, 20), (3, 3, 3)), (2, 32, 32, (6, 10, 12), (3, 3, 3)),
