@@ -28,6 +28,15 @@ __device__ __forceinline__ int uf_find(volatile int* L, int v) {
   return curr;
 }
 
+// read-only root lookup for the flatten pass: with no pointer-jumping writes in flight, the only stores are final
+// roots, so every voxel ends up labelled with its root (a jumping write could otherwise overwrite a final label
+// with a non-root ancestor).
+__device__ __forceinline__ int uf_root(const volatile int* L, int v) {
+  int curr = L[v], next;
+  while (curr > (next = L[curr])) curr = next;
+  return curr;
+}
+
 __device__ __forceinline__ void uf_union(int* L, int a, int b) {
   int ra = uf_find(L, a), rb = uf_find(L, b);
   while (ra != rb) {
@@ -82,7 +91,7 @@ __global__ void cc_count_kernel(const unsigned char* __restrict__ seg, int* __re
     if (!seg[gi]) continue;
     const int n = (int)(gi / V), i = (int)(gi - (long long)n * V);
     int* Ls = L + (long long)n * V;
-    const int r = uf_find(Ls, i);
+    const int r = uf_root(Ls, i);
     Ls[i] = r;
     atomicAdd(&cnt[(long long)n * V + r], 1);
   }

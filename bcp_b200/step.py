@@ -36,8 +36,10 @@ def _pan_box(patch_size):
 
 
 def la_self_train_step(model, ema_model, optimizer, volume, label, labeled_bs=4, mask_ratio=2 / 3, u_weight=0.5,
-                       nms=1, box=None):
-    """volume [B,1,X,Y,Z] fp32 (labeled first), label [B,X,Y,Z] uint8 -- both on the GPU.  Returns device scalars."""
+                       nms=1, box=None, plab_override=None):
+    """volume [B,1,X,Y,Z] fp32 (labeled first), label [B,X,Y,Z] uint8 -- both on the GPU.  Returns device scalars.
+    ``plab_override`` (uint8 [2*sub,...]) replaces the teacher's pseudo labels AFTER the teacher pass has run; it exists
+    for parity tests, where a random-weight teacher sits at p~0.5 and bf16 noise flips labels."""
     sub = labeled_bs // 2
     label = ops.to_u8_labels(label)
     img_a, img_b = volume[:sub], volume[sub:labeled_bs]
@@ -49,6 +51,9 @@ def la_self_train_step(model, ema_model, optimizer, volume, label, labeled_bs=4,
         plab = ops.pseudo_label(t_out, "thresh", 0.5)                      # get_cut_mask
         if nms:
             plab = ops.largest_cc(plab)                                    # LargestCC_pancreas, 26-connectivity
+        plab_own = plab
+        if plab_override is not None:
+            plab = ops.to_u8_labels(plab_override).contiguous()
         plab_a, plab_b = plab[:sub], plab[sub:]
         if box is None:
             box = context_box(img_a.shape, mask_ratio)
@@ -62,7 +67,7 @@ def la_self_train_step(model, ema_model, optimizer, volume, label, labeled_bs=4,
     optimizer.zero_grad()
     loss.backward()
     optimizer.step()                                                        # SGD + EMA teacher update, fused
-    return dict(loss=loss.detach(), loss_l=loss_l.detach(), loss_u=loss_u.detach(), box=box, plab=plab, mixed=mixed,
+    return dict(loss=loss.detach(), loss_l=loss_l.detach(), loss_u=loss_u.detach(), box=box, plab=plab_own, mixed=mixed,
                 out=out.detach())
 
 
@@ -87,7 +92,8 @@ def la_pre_train_step(model, optimizer, volume, label, labeled_bs=4, mask_ratio=
     return dict(loss=loss.detach(), loss_dice=r[1].detach(), loss_ce=r[2].detach(), box=box, out=out.detach())
 
 
-def acdc_self_train_step(model, ema_model, optimizer, volume, label, labeled_bs=12, u_weight=0.5, nms=1, box=None):
+def acdc_self_train_step(model, ema_model, optimizer, volume, label, labeled_bs=12, u_weight=0.5, nms=1, box=None,
+                         plab_override=None):
     """volume [B,1,H,W] fp32, label [B,H,W] uint8 on the GPU."""
     B = volume.shape[0]
     ls, us = labeled_bs // 2, (B - labeled_bs) // 2
@@ -101,6 +107,9 @@ def acdc_self_train_step(model, ema_model, optimizer, volume, label, labeled_bs=
         plab = ops.pseudo_label(pre, "argmax")
         if nms:
             plab = ops.largest_cc(plab)                                    # per-class 8-connected largest component
+        plab_own = plab
+        if plab_override is not None:
+            plab = ops.to_u8_labels(plab_override).contiguous()
         plab_a, plab_b = plab[:us], plab[us:]
         if box is None:
             box = _acdc_box(img_a.shape)
@@ -115,18 +124,21 @@ def acdc_self_train_step(model, ema_model, optimizer, volume, label, labeled_bs=
     optimizer.zero_grad()
     loss.backward()
     optimizer.step()                                                        # SGD + state_dict EMA, fused
-    return dict(loss=loss.detach(), loss_dice=loss_dice.detach(), loss_ce=loss_ce.detach(), box=box, plab=plab,
+    return dict(loss=loss.detach(), loss_dice=loss_dice.detach(), loss_ce=loss_ce.detach(), box=box, plab=plab_own,
                 mixed=mixed, out=out.detach())
 
 
 def pan_self_train_step(net, ema_net, optimizer, img_a, lab_a, img_b, lab_b, unimg_a, unimg_b, patch_size=64,
-                        connect_mode=2, box=None):
+                        connect_mode=2, box=None, plab_override=None):
     lab_a, lab_b = ops.to_u8_labels(lab_a), ops.to_u8_labels(lab_b)
     n = img_a.shape[0]
     with torch.no_grad():
         un = torch.cat([unimg_a, unimg_b])
         t_out = ema_net(un)[0]
         plab = ops.largest_cc(ops.pseudo_label(t_out, "thresh", 0.5), connectivity=connect_mode)
+        plab_own = plab
+        if plab_override is not None:
+            plab = ops.to_u8_labels(plab_override).contiguous()
         plab_a, plab_b = plab[:n], plab[n:]
         if box is None:
             box = _pan_box(patch_size)
@@ -140,4 +152,4 @@ def pan_self_train_step(net, ema_net, optimizer, img_a, lab_a, img_b, lab_b, uni
     optimizer.zero_grad()
     loss.backward()
     optimizer.step()
-    return dict(loss=loss.detach(), loss_1=loss_1.detach(), loss_2=loss_2.detach(), box=box, plab=plab, out=out.detach())
+    return dict(loss=loss.detach(), loss_1=loss_1.detach(), loss_2=loss_2.detach(), box=box, plab=plab_own, out=out.detach())

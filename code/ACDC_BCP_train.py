@@ -1,0 +1,154 @@
+#!/usr/bin/env python
+"""ACDC BCP training entry point on the B200-native kernels.
+
+Keeps the CLI flags/defaults and the two-stage schedule of the reference's ``code/ACDC_BCP_train.py``
+(/root/reference/code/ACDC_BCP_train.py:33-56,445-477).  The self-training step body is
+``bcp_b200.step.acdc_self_train_step`` (reference :354-390); pre-training (:237-255) mixes two labeled slices and reuses
+``mix_loss(u_weight=1.0, unlab=True)`` exactly like the reference.  ``--synthetic 1`` (default) generates seeded 256x256
+slices because the ACDC h5 data / h5py are not available here; validation (val_2d.py + medpy) is out of scope.
+"""
+import argparse
+import logging
+import os
+import random
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+
+parser = argparse.ArgumentParser()
+parser.add_argument('--root_path', type=str, default='/data/byh_data/SSNet_data/ACDC', help='Name of Experiment')
+parser.add_argument('--exp', type=str, default='BCP', help='experiment_name')
+parser.add_argument('--model', type=str, default='unet', help='model_name')
+parser.add_argument('--pre_iterations', type=int, default=10000, help='maximum epoch number to train')
+parser.add_argument('--max_iterations', type=int, default=30000, help='maximum epoch number to train')
+parser.add_argument('--batch_size', type=int, default=24, help='batch_size per gpu')
+parser.add_argument('--deterministic', type=int, default=1, help='whether use deterministic training')
+parser.add_argument('--base_lr', type=float, default=0.01, help='segmentation network learning rate')
+parser.add_argument('--patch_size', type=list, default=[256, 256], help='patch size of network input')
+parser.add_argument('--seed', type=int, default=1337, help='random seed')
+parser.add_argument('--num_classes', type=int, default=4, help='output channel of network')
+parser.add_argument('--labeled_bs', type=int, default=12, help='labeled_batch_size per gpu')
+parser.add_argument('--labelnum', type=int, default=7, help='labeled data')
+parser.add_argument('--u_weight', type=float, default=0.5, help='weight of unlabeled pixels')
+parser.add_argument('--gpu', type=str, default='0', help='GPU to use')
+parser.add_argument('--consistency', type=float, default=0.1, help='consistency')
+parser.add_argument('--consistency_rampup', type=float, default=200.0, help='consistency_rampup')
+parser.add_argument('--magnitude', type=float, default=6.0, help='magnitude')
+parser.add_argument('--s_param', type=int, default=6, help='multinum of random masks')
+parser.add_argument('--synthetic', type=int, default=1)
+parser.add_argument('--max_steps', type=int, default=0)
+parser.add_argument('--log_every', type=int, default=10)
+
+
+class SyntheticACDC:
+    """{'image': [B,1,256,256] fp32 in [0,1], 'label': [B,256,256] uint8 in 0..3}, labeled slices first
+    (dataloaders/dataset.py:15-50,69-88,280-307)."""
+
+    def __init__(self, batch_size, patch, seed, device):
+        self.bs, self.patch, self.dev = batch_size, tuple(patch), device
+        self.gen = torch.Generator(device="cpu").manual_seed(seed)
+
+    def __iter__(self):
+        while True:
+            img = torch.rand((self.bs, 1) + self.patch, generator=self.gen)
+            noise = torch.randn((self.bs, 1) + self.patch, generator=self.gen)
+            sm = torch.nn.functional.avg_pool2d(noise, 9, stride=1, padding=4)[:, 0]
+            sm = sm / sm.std()
+            lab = torch.bucketize(sm, torch.tensor([0.6, 1.0, 1.5])).to(torch.uint8)
+            yield {"image": img.pin_memory().to(self.dev, non_blocking=True), "label": lab.pin_memory().to(self.dev, non_blocking=True)}
+
+
+def make_loader(args, device, rank):
+    if args.synthetic:
+        return SyntheticACDC(args.batch_size, args.patch_size, args.seed + rank, device)
+    raise RuntimeError("real ACDC data needs h5py and the dataset at --root_path (use --synthetic 1)")
+
+
+def pre_train(args, snapshot_path, device, rank):
+    from bcp_b200 import ops
+    from bcp_b200.networks.net_factory import BCP_net
+    from bcp_b200.optim import FusedSGD_EMA
+    from bcp_b200.step import _acdc_box
+    model = BCP_net(in_chns=1, class_num=args.num_classes)
+    optimizer = FusedSGD_EMA(model, None, lr=args.base_lr, momentum=0.9, weight_decay=0.0001)
+    model.train()
+    sub = args.labeled_bs // 2
+    iters = args.pre_iterations if not args.max_steps else min(args.max_steps, args.pre_iterations)
+    it = 0
+    for batch in make_loader(args, device, rank):
+        vol, lab = batch['image'][:args.labeled_bs], batch['label'][:args.labeled_bs]
+        img_a, img_b, lab_a, lab_b = vol[:sub], vol[sub:], lab[:sub], lab[sub:]
+        box = _acdc_box(img_a.shape)
+        net_input = ops.mask_mix(img_a, img_b, box)                                   # ACDC_BCP_train.py:244
+        out = model(net_input)
+        r = ops.MixLoss.apply(out, lab_a, lab_b, box, None, 1, 1.0, 1.0)              # mix_loss(u_weight=1.0, unlab=True) :249
+        loss = (r[1] + r[2]) / 2
+        optimizer.zero_grad()
+        loss.backward()
+        optimizer.step()
+        it += 1
+        if it % args.log_every == 0 and rank == 0:
+            logging.info('iteration %d: loss: %f, mix_dice: %f, mix_ce: %f' % (it, float(loss), float(r[1]), float(r[2])))
+        if it >= iters:
+            break
+    if rank == 0:
+        torch.save({'net': model.state_dict(), 'opt': optimizer.state_dict()}, os.path.join(snapshot_path, '{}_best_model.pth'.format(args.model)))
+
+
+def self_train(args, pre_snapshot_path, snapshot_path, device, rank):
+    from bcp_b200.networks.net_factory import BCP_net
+    from bcp_b200.optim import FusedSGD_EMA
+    from bcp_b200.step import acdc_self_train_step
+    model = BCP_net(in_chns=1, class_num=args.num_classes)
+    ema_model = BCP_net(in_chns=1, class_num=args.num_classes, ema=True)
+    state = torch.load(os.path.join(pre_snapshot_path, '{}_best_model.pth'.format(args.model)))
+    model.load_state_dict(state['net'])
+    ema_model.load_state_dict(state['net'])
+    optimizer = FusedSGD_EMA(model, ema_model, lr=args.base_lr, momentum=0.9, weight_decay=0.0001, ema_alpha=0.99, ema_mode="state_dict")
+    optimizer.load_state_dict(state['opt'])                                          # load_net_opt(model, optimizer, ...) :335
+    model.train()
+    ema_model.train()
+    iters = args.max_iterations if not args.max_steps else min(args.max_steps, args.max_iterations)
+    it = 0
+    for batch in make_loader(args, device, rank):
+        r = acdc_self_train_step(model, ema_model, optimizer, batch['image'], batch['label'], args.labeled_bs, args.u_weight)
+        it += 1
+        if it % args.log_every == 0 and rank == 0:
+            logging.info('iteration %d: loss: %f, mix_dice: %f, mix_ce: %f' % (it, float(r['loss']), float(r['loss_dice']), float(r['loss_ce'])))
+        if it >= iters:
+            break
+    if rank == 0:
+        torch.save(model.state_dict(), os.path.join(snapshot_path, '{}_best_model.pth'.format(args.model)))
+
+
+if __name__ == "__main__":
+    args = parser.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    if args.deterministic:
+        random.seed(args.seed)
+        np.random.seed(args.seed + rank)
+        torch.manual_seed(args.seed)
+        torch.cuda.manual_seed(args.seed)
+    pre_snapshot_path = "./model/BCP/ACDC_{}_{}_labeled/pre_train".format(args.exp, args.labelnum)
+    self_snapshot_path = "./model/BCP/ACDC_{}_{}_labeled/self_train".format(args.exp, args.labelnum)
+    if rank == 0:
+        for p in (pre_snapshot_path, self_snapshot_path):
+            os.makedirs(p, exist_ok=True)
+    logging.basicConfig(level=logging.INFO, format='[%(asctime)s.%(msecs)03d] %(message)s', datefmt='%H:%M:%S',
+                        handlers=[logging.StreamHandler(sys.stdout)])
+    logging.info(str(args))
+    pre_train(args, pre_snapshot_path, device, rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    self_train(args, pre_snapshot_path, self_snapshot_path, device, rank)

@@ -261,6 +261,7 @@ def gen_la_step(tag, shape, nsteps, box_seed, sub=1):
         for k in ("loss", "loss_l", "loss_u"):
             out[f"s{it}_{k}"] = r[k]
         out[f"s{it}_plab_a_sum"], out[f"s{it}_plab_b_sum"] = r["plab_a"].sum(), r["plab_b"].sum()
+        out[f"s{it}_plab"] = torch.cat([r["plab_a"], r["plab_b"]]).to(torch.uint8)
         out[f"s{it}_out_l"] = r["out_l"][..., ::sub, ::sub, ::sub]
         out[f"s{it}_out_u"] = r["out_u"][..., ::sub, ::sub, ::sub]
         out[f"s{it}_mixl_digest"] = tensor_digest(r["mixl"])
@@ -336,7 +337,7 @@ def gen_acdc_step():
         opt.step()
         ACDC_ns.update_model_ema(model, ema, 0.99)
         out.update({f"s{it}_loss": loss.detach(), f"s{it}_loss_dice": loss_dice.detach(), f"s{it}_loss_ce": loss_ce.detach(),
-                    f"s{it}_plab_a": plab_a, f"s{it}_out_unl": out_unl.detach(), f"s{it}_out_l": out_l.detach(),
+                    f"s{it}_plab_a": plab_a, f"s{it}_plab": torch.cat([plab_a, plab_b]).to(torch.uint8), f"s{it}_out_unl": out_unl.detach(), f"s{it}_out_l": out_l.detach(),
                     f"s{it}_grad_digest": digest_named({n: p.grad for n, p in model.named_parameters() if p.grad is not None}),
                     f"s{it}_model_digest": digest_named(model.state_dict()), f"s{it}_ema_digest": digest_named(ema.state_dict())})
         print("acdc step", it, float(loss))
@@ -378,7 +379,7 @@ def gen_pan_step():
         opt.step()
         PANU.update_ema_variables(net, ema, 0.99)
         out.update({f"s{it}_loss": loss.detach(), f"s{it}_loss_1": loss_1.detach(), f"s{it}_loss_2": loss_2.detach(),
-                    f"s{it}_plab_a_sum": plab_a.sum(), f"s{it}_out_1": o1.detach()[..., ::4, ::4, ::4],
+                    f"s{it}_plab_a_sum": plab_a.sum(), f"s{it}_plab": torch.cat([plab_a, plab_b]).to(torch.uint8), f"s{it}_out_1": o1.detach()[..., ::4, ::4, ::4],
                     f"s{it}_grad_digest": digest_named({n: p.grad for n, p in net.named_parameters() if p.grad is not None}),
                     f"s{it}_model_digest": digest_named(net.state_dict()), f"s{it}_ema_digest": digest_named(ema.state_dict())})
         print("pan step", it, float(loss), "t=%.1fs" % (time.time() - t0))

@@ -16,6 +16,8 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module")
 def dev():
+    torch.backends.cudnn.allow_tf32 = False          # the torch references below must be true fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
     return torch.device("cuda:0")
 
 
