@@ -138,7 +138,7 @@ class Encoder(nn.Module):
         scale = None
         if self.has_dropout and self.dropout.training:
             n, c = x4_dw.shape[0], x4_dw.shape[1] * 8
-            scale = NetRuntime.channel_dropout_scale(self.dropout, n, c, x4_dw.device)
+            scale = NetRuntime.channel_dropout_scale(self.dropout, n, c, x4_dw.device, self.block_five._rt.spg)
         x5 = self.block_five(x4_dw, chan_scale=scale)
         return [x1, x2, x3, x4, x5]
 
@@ -163,7 +163,7 @@ class Decoder(nn.Module):
         scale = None
         if self.has_dropout and self.dropout.training:
             n, c = x8_up.shape[0], x8_up.shape[1] * 8
-            scale = NetRuntime.channel_dropout_scale(self.dropout, n, c, x8_up.device)
+            scale = NetRuntime.channel_dropout_scale(self.dropout, n, c, x8_up.device, self.block_nine._rt.spg)
         x9 = self.block_nine(x8_up, chan_scale=scale)
         out_seg = ops.Head.apply(x9, self.out_conv.weight, self.out_conv.bias, False)
         return out_seg, x8_up

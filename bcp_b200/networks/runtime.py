@@ -154,23 +154,28 @@ class NetRuntime:
 
     # ---- dropout masks ------------------------------------------------------------------------
     @staticmethod
-    def channel_dropout_scale(mod, n, c, device):
-        """Dropout3d: one Bernoulli per (n, c), value 0 or 1/(1-p) (networks/VNet.py:165,211)."""
-        if hasattr(mod, "make_mask"):                      # injected (parity tests)
-            return mod.make_mask((n, c, 1, 1, 1), device).reshape(n, c).float().contiguous()
+    def channel_dropout_scale(mod, n, c, device, spg=None):
+        """Dropout3d: one Bernoulli per (n, c), value 0 or 1/(1-p) (networks/VNet.py:165,211).  With an injected mask
+        provider (parity tests) one mask is drawn per reference forward call, i.e. per group of ``spg`` samples."""
+        if hasattr(mod, "make_mask"):
+            spg = spg or n
+            parts = [mod.make_mask((spg, c, 1, 1, 1), device).reshape(spg, c).float() for _ in range(n // spg)]
+            return torch.cat(parts).contiguous()
         p = float(mod.p)
         return torch.empty(n, c, dtype=torch.float32, device=device).bernoulli_(1.0 - p).div_(1.0 - p)
 
     @staticmethod
-    def element_dropout_keep(mod, n, c, spatial, device):
+    def element_dropout_keep(mod, n, c, spatial, device, spg=None):
         """nn.Dropout: uint8 keep flags in CB8 order [N][C/8][X][Y][Z][8] plus the 1/(1-p) scale."""
         p = float(mod.p)
         if p <= 0.0:
             return None, 1.0
         x, y, z = spatial
         if hasattr(mod, "make_mask"):
-            shape = (n, c, y, z) if x == 1 else (n, c, x, y, z)
-            keep = (mod.make_mask(shape, device) > 0).to(torch.uint8).reshape(n, c // 8, 8, x, y, z)
+            spg = spg or n
+            shape = (spg, c, y, z) if x == 1 else (spg, c, x, y, z)
+            full = torch.cat([mod.make_mask(shape, device) for _ in range(n // spg)])
+            keep = (full > 0).to(torch.uint8).reshape(n, c // 8, 8, x, y, z)
             keep = keep.permute(0, 1, 3, 4, 5, 2).contiguous()
         else:
             keep = torch.empty((n, c // 8, x, y, z, 8), dtype=torch.uint8, device=device).bernoulli_(1.0 - p)

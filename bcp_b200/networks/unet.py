@@ -53,7 +53,7 @@ class ConvBlock(nn.Module):
         keep, scale = None, 1.0
         if drop.training:
             n, cb, x, yy, z, _ = y.shape
-            keep, scale = NetRuntime.element_dropout_keep(drop, n, cb * 8, (x, yy, z), y.device)
+            keep, scale = NetRuntime.element_dropout_keep(drop, n, cb * 8, (x, yy, z), y.device, rt.spg)
         a = self._bn_act(y, bn0, act0.negative_slope, keep, scale)
         y = ops.ConvSame.apply(a, c1.weight, c1.bias, rt.pack(c1), (1, 3, 3))
         return self._bn_act(y, bn1, act1.negative_slope)

@@ -143,6 +143,14 @@ def run_native(args):
         barrier()
         return ms, out
 
+    if args.profile:          # under ncu: one warm-up + one step, nothing else (numbers printed here are NOT bench values)
+        step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.nvtx.range_push("profiled_step")
+        step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.nvtx.range_pop()
+        return
     for _ in range(max(args.warmup, 3)):
         r = step_resident()
     sampler = ClockSampler(local)
@@ -291,6 +299,7 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="one warm-up + one step only (for ncu launch lists)")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)
