@@ -34,6 +34,7 @@ struct TcParams {
   int nchunks;         // Cin / 16
   int T;               // taps
   int SA, SB;          // ring depths
+  int TG;              // taps per B stage (divides T)
   int AS;              // accumulator stages in TMEM (1 or 2)
   int tmem_cols;       // power of two >= AS*MT*Cout
   unsigned slotA_bytes, stageB_bytes;
@@ -156,12 +157,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16* __
           mbar_expect_tx(full_a + 8 * sa, a_bytes);
           tma_load_5d(a_base + sa * p.slotA_bytes, &tmap, full_a + 8 * sa, 0, z0, y0, x0, n * Cib + 2 * c);
           ++ia;
-          for (int t = 0; t < p.T; ++t) {
+          for (int t = 0; t < p.T; t += p.TG) {
             const uint32_t sb = ib % p.SB, pb = (ib / p.SB) & 1;
             mbar_wait(empty_b + 8 * sb, pb ^ 1);
             mbar_expect_tx(full_b + 8 * sb, p.stageB_bytes);
-            const __nv_bfloat16* src = wpack + ((size_t)t * Cib + 2 * c) * (size_t)p.Cout * 8;
-            bulk_load(b_base + sb * p.stageB_bytes, src, p.stageB_bytes, full_b + 8 * sb);
+            const uint32_t tap_bytes = p.stageB_bytes / p.TG;
+            for (int g = 0; g < p.TG; ++g) {
+              const __nv_bfloat16* src = wpack + ((size_t)(t + g) * Cib + 2 * c) * (size_t)p.Cout * 8;
+              bulk_load(b_base + sb * p.stageB_bytes + g * tap_bytes, src, tap_bytes, full_b + 8 * sb);
+            }
             ++ib;
           }
         }
@@ -171,7 +175,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16* __
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Cout >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t lboA = (uint32_t)p.rows_h * 16u, lboB = (uint32_t)p.Cout * 16u;
+      // descriptors differ only in their 14-bit start-address field (16-byte units): build the constant part once and
+      // add row offsets -- the issuing lane then spends a handful of integer ops per MMA
+      const uint64_t adesc0 = make_desc(0, (uint32_t)p.rows_h * 16u, 128u);
+      const uint64_t bdesc0 = make_desc(0, (uint32_t)p.Cout * 16u, 128u);
+      const uint32_t tap_rows_b = (p.stageB_bytes / p.TG) >> 4;          // 16-byte units per tap inside a B stage
       uint32_t ia = 0, ib = 0, it = 0;
       for (int brick = blockIdx.x; brick < p.nbricks; brick += gridDim.x, ++it) {
         const uint32_t as = it % p.AS, ap = (it / p.AS) & 1;
@@ -182,18 +190,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16* __
           const uint32_t sa = ia % p.SA, pa = (ia / p.SA) & 1;
           mbar_wait(full_a + 8 * sa, pa);
           tc_fence_after();
-          const uint32_t a_slot = a_base + sa * p.slotA_bytes;
-          for (int t = 0; t < p.T; ++t) {
+          const uint64_t a_slot = adesc0 + (uint64_t)((a_base + sa * p.slotA_bytes) >> 4);
+          int tx = 0, ty = 0, tz = 0;
+          for (int t = 0; t < p.T; t += p.TG) {
             const uint32_t sb = ib % p.SB, pb = (ib / p.SB) & 1;
             mbar_wait(full_b + 8 * sb, pb);
             tc_fence_after();
-            const int tz = t % 3, ty = (t / 3) % 3, tx = t / 9;
-            const uint32_t tapoff = (uint32_t)((tx * p.HY + ty) * p.HZ + tz) * 16u;
-            const uint64_t bdesc = make_desc(b_base + sb * p.stageB_bytes, lboB, 128u);
-            const uint32_t acc = (c | t) ? 1u : 0u;
-            for (int mt = 0; mt < p.MT; ++mt) {
-              const uint64_t adesc = make_desc(a_slot + tapoff + (uint32_t)mt * 2048u, lboA, 128u);
-              umma_bf16(d0 + (uint32_t)(mt * p.Cout), adesc, bdesc, idesc, acc);
+            uint64_t bdesc = bdesc0 + (uint64_t)((b_base + sb * p.stageB_bytes) >> 4);
+            for (int g = 0; g < p.TG; ++g) {
+              const uint64_t adesc_t = a_slot + (uint64_t)((tx * p.HY + ty) * p.HZ + tz);
+              const uint32_t acc = (c | t | g) ? 1u : 0u;
+              uint32_t d = d0;
+#pragma unroll 4
+              for (int mt = 0; mt < p.MT; ++mt) {
+                umma_bf16(d, adesc_t + (uint64_t)(mt * 128), bdesc, idesc, acc);
+                d += (uint32_t)p.Cout;
+              }
+              bdesc += tap_rows_b;
+              if (++tz == 3) { tz = 0; if (++ty == 3) { ty = 0; ++tx; } }
             }
             umma_commit(empty_b + 8 * sb);
             ++ib;
@@ -526,26 +540,35 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     if (lane == 0 && has_work) {
       // M = 128, N = Cin, both operands MN-major (bits 15, 16)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.Cin >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t sboA = (uint32_t)p.rows_dy * 16u, sboB = (uint32_t)p.rows_a * 16u;
+      // constant descriptor parts; per MMA only the 16-byte-unit start address changes
+      const uint64_t adesc0 = make_desc(0, 128u, (uint32_t)p.rows_dy * 16u);
+      const uint64_t bdesc0 = make_desc(0, 128u, (uint32_t)p.rows_a * 16u);
+      // per-tap row offset of this CTA's taps (same-conv: halo shift; stride-2: separate gathered brick per tap)
+      uint32_t tapoff[27];
+      for (int tl = 0; tl < 27; ++tl) {
+        const int t = t0 + tl;
+        const int tz = t % 3, ty = (t / 3) % 3, tx = t / 9;
+        tapoff[tl] = p.s2 ? (uint32_t)tl * (p.tap_bytes >> 4) : (uint32_t)((tx * p.HY + ty) * p.HZ + tz);
+      }
       uint32_t it = 0;
       uint32_t acc = 0;
+      const int row_step_y = p.s2 ? p.ZP : p.HZ;                 // B-row distance between consecutive lines
+      const int row_step_x = p.s2 ? p.BY * p.ZP : p.HY * p.HZ;
       for (int brick = split; brick < p.nbricks; brick += p.splits, ++it) {
         const uint32_t s = it % p.S, ph = (it / p.S) & 1;
         mbar_wait(full + 8 * s, ph);
         tc_fence_after();
         const uint32_t a_slot = sbase + s * p.slot_bytes, dy_slot = a_slot + p.a_alloc_bytes;
+        const uint64_t a_slot_d = adesc0 + (uint64_t)(dy_slot >> 4), b_slot_d = bdesc0 + (uint64_t)(a_slot >> 4);
         for (int ix = 0; ix < p.BX; ++ix) {
           for (int iy = 0; iy < p.BY; ++iy) {
+            const uint64_t arow = a_slot_d + (uint64_t)((ix * p.BY + iy) * p.ZP);
+            const uint64_t brow = b_slot_d + (uint64_t)(ix * row_step_x + iy * row_step_y);
             for (int zc = 0; zc < p.ZP; zc += 16) {
-              const uint32_t dy_row = (uint32_t)((ix * p.BY + iy) * p.ZP + zc);
-              const uint64_t adesc = make_desc(dy_slot + dy_row * 16u, 128u, sboA);
-              for (int tl = 0; tl < ntap; ++tl) {
-                const int t = t0 + tl;
-                const int tz = t % 3, ty = (t / 3) % 3, tx = t / 9;
-                const uint32_t a_row = p.s2 ? dy_row : (uint32_t)(((ix + tx) * p.HY + iy + ty) * p.HZ + tz + zc);
-                const uint64_t bdesc = make_desc(a_slot + (p.s2 ? (uint32_t)tl * p.tap_bytes : 0u) + a_row * 16u, 128u, sboB);
-                umma_bf16(tmem_base + (uint32_t)(tl * p.Cin), adesc, bdesc, idesc, acc);
-              }
+              const uint64_t adesc = arow + (uint64_t)zc, bz = brow + (uint64_t)zc;
+#pragma unroll 3
+              for (int tl = 0; tl < ntap; ++tl)
+                umma_bf16(tmem_base + (uint32_t)(tl * p.Cin), adesc, bz + (uint64_t)tapoff[tl], idesc, acc);
               acc = 1;
             }
           }
@@ -629,7 +652,14 @@ static bool plan(TcParams& p, int nsm) {
   const int T = p.kx * 9;
   p.T = T;
   p.nchunks = p.Cin / 16;
-  p.stageB_bytes = (unsigned)p.Cout * 32u;
+  {
+    // several taps share one weight stage (fewer barrier round trips for the issuing lane): largest group <= 32 KB
+    const int cands[4] = {T, 9, 3, 1};
+    p.TG = 1;
+    for (int i = 0; i < 4; ++i)
+      if (cands[i] <= T && T % cands[i] == 0 && cands[i] * p.Cout * 32 <= 32 * 1024) { p.TG = cands[i]; break; }
+  }
+  p.stageB_bytes = (unsigned)p.TG * (unsigned)p.Cout * 32u;
   double best = 1e300;
   TcParams bestp = p;
   bool found = false;
@@ -654,8 +684,8 @@ static bool plan(TcParams& p, int nsm) {
         if (MT * p.Cout > 512) break;
         const long long rows_alloc = (long long)MT * 128 + ((long long)(p.kx - 1) * HY + 2) * HZ + 2;
         const long long slotA = ((rows_h + (rows_alloc > rows_h ? rows_alloc : rows_h)) * 16 + 127) / 128 * 128;
-        // ring depths: at least 2 A slots (3 preferred), 4 B stages
-        int SB = 4;
+        // ring depths: at least 2 A slots (3 preferred), 3 B stages
+        int SB = 3;
         long long avail = (long long)SMEM_BUDGET - 1024 - (long long)SB * p.stageB_bytes;
         int SA = (int)(avail / slotA);
         if (SA < 2) break;
@@ -664,7 +694,7 @@ static bool plan(TcParams& p, int nsm) {
         const long long nb = (long long)p.N * nbx * nby * nbz;
         const long long waves = (nb + nsm - 1) / nsm;
         const double mma_cyc = (double)MT * T * p.nchunks * per_mma;
-        const double load_cyc = (double)rows_h * p.Cin * 2.0 / 40.0 + (double)T * p.nchunks * p.stageB_bytes / 40.0;
+        const double load_cyc = (double)rows_h * p.Cin * 2.0 / 40.0 + (double)T * p.nchunks * p.Cout * 32.0 / 40.0;
         const double epi_cyc = (double)MT * p.Cout * 12.0;
         const int AS = (2 * MT * p.Cout <= 512) ? 2 : 1;
         double brick = (mma_cyc > load_cyc ? mma_cyc : load_cyc) + (AS == 2 ? 0.0 : epi_cyc) + 1500.0;
