@@ -35,6 +35,7 @@ struct TcParams {
   int T;               // taps
   int SA, SB;          // ring depths
   int TG;              // taps per B stage (divides T)
+  int NS, Ns;          // output-channel slices per brick (work item = brick x slice) and channels per slice
   int AS;              // accumulator stages in TMEM (1 or 2)
   int tmem_cols;       // power of two >= AS*MT*Cout
   unsigned slotA_bytes, stageB_bytes;
@@ -85,6 +86,17 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// One lane of a fully converged warp (warp-uniform control flow around it lets ptxas keep descriptors/addresses in
+// uniform registers; issuing from inside `if (lane == 0)` makes it wrap every UTCHMMA/UTMALDG in an election loop).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -138,13 +150,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16* __
 
   const int Cib = p.Cin >> 3, Cob = p.Cout >> 3;
   const int bricks_per_n = p.nbx * p.nby * p.nbz;
+  const int nitems = p.nbricks * p.NS;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (warp-uniform; one elected lane issues)
+    {
       uint32_t ia = 0, ib = 0;                       // running item counters -> slot = i % S, phase = (i / S) & 1
       const uint32_t a_bytes = (uint32_t)p.rows_h * 32u;
-      for (int brick = blockIdx.x; brick < p.nbricks; brick += gridDim.x) {
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int brick = item / p.NS, n0 = (item - brick * p.NS) * p.Ns;
         const int n = brick / bricks_per_n;
         int r = brick - n * bricks_per_n;
         const int bz = r % p.nbz; r /= p.nbz;
@@ -154,38 +168,50 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16* __
         for (int c = 0; c < p.nchunks; ++c) {
           const uint32_t sa = ia % p.SA, pa = (ia / p.SA) & 1;
           mbar_wait(empty_a + 8 * sa, pa ^ 1);
-          mbar_expect_tx(full_a + 8 * sa, a_bytes);
-          tma_load_5d(a_base + sa * p.slotA_bytes, &tmap, full_a + 8 * sa, 0, z0, y0, x0, n * Cib + 2 * c);
+          if (elect_one()) {
+            mbar_expect_tx(full_a + 8 * sa, a_bytes);
+            tma_load_5d(a_base + sa * p.slotA_bytes, &tmap, full_a + 8 * sa, 0, z0, y0, x0, n * Cib + 2 * c);
+          }
+          __syncwarp();
           ++ia;
           for (int t = 0; t < p.T; t += p.TG) {
             const uint32_t sb = ib % p.SB, pb = (ib / p.SB) & 1;
             mbar_wait(empty_b + 8 * sb, pb ^ 1);
-            mbar_expect_tx(full_b + 8 * sb, p.stageB_bytes);
-            const uint32_t tap_bytes = p.stageB_bytes / p.TG;
-            for (int g = 0; g < p.TG; ++g) {
-              const __nv_bfloat16* src = wpack + ((size_t)(t + g) * Cib + 2 * c) * (size_t)p.Cout * 8;
-              bulk_load(b_base + sb * p.stageB_bytes + g * tap_bytes, src, tap_bytes, full_b + 8 * sb);
+            if (elect_one()) {
+              mbar_expect_tx(full_b + 8 * sb, p.stageB_bytes);
+              const uint32_t tap_bytes = p.stageB_bytes / p.TG;
+              for (int g = 0; g < p.TG; ++g) {
+                const __nv_bfloat16* src = wpack + (((size_t)(t + g) * Cib + 2 * c) * (size_t)p.Cout + n0) * 8;
+                const uint32_t dst = b_base + sb * p.stageB_bytes + g * tap_bytes;
+                if (p.NS == 1) {
+                  bulk_load(dst, src, tap_bytes, full_b + 8 * sb);
+                } else {                                  // a channel slice is contiguous per 8-channel plane only
+                  bulk_load(dst, src, tap_bytes / 2, full_b + 8 * sb);
+                  bulk_load(dst + tap_bytes / 2, src + (size_t)p.Cout * 8, tap_bytes / 2, full_b + 8 * sb);
+                }
+              }
             }
+            __syncwarp();
             ++ib;
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Cout >> 3) << 17) | ((128u >> 4) << 24);
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform; one elected lane issues)
+    {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Ns >> 3) << 17) | ((128u >> 4) << 24);
       // descriptors differ only in their 14-bit start-address field (16-byte units): build the constant part once and
       // add row offsets -- the issuing lane then spends a handful of integer ops per MMA
       const uint64_t adesc0 = make_desc(0, (uint32_t)p.rows_h * 16u, 128u);
-      const uint64_t bdesc0 = make_desc(0, (uint32_t)p.Cout * 16u, 128u);
+      const uint64_t bdesc0 = make_desc(0, (uint32_t)p.Ns * 16u, 128u);
       const uint32_t tap_rows_b = (p.stageB_bytes / p.TG) >> 4;          // 16-byte units per tap inside a B stage
       uint32_t ia = 0, ib = 0, it = 0;
-      for (int brick = blockIdx.x; brick < p.nbricks; brick += gridDim.x, ++it) {
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
         const uint32_t as = it % p.AS, ap = (it / p.AS) & 1;
         mbar_wait(tmem_empty + 8 * as, ap ^ 1);
         tc_fence_after();
-        const uint32_t d0 = tmem_base + as * (uint32_t)(p.MT * p.Cout);
+        const uint32_t d0 = tmem_base + as * (uint32_t)(p.MT * p.Ns);
         for (int c = 0; c < p.nchunks; ++c) {
           const uint32_t sa = ia % p.SA, pa = (ia / p.SA) & 1;
           mbar_wait(full_a + 8 * sa, pa);
@@ -197,25 +223,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16* __
             mbar_wait(full_b + 8 * sb, pb);
             tc_fence_after();
             uint64_t bdesc = bdesc0 + (uint64_t)((b_base + sb * p.stageB_bytes) >> 4);
+            const bool leader = elect_one();
             for (int g = 0; g < p.TG; ++g) {
               const uint64_t adesc_t = a_slot + (uint64_t)((tx * p.HY + ty) * p.HZ + tz);
               const uint32_t acc = (c | t | g) ? 1u : 0u;
-              uint32_t d = d0;
+              if (leader) {
+                uint32_t d = d0;
 #pragma unroll 4
-              for (int mt = 0; mt < p.MT; ++mt) {
-                umma_bf16(d, adesc_t + (uint64_t)(mt * 128), bdesc, idesc, acc);
-                d += (uint32_t)p.Cout;
+                for (int mt = 0; mt < p.MT; ++mt) {
+                  umma_bf16(d, adesc_t + (uint64_t)(mt * 128), bdesc, idesc, acc);
+                  d += (uint32_t)p.Ns;
+                }
               }
               bdesc += tap_rows_b;
               if (++tz == 3) { tz = 0; if (++ty == 3) { ty = 0; ++tx; } }
             }
-            umma_commit(empty_b + 8 * sb);
+            if (leader) umma_commit(empty_b + 8 * sb);
+            __syncwarp();
             ++ib;
           }
-          umma_commit(empty_a + 8 * sa);
+          if (elect_one()) umma_commit(empty_a + 8 * sa);
+          __syncwarp();
           ++ia;
         }
-        umma_commit(tmem_full + 8 * as);
+        if (elect_one()) umma_commit(tmem_full + 8 * as);
+        __syncwarp();
       }
     }
   } else {
@@ -223,7 +255,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16* __
     const int q = warp & 3;
     uint32_t it = 0;
     const long long S = (long long)p.X * p.Y * p.Z;
-    for (int brick = blockIdx.x; brick < p.nbricks; brick += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+      const int brick = item / p.NS, n0 = (item - brick * p.NS) * p.Ns;
       const int n = brick / bricks_per_n;
       int r = brick - n * bricks_per_n;
       const int bz = r % p.nbz; r /= p.nbz;
@@ -232,7 +265,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16* __
       const uint32_t as = it % p.AS, ap = (it / p.AS) & 1;
       mbar_wait(tmem_full + 8 * as, ap);
       tc_fence_after();
-      const uint32_t d0 = tmem_base + as * (uint32_t)(p.MT * p.Cout) + ((uint32_t)(q * 32) << 16);
+      const uint32_t d0 = tmem_base + as * (uint32_t)(p.MT * p.Ns) + ((uint32_t)(q * 32) << 16);
       for (int mt = 0; mt < p.MT; ++mt) {
         const int L = mt * 128 + q * 32 + lane;
         const int iz = L % p.HZ;
@@ -241,15 +274,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16* __
         const int x = bx * p.BX + ix, y = by * p.BY + iy, z = bz * p.BZ + iz;
         const bool valid = (ix < p.BX) && (iy < p.BY) && (iz < p.BZ) && (x < p.X) && (y < p.Y) && (z < p.Z);
         const long long sp = ((long long)x * p.Y + y) * p.Z + z;
-        for (int c16 = 0; c16 < p.Cout; c16 += 16) {
+        for (int c16 = 0; c16 < p.Ns; c16 += 16) {
           uint32_t v[16];
-          tmem_ld16(d0 + (uint32_t)(mt * p.Cout + c16), v);
+          tmem_ld16(d0 + (uint32_t)(mt * p.Ns + c16), v);
           tmem_ld_wait();
           if (valid) {
             float f[16];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v[k]) + (bias ? __ldg(bias + c16 + k) : 0.f);
-            uint4* dst = out + ((long long)n * Cob + (c16 >> 3)) * S + sp;
+            for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v[k]) + (bias ? __ldg(bias + n0 + c16 + k) : 0.f);
+            uint4* dst = out + ((long long)n * Cob + ((n0 + c16) >> 3)) * S + sp;
             dst[0] = pack8(f);
             dst[S] = pack8(f + 8);
           }
@@ -324,7 +357,7 @@ conv_tc_s2_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16*
   const int ntiles = p.nbricks * p.npieces;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       uint32_t ia = 0, ib = 0;
       const uint32_t a_bytes = (uint32_t)p.rows * 32u;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -339,30 +372,33 @@ conv_tc_s2_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16*
           const int t = (p.mode == 1) ? (k & 7) : 0;
           const uint32_t sa = ia % p.SA, pa = (ia / p.SA) & 1;
           mbar_wait(empty_a + 8 * sa, pa ^ 1);
-          mbar_expect_tx(full_a + 8 * sa, a_bytes);
-          if (p.mode == 1)
-            tma_load_5d(a_base + sa * p.slotA_bytes, &tmap, full_a + 8 * sa, 0, 2 * bz * p.BZ + (t & 1), 2 * by * p.BY + ((t >> 1) & 1),
-                        2 * bx * p.BX + (t >> 2), n * Cib + 2 * c);
-          else
-            tma_load_5d(a_base + sa * p.slotA_bytes, &tmap, full_a + 8 * sa, 0, bz * p.BZ, by * p.BY, bx * p.BX, n * Cib + 2 * c);
-          ++ia;
           const uint32_t sb = ib % p.SB, pb = (ib / p.SB) & 1;
           mbar_wait(empty_b + 8 * sb, pb ^ 1);
-          mbar_expect_tx(full_b + 8 * sb, p.stageB_bytes);
-          if (p.mode == 1) {
-            bulk_load(b_base + sb * p.stageB_bytes, wpack + ((size_t)t * Cib + 2 * c) * (size_t)p.Cout * 8, p.stageB_bytes, full_b + 8 * sb);
-          } else {
-            const uint32_t half = p.stageB_bytes / 2;
-            const size_t t0 = (size_t)piece * p.TPc;
-            bulk_load(b_base + sb * p.stageB_bytes, wpack + (((size_t)(2 * c) * 8 + t0) * p.Cout) * 8, half, full_b + 8 * sb);
-            bulk_load(b_base + sb * p.stageB_bytes + half, wpack + (((size_t)(2 * c + 1) * 8 + t0) * p.Cout) * 8, half, full_b + 8 * sb);
+          if (elect_one()) {
+            mbar_expect_tx(full_a + 8 * sa, a_bytes);
+            if (p.mode == 1)
+              tma_load_5d(a_base + sa * p.slotA_bytes, &tmap, full_a + 8 * sa, 0, 2 * bz * p.BZ + (t & 1), 2 * by * p.BY + ((t >> 1) & 1),
+                          2 * bx * p.BX + (t >> 2), n * Cib + 2 * c);
+            else
+              tma_load_5d(a_base + sa * p.slotA_bytes, &tmap, full_a + 8 * sa, 0, bz * p.BZ, by * p.BY, bx * p.BX, n * Cib + 2 * c);
+            mbar_expect_tx(full_b + 8 * sb, p.stageB_bytes);
+            if (p.mode == 1) {
+              bulk_load(b_base + sb * p.stageB_bytes, wpack + ((size_t)t * Cib + 2 * c) * (size_t)p.Cout * 8, p.stageB_bytes, full_b + 8 * sb);
+            } else {
+              const uint32_t half = p.stageB_bytes / 2;
+              const size_t t0 = (size_t)piece * p.TPc;
+              bulk_load(b_base + sb * p.stageB_bytes, wpack + (((size_t)(2 * c) * 8 + t0) * p.Cout) * 8, half, full_b + 8 * sb);
+              bulk_load(b_base + sb * p.stageB_bytes + half, wpack + (((size_t)(2 * c + 1) * 8 + t0) * p.Cout) * 8, half, full_b + 8 * sb);
+            }
           }
+          __syncwarp();
+          ++ia;
           ++ib;
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Npiece >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t lboA = (uint32_t)p.rows * 16u, lboB = (uint32_t)p.Npiece * 16u;
       uint32_t ia = 0, ib = 0, it = 0;
@@ -378,15 +414,18 @@ conv_tc_s2_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16*
           mbar_wait(full_b + 8 * sb, pb);
           tc_fence_after();
           const uint64_t bdesc = make_desc(b_base + sb * p.stageB_bytes, lboB, 128u);
-          for (int mt = 0; mt < p.MT; ++mt) {
-            const uint64_t adesc = make_desc(a_base + sa * p.slotA_bytes + (uint32_t)mt * 2048u, lboA, 128u);
-            umma_bf16(d0 + (uint32_t)(mt * p.Npiece), adesc, bdesc, idesc, k ? 1u : 0u);
+          const uint64_t adesc = make_desc(a_base + sa * p.slotA_bytes, lboA, 128u);
+          if (elect_one()) {
+            for (int mt = 0; mt < p.MT; ++mt)
+              umma_bf16(d0 + (uint32_t)(mt * p.Npiece), adesc + (uint64_t)(mt * 128), bdesc, idesc, k ? 1u : 0u);
+            umma_commit(empty_a + 8 * sa);
+            umma_commit(empty_b + 8 * sb);
           }
-          umma_commit(empty_a + 8 * sa);
-          umma_commit(empty_b + 8 * sb);
+          __syncwarp();
           ++ia; ++ib;
         }
-        umma_commit(tmem_full + 8 * as);
+        if (elect_one()) umma_commit(tmem_full + 8 * as);
+        __syncwarp();
       }
     }
   } else {
@@ -513,7 +552,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   const bool has_work = split < p.nbricks;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       uint32_t it = 0;
       for (int brick = split; brick < p.nbricks; brick += p.splits, ++it) {
         const int n = brick / bricks_per_n;
@@ -522,6 +561,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         const uint32_t s = it % p.S, ph = (it / p.S) & 1;
         mbar_wait(empty + 8 * s, ph ^ 1);
         const uint32_t slot = sbase + s * p.slot_bytes;
+        if (elect_one()) {
         if (p.s2) {
           mbar_expect_tx(full + 8 * s, (uint32_t)ntap * p.tap_bytes + p.dy_tx_bytes);
           for (int tl = 0; tl < ntap; ++tl) {
@@ -534,22 +574,25 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           tma_load_5d(slot, &map_a, full + 8 * s, 0, -1, by * p.BY - 1, bx * p.BX - (p.kx >> 1), n * Cib);
         }
         tma_load_5d(slot + p.a_alloc_bytes, &map_dy, full + 8 * s, 0, 0, by * p.BY, bx * p.BX, n * Cob + mh * 16);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && has_work) {
+    if (has_work) {
       // M = 128, N = Cin, both operands MN-major (bits 15, 16)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.Cin >> 3) << 17) | ((128u >> 4) << 24);
       // constant descriptor parts; per MMA only the 16-byte-unit start address changes
       const uint64_t adesc0 = make_desc(0, 128u, (uint32_t)p.rows_dy * 16u);
       const uint64_t bdesc0 = make_desc(0, 128u, (uint32_t)p.rows_a * 16u);
       // per-tap row offset of this CTA's taps (same-conv: halo shift; stride-2: separate gathered brick per tap)
-      uint32_t tapoff[27];
-      for (int tl = 0; tl < 27; ++tl) {
-        const int t = t0 + tl;
+      uint32_t* tapoff = reinterpret_cast<uint32_t*>(smem + p.offBar + 8 * (2 * p.S + 1) + 16);
+      if (lane < 27) {
+        const int t = t0 + lane;
         const int tz = t % 3, ty = (t / 3) % 3, tx = t / 9;
-        tapoff[tl] = p.s2 ? (uint32_t)tl * (p.tap_bytes >> 4) : (uint32_t)((tx * p.HY + ty) * p.HZ + tz);
+        tapoff[lane] = p.s2 ? (uint32_t)lane * (p.tap_bytes >> 4) : (uint32_t)((tx * p.HY + ty) * p.HZ + tz);
       }
+      __syncwarp();
       uint32_t it = 0;
       uint32_t acc = 0;
       const int row_step_y = p.s2 ? p.ZP : p.HZ;                 // B-row distance between consecutive lines
@@ -560,6 +603,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         tc_fence_after();
         const uint32_t a_slot = sbase + s * p.slot_bytes, dy_slot = a_slot + p.a_alloc_bytes;
         const uint64_t a_slot_d = adesc0 + (uint64_t)(dy_slot >> 4), b_slot_d = bdesc0 + (uint64_t)(a_slot >> 4);
+        const bool leader = elect_one();
+        if (leader)
         for (int ix = 0; ix < p.BX; ++ix) {
           for (int iy = 0; iy < p.BY; ++iy) {
             const uint64_t arow = a_slot_d + (uint64_t)((ix * p.BY + iy) * p.ZP);
@@ -573,9 +618,11 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             }
           }
         }
-        umma_commit(empty + 8 * s);
+        if (leader) umma_commit(empty + 8 * s);
+        __syncwarp();
       }
-      umma_commit(tmem_full);
+      if (elect_one()) umma_commit(tmem_full);
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;
@@ -652,61 +699,67 @@ static bool plan(TcParams& p, int nsm) {
   const int T = p.kx * 9;
   p.T = T;
   p.nchunks = p.Cin / 16;
-  {
-    // several taps share one weight stage (fewer barrier round trips for the issuing lane): largest group <= 32 KB
-    const int cands[4] = {T, 9, 3, 1};
-    p.TG = 1;
-    for (int i = 0; i < 4; ++i)
-      if (cands[i] <= T && T % cands[i] == 0 && cands[i] * p.Cout * 32 <= 32 * 1024) { p.TG = cands[i]; break; }
-  }
-  p.stageB_bytes = (unsigned)p.TG * (unsigned)p.Cout * 32u;
   double best = 1e300;
   TcParams bestp = p;
   bool found = false;
-  const double per_mma = (p.Cout / 2.0 > 32.0 + p.Cout / 4.0) ? p.Cout / 2.0 : 32.0 + p.Cout / 4.0;
   int bz_opts[4];
   int nz = 0;
   for (int d = 1; d <= 8 && nz < 4; d *= 2) {
     const int bz = (p.Z + d - 1) / d;
     if (bz + 2 <= 256 && (nz == 0 || bz_opts[nz - 1] != bz)) bz_opts[nz++] = bz;
   }
-  for (int zi = 0; zi < nz; ++zi) {
-    const int BZ = bz_opts[zi], HZ = BZ + 2;
-    for (int BY = 1; BY <= p.Y && BY + 2 <= 256; ++BY) {
-      const int HY = BY + 2;
-      const int bxmax = (p.kx == 1) ? 1 : p.X;
-      for (int BX = 1; BX <= bxmax; ++BX) {
-        const int HX = BX + p.kx - 1;
-        if (HX > 256) break;
-        const long long rows_h = (long long)HX * HY * HZ;
-        const long long lmax = ((long long)(BX - 1) * HY + (BY - 1)) * HZ + BZ;
-        const int MT = (int)((lmax + 127) / 128);
-        if (MT * p.Cout > 512) break;
-        const long long rows_alloc = (long long)MT * 128 + ((long long)(p.kx - 1) * HY + 2) * HZ + 2;
-        const long long slotA = ((rows_h + (rows_alloc > rows_h ? rows_alloc : rows_h)) * 16 + 127) / 128 * 128;
-        // ring depths: at least 2 A slots (3 preferred), 3 B stages
-        int SB = 3;
-        long long avail = (long long)SMEM_BUDGET - 1024 - (long long)SB * p.stageB_bytes;
-        int SA = (int)(avail / slotA);
-        if (SA < 2) break;
-        if (SA > 4) SA = 4;
-        const int nbx = (p.X + BX - 1) / BX, nby = (p.Y + BY - 1) / BY, nbz = (p.Z + BZ - 1) / BZ;
-        const long long nb = (long long)p.N * nbx * nby * nbz;
-        const long long waves = (nb + nsm - 1) / nsm;
-        const double mma_cyc = (double)MT * T * p.nchunks * per_mma;
-        const double load_cyc = (double)rows_h * p.Cin * 2.0 / 40.0 + (double)T * p.nchunks * p.Cout * 32.0 / 40.0;
-        const double epi_cyc = (double)MT * p.Cout * 12.0;
-        const int AS = (2 * MT * p.Cout <= 512) ? 2 : 1;
-        double brick = (mma_cyc > load_cyc ? mma_cyc : load_cyc) + (AS == 2 ? 0.0 : epi_cyc) + 1500.0;
-        const double cost = (double)waves * brick;
-        if (cost < best) {
-          best = cost;
-          found = true;
-          bestp = p;
-          bestp.BX = BX; bestp.BY = BY; bestp.BZ = BZ; bestp.HX = HX; bestp.HY = HY; bestp.HZ = HZ;
-          bestp.nbx = nbx; bestp.nby = nby; bestp.nbz = nbz; bestp.nbricks = (int)nb;
-          bestp.rows_h = (int)rows_h; bestp.MT = MT; bestp.SA = SA; bestp.SB = SB; bestp.AS = AS;
-          bestp.slotA_bytes = (unsigned)slotA;
+  for (int NS = 1; NS <= 4; NS *= 2) {
+    if (p.Cout % (16 * NS)) break;
+    const int Ns = p.Cout / NS;
+    // several taps share one weight stage (fewer barrier round trips for the issuing lane): largest group <= 32 KB
+    const int cands[4] = {T, 9, 3, 1};
+    int TG = 1;
+    for (int i = 0; i < 4; ++i)
+      if (cands[i] <= T && T % cands[i] == 0 && cands[i] * Ns * 32 <= 32 * 1024) { TG = cands[i]; break; }
+    const unsigned stageB = (unsigned)TG * (unsigned)Ns * 32u;
+    const double per_mma = (Ns / 2.0 > 32.0 + Ns / 4.0) ? Ns / 2.0 : 32.0 + Ns / 4.0;
+    for (int zi = 0; zi < nz; ++zi) {
+      const int BZ = bz_opts[zi], HZ = BZ + 2;
+      for (int BY = 1; BY <= p.Y && BY + 2 <= 256; ++BY) {
+        const int HY = BY + 2;
+        const int bxmax = (p.kx == 1) ? 1 : p.X;
+        for (int BX = 1; BX <= bxmax; ++BX) {
+          const int HX = BX + p.kx - 1;
+          if (HX > 256) break;
+          const long long rows_h = (long long)HX * HY * HZ;
+          if (rows_h >= 16384) break;
+          const long long lmax = ((long long)(BX - 1) * HY + (BY - 1)) * HZ + BZ;
+          const int MT = (int)((lmax + 127) / 128);
+          if (MT * Ns > 512) break;
+          const long long rows_alloc = (long long)MT * 128 + ((long long)(p.kx - 1) * HY + 2) * HZ + 2;
+          const long long slotA = ((rows_h + (rows_alloc > rows_h ? rows_alloc : rows_h)) * 16 + 127) / 128 * 128;
+          int SB = 3;
+          long long avail = (long long)SMEM_BUDGET - 1024 - (long long)SB * stageB;
+          int SA = (int)(avail / slotA);
+          if (SA < 2) break;
+          if (SA > 4) SA = 4;
+          const int nbx = (p.X + BX - 1) / BX, nby = (p.Y + BY - 1) / BY, nbz = (p.Z + BZ - 1) / BZ;
+          const long long nb = (long long)p.N * nbx * nby * nbz;
+          const long long items = nb * NS;
+          const long long waves = (items + nsm - 1) / nsm;
+          const double mma_cyc = (double)MT * T * p.nchunks * per_mma;
+          const double item_bytes = (double)rows_h * p.Cin * 2.0 + (double)T * p.nchunks * Ns * 32.0;
+          const double load_cyc = item_bytes / 40.0;                      // one SM's TMA intake
+          const double epi_cyc = (double)MT * Ns * 12.0;
+          const int AS = (2 * MT * Ns <= 512) ? 2 : 1;
+          const double per_item = (mma_cyc > load_cyc ? mma_cyc : load_cyc) + (AS == 2 ? 0.0 : epi_cyc) + 1500.0;
+          const double l2_bound = (double)items * item_bytes / 2500.0;   // chip-wide L2 -> SM bandwidth (bytes/clk)
+          const double t_sm = (double)waves * per_item;
+          const double cost = t_sm > l2_bound ? t_sm : l2_bound;
+          if (cost < best) {
+            best = cost;
+            found = true;
+            bestp = p;
+            bestp.BX = BX; bestp.BY = BY; bestp.BZ = BZ; bestp.HX = HX; bestp.HY = HY; bestp.HZ = HZ;
+            bestp.nbx = nbx; bestp.nby = nby; bestp.nbz = nbz; bestp.nbricks = (int)nb;
+            bestp.rows_h = (int)rows_h; bestp.MT = MT; bestp.SA = SA; bestp.SB = SB; bestp.AS = AS;
+            bestp.slotA_bytes = (unsigned)slotA; bestp.stageB_bytes = stageB; bestp.TG = TG; bestp.NS = NS; bestp.Ns = Ns;
+          }
         }
       }
     }
@@ -714,7 +767,7 @@ static bool plan(TcParams& p, int nsm) {
   if (!found) return false;
   p = bestp;
   int cols = 32;
-  while (cols < p.AS * p.MT * p.Cout) cols *= 2;
+  while (cols < p.AS * p.MT * p.Ns) cols *= 2;
   p.tmem_cols = cols;
   p.offA = 0;
   p.offB = p.SA * p.slotA_bytes;
@@ -878,7 +931,7 @@ int bcp_conv_tc_plan(int n, int cin, int cout, const int* dims, const int* kerne
   TcParams p{};
   p.N = n; p.X = dims[0]; p.Y = dims[1]; p.Z = dims[2]; p.Cin = cin; p.Cout = cout; p.kx = kernel[0];
   if (!plan(p, sm_count())) { set_last_error("conv_tc_plan: no brick shape fits"); return BCP_ERR_UNSUPPORTED; }
-  const int v[10] = {p.BX, p.BY, p.BZ, p.MT, p.SA, p.SB, p.AS, p.nbricks, p.tmem_cols, (int)(p.offBar + 8 * (2 * p.SA + 2 * p.SB + 2 * p.AS) + 16 + 128)};
+  const int v[10] = {p.BX, p.BY, p.BZ, p.MT, p.SA, p.NS * 100 + p.TG, p.AS, p.nbricks, p.tmem_cols, (int)(p.offBar + 8 * (2 * p.SA + 2 * p.SB + 2 * p.AS) + 16 + 128)};
   for (int i = 0; i < 10; ++i) plan10[i] = v[i];
   return BCP_OK;
 }
@@ -907,7 +960,8 @@ int bcp_conv_tc_fwd(const void* in, const void* wpack, const float* bias, void* 
   const size_t smem = (size_t)p.offBar + 8 * (2 * p.SA + 2 * p.SB + 2 * p.AS) + 16 + 128;
   static std::once_flag attr_once;
   std::call_once(attr_once, [] { cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
-  const int grid = p.nbricks < nsm ? p.nbricks : nsm;
+  const int nitems = p.nbricks * p.NS;
+  const int grid = nitems < nsm ? nitems : nsm;
   conv_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(tmap, (const __nv_bfloat16*)wpack, bias, (uint4*)out, p);
   return check_launch("conv_tc_fwd");
 }
@@ -959,7 +1013,7 @@ int bcp_conv_tc_wgrad(const void* a, const void* dy, float* dw, float* workspace
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { set_last_error("conv_tc_wgrad: tensor map (dy) failed (%d)", (int)cr); return BCP_ERR_CUDA; }
   }
-  const size_t smem = (size_t)p.offBar + 8 * (2 * p.S + 1) + 16 + 128;
+  const size_t smem = (size_t)p.offBar + 8 * (2 * p.S + 1) + 16 + 128 + 128;
   static std::once_flag attr_once;
   std::call_once(attr_once, [] { cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
   dim3 grid(p.splits, p.npass_t * p.MH);
@@ -1110,7 +1164,7 @@ int bcp_conv_tc_s2_wgrad(const void* full, const void* half, float* dw, float* w
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { set_last_error("conv_tc_s2_wgrad: tensor map (half) failed (%d)", (int)cr); return BCP_ERR_CUDA; }
   }
-  const size_t smem = (size_t)p.offBar + 8 * (2 * p.S + 1) + 16 + 128;
+  const size_t smem = (size_t)p.offBar + 8 * (2 * p.S + 1) + 16 + 128 + 128;
   static std::once_flag attr_once;
   std::call_once(attr_once, [] { cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
   dim3 grid(p.splits, p.npass_t * p.MH);
