@@ -24,7 +24,7 @@ _CT = {
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim)
 KERNELS_PER_CALL = {
-    "bcp_norm_stats": 2, "bcp_norm_bwd": 3, "bcp_mix_loss_fwd": 2, "bcp_conv_direct_wgrad": 2,
+    "bcp_norm_stats": 1, "bcp_norm_bwd": 2, "bcp_mix_loss_fwd": 2, "bcp_conv_direct_wgrad": 2,
     "bcp_chan_sum": 2, "bcp_conv_first_wgrad": 2, "bcp_head_wgrad": 2, "bcp_largest_cc": 5,
     "bcp_conv_tc_wgrad": 2,
 }

@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(128) conv_wgrad_partial_kernel(const uint4* __
 
 // dst layout selectable: [A][B][T] (PyTorch conv weight layout; A = channels of `og`, B = channels of `in`)
 __global__ void conv_wgrad_finalize_kernel(const float* __restrict__ partial, float* __restrict__ dw, int chunks, int T,
-                                           int Cin, int Cout) {
+                                           int Cin, int Cout, int accumulate) {
   const int Cib = (Cin + 7) / 8, Cob = (Cout + 7) / 8;
   const long long per = (long long)T * Cib * Cob * 64;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -183,7 +183,8 @@ __global__ void conv_wgrad_finalize_kernel(const float* __restrict__ partial, fl
   if (a >= Cout || b >= Cin) return;
   float s = 0.f;
   for (int c = 0; c < chunks; ++c) s += partial[(long long)c * per + i];
-  dw[((long long)a * Cin + b) * T + t] = s;
+  float* dst = dw + ((long long)a * Cin + b) * T + t;
+  *dst = accumulate ? *dst + s : s;
 }
 
 // per-channel sum of a CB8 tensor (conv bias gradient): partial then fixed-order sum
@@ -224,11 +225,14 @@ __global__ void chan_sum_finalize_kernel(const float* __restrict__ partial, floa
 // -------------------------------------------------------------------------------------------------
 // first layer: Cin = 1, fp32 planar input [N][X][Y][Z]; weights fp32 [Cout][1][T] (PyTorch layout)
 // -------------------------------------------------------------------------------------------------
+template <int KX>
 __global__ void __launch_bounds__(128) conv_first_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                               const float* __restrict__ bias, uint4* __restrict__ out,
                                                               Geom g, int Cout) {
+  // kernel KX x 3 x 3, 'same' padding; fully unrolled taps (27 or 9 input values live in registers)
+  constexpr int T = KX * 9;
   extern __shared__ float wsm[];   // [T][Cob*8]
-  const int Cob = (Cout + 7) / 8, T = g.kx * g.ky * g.kz;
+  const int Cob = (Cout + 7) / 8;
   for (int i = threadIdx.x; i < T * Cob * 8; i += 128) {
     const int t = i / (Cob * 8), c = i % (Cob * 8);
     wsm[i] = (c < Cout) ? w[(long long)c * T + t] : 0.f;
@@ -240,22 +244,29 @@ __global__ void __launch_bounds__(128) conv_first_fwd_kernel(const float* __rest
   for (long long o = (long long)blockIdx.x * 128 + threadIdx.x; o < total; o += stride) {
     int n, x, y, z;
     decompose(o, g, n, x, y, z);
-    float v[27];
-    for (int t = 0; t < T; ++t) {
-      const int tz = t % g.kz, ty = (t / g.kz) % g.ky, tx = t / (g.kz * g.ky);
-      const int ix = x + tx - g.px, iy = y + ty - g.py, iz = z + tz - g.pz;
-      const bool ok = ix >= 0 && ix < g.Xi && iy >= 0 && iy < g.Yi && iz >= 0 && iz < g.Zi;
-      v[t] = ok ? __ldg(in + ((long long)n * g.Xi + ix) * g.Yi * g.Zi + (long long)iy * g.Zi + iz) : 0.f;
-    }
+    float v[T];
+    const float* base = in + (long long)n * g.Xi * g.Yi * g.Zi;
+#pragma unroll
+    for (int tx = 0; tx < KX; ++tx)
+#pragma unroll
+      for (int ty = 0; ty < 3; ++ty)
+#pragma unroll
+        for (int tz = 0; tz < 3; ++tz) {
+          const int ix = x + tx - (KX >> 1), iy = y + ty - 1, iz = z + tz - 1;
+          const bool ok = ix >= 0 && ix < g.Xi && iy >= 0 && iy < g.Yi && iz >= 0 && iz < g.Zi;
+          v[(tx * 3 + ty) * 3 + tz] = ok ? __ldg(base + ((long long)ix * g.Yi + iy) * g.Zi + iz) : 0.f;
+        }
     const long long so = o - (long long)n * So;
     for (int cob = 0; cob < Cob; ++cob) {
       float acc[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = (bias && cob * 8 + j < Cout) ? bias[cob * 8 + j] : 0.f;
-      for (int t = 0; t < T; ++t) {
-        const float* wr = wsm + t * Cob * 8 + cob * 8;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += v[t] * wr[j];
+      for (int t = 0; t < T; ++t) {
+        const float4 w0 = *reinterpret_cast<const float4*>(wsm + t * Cob * 8 + cob * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(wsm + t * Cob * 8 + cob * 8 + 4);
+        acc[0] += v[t] * w0.x; acc[1] += v[t] * w0.y; acc[2] += v[t] * w0.z; acc[3] += v[t] * w0.w;
+        acc[4] += v[t] * w1.x; acc[5] += v[t] * w1.y; acc[6] += v[t] * w1.z; acc[7] += v[t] * w1.w;
       }
       out[((long long)n * Cob + cob) * So + so] = pack8(acc);
     }
@@ -309,7 +320,7 @@ __global__ void __launch_bounds__(128) conv_first_wgrad_partial_kernel(const flo
 }
 
 __global__ void conv_first_wgrad_finalize_kernel(const float* __restrict__ partial, float* __restrict__ dw, int chunks,
-                                                 int Cout, int kx, int ky, int kz) {
+                                                 int Cout, int kx, int ky, int kz, int accumulate) {
   const int Cob = (Cout + 7) / 8, T = kx * ky * kz;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Cout * T) return;
@@ -318,7 +329,7 @@ __global__ void conv_first_wgrad_finalize_kernel(const float* __restrict__ parti
   const int cob = co >> 3, j = co & 7;
   float s = 0.f;
   for (int c = 0; c < chunks; ++c) s += partial[(((long long)c * Cob + cob) * kx + tx) * 72 + (ty * 3 + tz) * 8 + j];
-  dw[i] = s;
+  dw[i] = accumulate ? dw[i] + s : s;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -443,7 +454,7 @@ __global__ void __launch_bounds__(128) head_wgrad_partial_kernel(const uint4* __
 
 template <int NC>
 __global__ void head_wgrad_finalize_kernel(const float* __restrict__ partial, float* __restrict__ dw, float* __restrict__ db,
-                                           int chunks, int T, int Cin) {
+                                           int chunks, int T, int Cin, int accumulate) {
   const int Cib = (Cin + 7) / 8;
   constexpr int K = NC * 8 + NC;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -451,12 +462,12 @@ __global__ void head_wgrad_finalize_kernel(const float* __restrict__ partial, fl
     const int t = i % T, ci = (i / T) % Cin, k = i / (T * Cin);
     float s = 0.f;
     for (int c = 0; c < chunks; ++c) s += partial[(((long long)c * T + t) * Cib + (ci >> 3)) * K + k * 8 + (ci & 7)];
-    dw[i] = s;
+    dw[i] = accumulate ? dw[i] + s : s;
   } else if (i < NC * Cin * T + NC && db) {
     const int k = i - NC * Cin * T;
     float s = 0.f;
     for (int c = 0; c < chunks; ++c) s += partial[(((long long)c * T + 0) * Cib + 0) * K + NC * 8 + k];
-    db[k] = s;
+    db[k] = accumulate ? db[k] + s : s;
   }
 }
 
@@ -511,7 +522,8 @@ long long bcp_conv_wgrad_workspace_floats(int n, int cin, int cout, const int* o
 
 // dw[cout][cin][T] where `outgrad` has `cout` channels at output resolution and `in` has `cin` channels
 int bcp_conv_direct_wgrad(const void* in, const void* outgrad, float* dw, float* workspace, int n, int cin, int cout,
-                          const int* in_dims, const int* kernel, const int* stride, const int* pad, cudaStream_t stream) {
+                          const int* in_dims, const int* kernel, const int* stride, const int* pad, int accumulate,
+                          cudaStream_t stream) {
   BCP_REQUIRE(in && outgrad && dw && workspace, "conv_direct_wgrad: null pointer");
   Geom g;
   BCP_REQUIRE(make_geom(g, n, in_dims, kernel, stride, pad, 0) == 0, "conv_direct_wgrad: bad geometry");
@@ -521,7 +533,7 @@ int bcp_conv_direct_wgrad(const void* in, const void* outgrad, float* dw, float*
   dim3 grid(chunks, Cib * ((Cob + 3) / 4), T);
   conv_wgrad_partial_kernel<<<grid, 128, 0, stream>>>((const uint4*)in, (const uint4*)outgrad, workspace, g, cin, cout);
   const long long per = (long long)T * Cib * Cob * 64;
-  conv_wgrad_finalize_kernel<<<(unsigned)((per + 255) / 256), 256, 0, stream>>>(workspace, dw, chunks, T, cin, cout);
+  conv_wgrad_finalize_kernel<<<(unsigned)((per + 255) / 256), 256, 0, stream>>>(workspace, dw, chunks, T, cin, cout, accumulate);
   return check_launch("conv_direct_wgrad");
 }
 
@@ -550,14 +562,17 @@ int bcp_conv_first_fwd(const float* in, const float* w, const float* bias, void*
   const int pad[3] = {kernel[0] / 2, kernel[1] / 2, kernel[2] / 2};
   Geom g;
   BCP_REQUIRE(make_geom(g, n, dims, kernel, stride, pad, 0) == 0, "conv_first_fwd: bad geometry");
-  BCP_REQUIRE(g.kx * g.ky * g.kz <= 27, "conv_first_fwd: kernel too large");
+  BCP_REQUIRE((g.kx == 3 || g.kx == 1) && g.ky == 3 && g.kz == 3, "conv_first_fwd: kernel must be 3x3x3 or 1x3x3");
   const int Cob = (cout + 7) / 8;
   const long long total = (long long)n * g.Xo * g.Yo * g.Zo;
   long long blocks = (total + 127) / 128;
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
   const size_t smem = (size_t)g.kx * g.ky * g.kz * Cob * 8 * sizeof(float);
-  conv_first_fwd_kernel<<<(unsigned)blocks, 128, smem, stream>>>(in, w, bias, (uint4*)out, g, cout);
+  if (g.kx == 3)
+    conv_first_fwd_kernel<3><<<(unsigned)blocks, 128, smem, stream>>>(in, w, bias, (uint4*)out, g, cout);
+  else
+    conv_first_fwd_kernel<1><<<(unsigned)blocks, 128, smem, stream>>>(in, w, bias, (uint4*)out, g, cout);
   return check_launch("conv_first_fwd");
 }
 
@@ -567,7 +582,7 @@ long long bcp_conv_first_wgrad_workspace_floats(int n, int cout, const int* dims
 }
 
 int bcp_conv_first_wgrad(const float* in, const void* outgrad, float* dw, float* workspace, int n, int cout,
-                         const int* dims, const int* kernel, cudaStream_t stream) {
+                         const int* dims, const int* kernel, int accumulate, cudaStream_t stream) {
   BCP_REQUIRE(in && outgrad && dw && workspace, "conv_first_wgrad: null pointer");
   const int stride[3] = {1, 1, 1};
   const int pad[3] = {kernel[0] / 2, kernel[1] / 2, kernel[2] / 2};
@@ -580,7 +595,7 @@ int bcp_conv_first_wgrad(const float* in, const void* outgrad, float* dw, float*
   dim3 grid(chunks, Cob, g.kx);
   conv_first_wgrad_partial_kernel<<<grid, 128, 0, stream>>>(in, (const uint4*)outgrad, workspace, g, cout);
   const int T = g.kx * g.ky * g.kz;
-  conv_first_wgrad_finalize_kernel<<<(cout * T + 127) / 128, 128, 0, stream>>>(workspace, dw, chunks, cout, g.kx, g.ky, g.kz);
+  conv_first_wgrad_finalize_kernel<<<(cout * T + 127) / 128, 128, 0, stream>>>(workspace, dw, chunks, cout, g.kx, g.ky, g.kz, accumulate);
   return check_launch("conv_first_wgrad");
 }
 
@@ -632,7 +647,7 @@ long long bcp_head_wgrad_workspace_floats(int n, int cin, int ncls, const int* d
 }
 
 int bcp_head_wgrad(const void* in, const float* dlogits, float* dw, float* db, float* workspace, int n, int cin, int ncls,
-                   const int* dims, const int* kernel, cudaStream_t stream) {
+                   const int* dims, const int* kernel, int accumulate, cudaStream_t stream) {
   BCP_REQUIRE(in && dlogits && dw && workspace, "head_wgrad: null pointer");
   Geom g;
   BCP_REQUIRE(head_geom(g, n, dims, kernel) == 0, "head_wgrad: bad geometry");
@@ -641,7 +656,7 @@ int bcp_head_wgrad(const void* in, const float* dlogits, float* dw, float* db, f
   dim3 grid(chunks, Cib, T);
   HEAD_DISPATCH(ncls, (head_wgrad_partial_kernel<NC><<<grid, 128, 0, stream>>>((const uint4*)in, dlogits, workspace, g, cin)));
   const int nout = ncls * cin * T + ncls;
-  HEAD_DISPATCH(ncls, (head_wgrad_finalize_kernel<NC><<<(nout + 127) / 128, 128, 0, stream>>>(workspace, dw, db, chunks, T, cin)));
+  HEAD_DISPATCH(ncls, (head_wgrad_finalize_kernel<NC><<<(nout + 127) / 128, 128, 0, stream>>>(workspace, dw, db, chunks, T, cin, accumulate)));
   return check_launch("head_wgrad");
 }
 

@@ -662,7 +662,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 
 // dw[co][ci][t] = sum_split partial[split][t][co][ci]   (fixed order)
 __global__ void conv_tc_wgrad_finalize_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int T,
-                                              int Cout, int Cin) {
+                                              int Cout, int Cin, int accumulate) {
   const long long per = (long long)T * Cout * Cin;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= per) return;
@@ -671,7 +671,8 @@ __global__ void conv_tc_wgrad_finalize_kernel(const float* __restrict__ partial,
   const int t = (int)(i / ((long long)Cin * Cout));
   float s = 0.f;
   for (int k = 0; k < splits; ++k) s += partial[(long long)k * per + i];
-  dw[((long long)co * Cin + ci) * T + t] = s;
+  float* dst = dw + ((long long)co * Cin + ci) * T + t;
+  *dst = accumulate ? *dst + s : s;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -987,7 +988,7 @@ long long bcp_conv_tc_wgrad_workspace_floats(int n, int cin, int cout, const int
 
 // dw[cout][cin][T] fp32; `a` = layer input (cin channels), `dy` = output gradient (cout channels), both CB8 at `dims`
 int bcp_conv_tc_wgrad(const void* a, const void* dy, float* dw, float* workspace, int n, int cin, int cout,
-                      const int* dims, const int* kernel, cudaStream_t stream) {
+                      const int* dims, const int* kernel, int accumulate, cudaStream_t stream) {
   BCP_REQUIRE(a && dy && dw && workspace && dims && kernel, "conv_tc_wgrad: null pointer");
   if (!wg_shape_ok(cin, cout, dims, kernel)) { set_last_error("conv_tc_wgrad: unsupported shape"); return BCP_ERR_UNSUPPORTED; }
   EncodeTiledFn enc = get_encode();
@@ -1019,7 +1020,7 @@ int bcp_conv_tc_wgrad(const void* a, const void* dy, float* dw, float* workspace
   dim3 grid(p.splits, p.npass_t * p.MH);
   conv_tc_wgrad_kernel<<<grid, TC_THREADS, smem, stream>>>(map_a, map_dy, workspace, p);
   const long long per = (long long)p.T * cout * cin;
-  conv_tc_wgrad_finalize_kernel<<<(unsigned)((per + 255) / 256), 256, 0, stream>>>(workspace, dw, p.splits, p.T, cout, cin);
+  conv_tc_wgrad_finalize_kernel<<<(unsigned)((per + 255) / 256), 256, 0, stream>>>(workspace, dw, p.splits, p.T, cout, cin, accumulate);
   return check_launch("conv_tc_wgrad");
 }
 
@@ -1135,7 +1136,7 @@ long long bcp_conv_tc_s2_wgrad_workspace_floats(int n, int c_half, int c_full, c
 }
 
 int bcp_conv_tc_s2_wgrad(const void* full, const void* half, float* dw, float* workspace, int n, int c_half, int c_full,
-                         const int* half_dims, cudaStream_t stream) {
+                         const int* half_dims, int accumulate, cudaStream_t stream) {
   BCP_REQUIRE(full && half && dw && workspace && half_dims, "conv_tc_s2_wgrad: null pointer");
   if (!s2_shape_ok(c_full, c_half, half_dims)) { set_last_error("conv_tc_s2_wgrad: unsupported shape"); return BCP_ERR_UNSUPPORTED; }
   EncodeTiledFn enc = get_encode();
@@ -1170,7 +1171,7 @@ int bcp_conv_tc_s2_wgrad(const void* full, const void* half, float* dw, float* w
   dim3 grid(p.splits, p.npass_t * p.MH);
   conv_tc_wgrad_kernel<<<grid, TC_THREADS, smem, stream>>>(map_a, map_dy, workspace, p);
   const long long per = 8ll * c_half * c_full;
-  conv_tc_wgrad_finalize_kernel<<<(unsigned)((per + 255) / 256), 256, 0, stream>>>(workspace, dw, p.splits, 8, c_half, c_full);
+  conv_tc_wgrad_finalize_kernel<<<(unsigned)((per + 255) / 256), 256, 0, stream>>>(workspace, dw, p.splits, 8, c_half, c_full, accumulate);
   return check_launch("conv_tc_s2_wgrad");
 }
 

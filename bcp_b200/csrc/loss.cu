@@ -85,11 +85,30 @@ __global__ void __launch_bounds__(LT) mix_loss_fwd_kernel(const float* __restric
 
 // ctx layout (floats): [0]=loss=(dice+ce)/2, [1]=dice, [2]=ce, [3]=unused, [4..5]=ce coef per set,
 // then [N][2][C][3] = {cA, cB, cC}:   dDice/dp_c(v) = cA*[T==c] + cB + cC*p_c   (v in set s, sample n)
+// deterministic warp-parallel sum of partial[(n*blocks + b)*K + k] over b (lane-strided, then a fixed shuffle tree)
+template <int K>
+__device__ __forceinline__ void sum_partials(const float* __restrict__ partial, int n, int blocks, double (&a)[K]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < K; ++k) a[k] = 0.0;
+  for (int b = lane; b < blocks; b += 32) {
+    const float* src = partial + ((long long)n * blocks + b) * K;
+#pragma unroll
+    for (int k = 0; k < K; ++k) a[k] += (double)src[k];
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], o);
+}
+
+// ctx layout (floats): [0]=loss=(dice+ce)/2, [1]=dice, [2]=ce, [3]=unused, [4..5]=ce coef per set,
+// then [N][2][C][3] = {cA, cB, cC}:   dDice/dp_c(v) = cA*[T==c] + cB + cC*p_c   (v in set s, sample n)
 template <int C, int FORM>
 __global__ void mix_loss_finalize_kernel(const float* __restrict__ partial, float* __restrict__ ctx, int N, int blocks,
                                          float w_img, float w_patch) {
   constexpr int K = 2 * C * 3 + 4;
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const bool writer = threadIdx.x == 0;
   const double w[2] = {(double)w_img, (double)w_patch};
   double cnt[2] = {0.0, 0.0};     // mask.sum() / (1-mask).sum() over the whole [N, ...] loss mask
   double dice = 0.0, ce = 0.0;
@@ -100,19 +119,19 @@ __global__ void mix_loss_finalize_kernel(const float* __restrict__ partial, floa
     double dsum[2] = {0.0, 0.0};
     for (int n = 0; n < N; ++n) {
       double a[K];
-      for (int k = 0; k < K; ++k) a[k] = 0.0;
-      for (int b = 0; b < blocks; ++b)
-        for (int k = 0; k < K; ++k) a[k] += (double)partial[((long long)n * blocks + b) * K + k];
+      sum_partials<K>(partial, n, blocks, a);
       for (int s = 0; s < 2; ++s) {
         for (int c = 0; c < C; ++c) {
           const double I = a[(s * C + c) * 3], U = a[(s * C + c) * 3 + 1];
           const double D = (2.0 * I + eps) / (U + eps);
           dsum[s] += D;
           const double k0 = -w[s] / ((double)N * C);
-          float* t = tab + (((long long)n * 2 + s) * C + c) * 3;
-          t[0] = (float)(k0 * 2.0 / (U + eps));
-          t[1] = (float)(-k0 * D / (U + eps));
-          t[2] = 0.f;
+          if (writer) {
+            float* t = tab + (((long long)n * 2 + s) * C + c) * 3;
+            t[0] = (float)(k0 * 2.0 / (U + eps));
+            t[1] = (float)(-k0 * D / (U + eps));
+            t[2] = 0.f;
+          }
         }
         cesum[s] += a[2 * C * 3 + s];
         cnt[s] += a[2 * C * 3 + 2 + s];
@@ -123,9 +142,11 @@ __global__ void mix_loss_finalize_kernel(const float* __restrict__ partial, floa
     const double eps = 1e-10;
     double a[K];
     for (int k = 0; k < K; ++k) a[k] = 0.0;
-    for (int n = 0; n < N; ++n)
-      for (int b = 0; b < blocks; ++b)
-        for (int k = 0; k < K; ++k) a[k] += (double)partial[((long long)n * blocks + b) * K + k];
+    for (int n = 0; n < N; ++n) {
+      double an[K];
+      sum_partials<K>(partial, n, blocks, an);
+      for (int k = 0; k < K; ++k) a[k] += an[k];
+    }
     for (int s = 0; s < 2; ++s) {
       double dl = 0.0;
       for (int c = 0; c < C; ++c) {
@@ -134,24 +155,27 @@ __global__ void mix_loss_finalize_kernel(const float* __restrict__ partial, floa
         dl += 1.0 - (2.0 * I + eps) / den;
         const double cA = -w[s] / C * 2.0 / den;
         const double cC = w[s] / C * 2.0 * (2.0 * I + eps) / (den * den);
-        for (int n = 0; n < N; ++n) {
-          float* t = tab + (((long long)n * 2 + s) * C + c) * 3;
-          t[0] = (float)cA; t[1] = 0.f; t[2] = (float)cC;
-        }
+        if (writer)
+          for (int n = 0; n < N; ++n) {
+            float* t = tab + (((long long)n * 2 + s) * C + c) * 3;
+            t[0] = (float)cA; t[1] = 0.f; t[2] = (float)cC;
+          }
       }
       dice += w[s] * dl / C;
       cesum[s] = a[2 * C * 3 + s];
       cnt[s] = a[2 * C * 3 + 2 + s];
     }
   }
-  for (int s = 0; s < 2; ++s) {
-    ce += w[s] * cesum[s] / (cnt[s] + 1e-16);
-    ctx[4 + s] = (float)(w[s] / (cnt[s] + 1e-16));
+  if (writer) {
+    for (int s = 0; s < 2; ++s) {
+      ce += w[s] * cesum[s] / (cnt[s] + 1e-16);
+      ctx[4 + s] = (float)(w[s] / (cnt[s] + 1e-16));
+    }
+    ctx[0] = (float)((dice + ce) * 0.5);
+    ctx[1] = (float)dice;
+    ctx[2] = (float)ce;
+    ctx[3] = 0.f;
   }
-  ctx[0] = (float)((dice + ce) * 0.5);
-  ctx[1] = (float)dice;
-  ctx[2] = (float)ce;
-  ctx[3] = 0.f;
 }
 
 template <int C>

@@ -12,9 +12,71 @@ namespace bcp {
 
 constexpr int NT = 256;
 
-// partial[((n*Cb + cb)*chunks + chunk)*16 + {0..7: sum, 8..15: sumsq}]
-__global__ void __launch_bounds__(NT) bn_stats_partial_kernel(const uint4* __restrict__ y, float* __restrict__ partial,
-                                                               long long S, int chunks) {
+// Per-channel finalize, executed by ONE block (the last one to finish its partial): fixed-order double-precision
+// reduce of the partials => deterministic no matter which block happens to be last.
+// stat[g][C][2] = {mean, invstd}; coef[g][C][2] = {scale, shift}.
+__device__ void bn_finalize_block(const float* __restrict__ partial, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, float* __restrict__ running_mean,
+                                  float* __restrict__ running_var, long long* __restrict__ nbt,
+                                  float* __restrict__ stat, float* __restrict__ coef,
+                                  int N, int C, long long S, int chunks, int spg, float eps, float momentum) {
+  const int Cb = (C + 7) / 8;
+  const int G = N / spg;
+  if (threadIdx.x == 0 && nbt != nullptr) nbt[0] += G;
+  const double M = (double)spg * (double)S;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int cb = c >> 3, k = c & 7;
+    float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 0.f;
+    for (int g = 0; g < G; ++g) {
+      double s = 0.0, q = 0.0;
+      for (int n = g * spg; n < (g + 1) * spg; ++n) {
+        const float* p = partial + ((long long)n * Cb + cb) * chunks * 16;
+        for (int ch = 0; ch < chunks; ++ch) { s += (double)p[ch * 16 + k]; q += (double)p[ch * 16 + 8 + k]; }
+      }
+      const double mean = s / M;
+      double var = q / M - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+      const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+      const float scale = ga * invstd;
+      stat[((long long)g * C + c) * 2 + 0] = (float)mean;
+      stat[((long long)g * C + c) * 2 + 1] = invstd;
+      coef[((long long)g * C + c) * 2 + 0] = scale;
+      coef[((long long)g * C + c) * 2 + 1] = be - (float)mean * scale;
+      if (running_mean) {   // sequential per-call update, like calling the module once per group
+        const double unbiased = (M > 1.0) ? var * M / (M - 1.0) : var;
+        rm = (1.f - momentum) * rm + momentum * (float)mean;
+        rv = (1.f - momentum) * rv + momentum * (float)unbiased;
+      }
+    }
+    if (running_mean) { running_mean[c] = rm; running_var[c] = rv; }
+  }
+}
+
+// true in every thread of exactly one block: the last block of the grid to arrive (threadfence-reduction pattern).
+// `counter` must be zero on entry and is reset to zero by the last block => reusable by the next launch on the stream.
+__device__ __forceinline__ bool last_block_arrives(int* counter) {
+  __shared__ int is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int total = gridDim.x * gridDim.y * gridDim.z;
+    const int prev = atomicAdd(counter, 1);
+    is_last = (prev == total - 1);
+    if (is_last) *counter = 0;
+  }
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last != 0;
+}
+
+// partial[((n*Cb + cb)*chunks + chunk)*16 + {0..7: sum, 8..15: sumsq}]; the last block finalises
+__global__ void __launch_bounds__(NT) bn_stats_kernel(const uint4* __restrict__ y, float* __restrict__ partial,
+                                                       long long S, int chunks, int* __restrict__ counter,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                       long long* __restrict__ nbt, float* __restrict__ stat,
+                                                       float* __restrict__ coef, int N, int C, int spg, float eps, float momentum) {
   const int chunk = blockIdx.x, cb = blockIdx.y, n = blockIdx.z, Cb = gridDim.y;
   const uint4* base = y + ((long long)n * Cb + cb) * S;
   const long long per = (S + chunks - 1) / chunks;
@@ -36,45 +98,8 @@ __global__ void __launch_bounds__(NT) bn_stats_partial_kernel(const uint4* __res
 #pragma unroll
     for (int k = 0; k < 16; ++k) dst[k] = acc[k];
   }
-}
-
-// One thread per channel.  stat[g][C][2] = {mean, invstd}; coef[g][C][2] = {scale, shift}.
-__global__ void bn_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var, long long* __restrict__ nbt,
-                                   float* __restrict__ stat, float* __restrict__ coef,
-                                   int N, int C, long long S, int chunks, int spg, float eps, float momentum) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  const int Cb = (C + 7) / 8;
-  const int G = N / spg;
-  if (c == 0 && nbt != nullptr) nbt[0] += G;
-  if (c >= C) return;
-  const int cb = c >> 3, k = c & 7;
-  const double M = (double)spg * (double)S;
-  float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 0.f;
-  for (int g = 0; g < G; ++g) {
-    double s = 0.0, q = 0.0;
-    for (int n = g * spg; n < (g + 1) * spg; ++n) {
-      const float* p = partial + ((long long)n * Cb + cb) * chunks * 16;
-      for (int ch = 0; ch < chunks; ++ch) { s += (double)p[ch * 16 + k]; q += (double)p[ch * 16 + 8 + k]; }
-    }
-    const double mean = s / M;
-    double var = q / M - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
-    const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
-    const float scale = ga * invstd;
-    stat[((long long)g * C + c) * 2 + 0] = (float)mean;
-    stat[((long long)g * C + c) * 2 + 1] = invstd;
-    coef[((long long)g * C + c) * 2 + 0] = scale;
-    coef[((long long)g * C + c) * 2 + 1] = be - (float)mean * scale;
-    if (running_mean) {   // sequential per-call update, like calling the module once per group
-      const double unbiased = (M > 1.0) ? var * M / (M - 1.0) : var;
-      rm = (1.f - momentum) * rm + momentum * (float)mean;
-      rv = (1.f - momentum) * rv + momentum * (float)unbiased;
-    }
-  }
-  if (running_mean) { running_mean[c] = rm; running_var[c] = rv; }
+  if (last_block_arrives(counter))
+    bn_finalize_block(partial, gamma, beta, running_mean, running_var, nbt, stat, coef, N, C, S, chunks, spg, eps, momentum);
 }
 
 // eval-mode coefficients from running statistics
@@ -137,6 +162,9 @@ __global__ void __launch_bounds__(NT) bn_apply_kernel(const uint4* __restrict__ 
   }
 }
 
+__device__ void bn_bwd_finalize_block(const float* __restrict__ partial, float* __restrict__ sums, float* __restrict__ dgamma,
+                                      float* __restrict__ dbeta, int N, int C, long long S, int chunks, int spg, int accumulate);
+
 // backward pass 1: per (n, cb, chunk) partials of  s1 = sum g,  s2 = sum g*xhat   with
 // g = da * dropout * act'(pre)
 __global__ void __launch_bounds__(NT) bn_bwd_reduce_kernel(const uint4* __restrict__ da, const uint4* __restrict__ y,
@@ -144,7 +172,9 @@ __global__ void __launch_bounds__(NT) bn_bwd_reduce_kernel(const uint4* __restri
                                                             const float* __restrict__ chan_scale,
                                                             const unsigned char* __restrict__ elem_keep, float elem_scale,
                                                             float* __restrict__ partial, int C, long long S, int chunks,
-                                                            int spg, float slope) {
+                                                            int spg, float slope, int* __restrict__ counter,
+                                                            float* __restrict__ sums, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, int N, int accumulate) {
   const int chunk = blockIdx.x, cb = blockIdx.y, n = blockIdx.z, Cb = gridDim.y;
   const int g = n / spg;
   __shared__ float sc[8], sh[8], cs[8], mu[8], is[8];
@@ -187,29 +217,31 @@ __global__ void __launch_bounds__(NT) bn_bwd_reduce_kernel(const uint4* __restri
 #pragma unroll
     for (int k = 0; k < 16; ++k) dst[k] = acc[k];
   }
+  if (last_block_arrives(counter)) bn_bwd_finalize_block(partial, sums, dgamma, dbeta, N, C, S, chunks, spg, accumulate);
 }
 
-// sums[g][C][2] = {s1/M, s2/M};  dgamma[c] = sum_g s2, dbeta[c] = sum_g s1
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, float* __restrict__ sums,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                       int N, int C, long long S, int chunks, int spg) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const int Cb = (C + 7) / 8, cb = c >> 3, k = c & 7, G = N / spg;
+// sums[g][C][2] = {s1/M, s2/M};  dgamma[c] = sum_g s2, dbeta[c] = sum_g s1   (run by the last block of the reduce pass)
+__device__ void bn_bwd_finalize_block(const float* __restrict__ partial, float* __restrict__ sums,
+                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                      int N, int C, long long S, int chunks, int spg, int accumulate) {
+  const int Cb = (C + 7) / 8, G = N / spg;
   const double M = (double)spg * (double)S;
-  double tg = 0.0, tb = 0.0;
-  for (int g = 0; g < G; ++g) {
-    double a = 0.0, b = 0.0;
-    for (int n = g * spg; n < (g + 1) * spg; ++n) {
-      const float* p = partial + ((long long)n * Cb + cb) * chunks * 16;
-      for (int ch = 0; ch < chunks; ++ch) { a += (double)p[ch * 16 + k]; b += (double)p[ch * 16 + 8 + k]; }
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int cb = c >> 3, k = c & 7;
+    double tg = 0.0, tb = 0.0;
+    for (int g = 0; g < G; ++g) {
+      double a = 0.0, b = 0.0;
+      for (int n = g * spg; n < (g + 1) * spg; ++n) {
+        const float* p = partial + ((long long)n * Cb + cb) * chunks * 16;
+        for (int ch = 0; ch < chunks; ++ch) { a += (double)p[ch * 16 + k]; b += (double)p[ch * 16 + 8 + k]; }
+      }
+      sums[((long long)g * C + c) * 2 + 0] = (float)(a / M);
+      sums[((long long)g * C + c) * 2 + 1] = (float)(b / M);
+      tb += a; tg += b;
     }
-    sums[((long long)g * C + c) * 2 + 0] = (float)(a / M);
-    sums[((long long)g * C + c) * 2 + 1] = (float)(b / M);
-    tb += a; tg += b;
+    if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)tg : (float)tg;
+    if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)tb : (float)tb;
   }
-  if (dgamma) dgamma[c] = (float)tg;
-  if (dbeta) dbeta[c] = (float)tb;
 }
 
 // backward pass 2:  dy = scale * (g - mean(g) - xhat*mean(g*xhat))      (stats_grad=1)
@@ -276,15 +308,14 @@ long long bcp_norm_workspace_floats(int n, int c, long long s) {
 }
 
 int bcp_norm_stats(const void* y, const float* gamma, const float* beta, float* running_mean, float* running_var,
-                   long long* num_batches_tracked, float* stat, float* coef, float* workspace,
+                   long long* num_batches_tracked, float* stat, float* coef, float* workspace, int* counter,
                    int n, int c, long long s, int spg, float eps, float momentum, cudaStream_t stream) {
-  BCP_REQUIRE(y && stat && coef && workspace, "norm_stats: null pointer");
+  BCP_REQUIRE(y && stat && coef && workspace && counter, "norm_stats: null pointer");
   BCP_REQUIRE(n > 0 && c > 0 && s > 0 && spg > 0 && n % spg == 0, "norm_stats: bad shape n=%d spg=%d", n, spg);
   const int chunks = pick_chunks(s), Cb = (c + 7) / 8;
   dim3 grid(chunks, Cb, n);
-  bn_stats_partial_kernel<<<grid, NT, 0, stream>>>((const uint4*)y, workspace, s, chunks);
-  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, stream>>>(workspace, gamma, beta, running_mean, running_var,
-                                                            num_batches_tracked, stat, coef, n, c, s, chunks, spg, eps, momentum);
+  bn_stats_kernel<<<grid, NT, 0, stream>>>((const uint4*)y, workspace, s, chunks, counter, gamma, beta, running_mean, running_var,
+                                           num_batches_tracked, stat, coef, n, c, spg, eps, momentum);
   return check_launch("norm_stats");
 }
 
@@ -311,15 +342,15 @@ int bcp_norm_apply(const void* y, void* out, const float* coef, const float* cha
 
 int bcp_norm_bwd(const void* dact, const void* y, void* dy, const float* stat, const float* coef, const float* chan_scale,
                  const unsigned char* elem_keep, float elem_scale, float* dgamma, float* dbeta, float* sums,
-                 float* workspace, int n, int c, long long s, int spg, float slope, int stats_grad, cudaStream_t stream) {
-  BCP_REQUIRE(dact && y && dy && stat && coef && sums && workspace, "norm_bwd: null pointer");
+                 float* workspace, int* counter, int n, int c, long long s, int spg, float slope, int stats_grad,
+                 int accumulate, cudaStream_t stream) {
+  BCP_REQUIRE(dact && y && dy && stat && coef && sums && workspace && counter, "norm_bwd: null pointer");
   BCP_REQUIRE(n > 0 && c > 0 && s > 0 && spg > 0 && n % spg == 0, "norm_bwd: bad shape");
   const int chunks = pick_chunks(s), Cb = (c + 7) / 8;
   if (stats_grad || dgamma || dbeta) {
     dim3 grid(chunks, Cb, n);
     bn_bwd_reduce_kernel<<<grid, NT, 0, stream>>>((const uint4*)dact, (const uint4*)y, stat, coef, chan_scale, elem_keep,
-                                                  elem_scale, workspace, c, s, chunks, spg, slope);
-    bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, stream>>>(workspace, sums, dgamma, dbeta, n, c, s, chunks, spg);
+                                                  elem_scale, workspace, c, s, chunks, spg, slope, counter, sums, dgamma, dbeta, n, accumulate);
   }
   int gx = (int)((s + NT * 4 - 1) / (NT * 4));
   if (gx < 1) gx = 1;

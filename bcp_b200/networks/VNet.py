@@ -90,18 +90,21 @@ class _Stage3d(nn.Module):
             conv = self.conv[i * self._per]
             norm = self.conv[i * self._per + 1] if self._per == 3 else None
             last = i == self._n - 1
+            # a conv that feeds batch-statistic normalisation has an identically-zero bias gradient (ops._bias_grad)
+            bz = norm is not None and not isinstance(norm, nn.GroupNorm) and (
+                not isinstance(norm, nn.BatchNorm3d) or norm.training or not norm.track_running_stats)
             if self.kind == "same":
                 if a.dtype != torch.bfloat16:            # network input, planar fp32
                     if conv.in_channels == 1:
-                        y = ops.ConvFirst.apply(a, conv.weight, conv.bias)
+                        y = ops.ConvFirst.apply(a, conv.weight, conv.bias, bz)
                     else:
                         raise NotImplementedError("first layer with n_channels != 1")
                 else:
-                    y = ops.ConvSame.apply(a, conv.weight, conv.bias, rt.pack(conv), (3, 3, 3))
+                    y = ops.ConvSame.apply(a, conv.weight, conv.bias, rt.pack(conv), (3, 3, 3), bz)
             elif self.kind == "down":
-                y = ops.ConvDown2.apply(a, conv.weight, conv.bias, rt.pack(conv))
+                y = ops.ConvDown2.apply(a, conv.weight, conv.bias, rt.pack(conv), bz)
             else:
-                y = ops.ConvUp2.apply(a, conv.weight, conv.bias, rt.pack(conv))
+                y = ops.ConvUp2.apply(a, conv.weight, conv.bias, rt.pack(conv), bz)
             a = self._norm_act(y, norm, chan_scale if last else None, residual if last else None)
         return a
 

@@ -100,6 +100,7 @@ class NetRuntime:
             g = self.grad_arena[off:off + p.numel()].view(p.shape)
             if p.grad is None or p.grad.data_ptr() != g.data_ptr():
                 p.grad = g
+            p._bcp_direct = True          # kernels accumulate straight into the arena view (ops._direct)
         return self.grad_arena
 
     # ---- operand packs ------------------------------------------------------------------------

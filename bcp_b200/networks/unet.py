@@ -44,18 +44,20 @@ class ConvBlock(nn.Module):
     def forward(self, a):
         rt = self._rt
         c0, bn0, act0, drop, c1, bn1, act1 = self.conv_conv
+        bz0 = bn0.training or not bn0.track_running_stats       # batch-stat BN next: bias gradient is identically zero
+        bz1 = bn1.training or not bn1.track_running_stats
         if a.dtype != torch.bfloat16:
             if c0.in_channels != 1:
                 raise NotImplementedError("first layer with in_chns != 1")
-            y = ops.ConvFirst.apply(a, c0.weight, c0.bias)
+            y = ops.ConvFirst.apply(a, c0.weight, c0.bias, bz0)
         else:
-            y = ops.ConvSame.apply(a, c0.weight, c0.bias, rt.pack(c0), (1, 3, 3))
+            y = ops.ConvSame.apply(a, c0.weight, c0.bias, rt.pack(c0), (1, 3, 3), bz0)
         keep, scale = None, 1.0
         if drop.training:
             n, cb, x, yy, z, _ = y.shape
             keep, scale = NetRuntime.element_dropout_keep(drop, n, cb * 8, (x, yy, z), y.device, rt.spg)
         a = self._bn_act(y, bn0, act0.negative_slope, keep, scale)
-        y = ops.ConvSame.apply(a, c1.weight, c1.bias, rt.pack(c1), (1, 3, 3))
+        y = ops.ConvSame.apply(a, c1.weight, c1.bias, rt.pack(c1), (1, 3, 3), bz1)
         return self._bn_act(y, bn1, act1.negative_slope)
 
 

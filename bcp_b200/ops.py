@@ -40,6 +40,28 @@ def _f32(n, device):
     return torch.empty(int(n), dtype=torch.float32, device=device)
 
 
+def _direct(param):
+    """Gradient target for kernels that can accumulate in place: the parameter's view of the flat gradient arena
+    (set up by NetRuntime.ensure_grad_arena), or None to return the gradient through autograd as usual."""
+    if param is None or not getattr(param, "_bcp_direct", False):
+        return None
+    g = param.grad
+    return g if (g is not None and g.is_contiguous()) else None
+
+
+_COUNTERS = {}
+
+
+def _counter(device):
+    """Zero-initialised device int used by the 'last block finalises' reductions (self-resetting, stream-ordered)."""
+    key = (device.type, device.index)
+    c = _COUNTERS.get(key)
+    if c is None:
+        c = torch.zeros(16, dtype=torch.int32, device=device)
+        _COUNTERS[key] = c
+    return c
+
+
 # ----------------------------------------------------------------------------------------------
 # layout converts
 # ----------------------------------------------------------------------------------------------
@@ -112,20 +134,35 @@ def _conv_same(a, wpack, bias, cout, kernel, allow_tc=True):
     return out
 
 
-def _wgrad(inp, outgrad, cin, cout, in_dims, kernel, stride, pad, wshape, allow_tc=True):
+def _wgrad(inp, outgrad, cin, cout, in_dims, kernel, stride, pad, wshape, allow_tc=True, into=None):
+    """Weight gradient [cout][cin][taps].  ``into``: accumulate into this tensor (flat-arena view) and return None."""
     n = inp.shape[0]
+    acc = 1 if into is not None else 0
     same = tuple(stride) == (1, 1, 1) and tuple(pad) == tuple(k // 2 for k in kernel)
     if allow_tc and _TC_WGRAD and same and LIB.query("bcp_conv_tc_wgrad_supported", cin, cout, i3(*in_dims), i3(*kernel)):
         ws = _f32(LIB.query("bcp_conv_tc_wgrad_workspace_floats", n, cin, cout, i3(*in_dims), i3(*kernel)), inp.device)
-        dw = torch.empty(wshape, dtype=torch.float32, device=inp.device)
-        LIB.call("bcp_conv_tc_wgrad", ptr(inp), ptr(outgrad), ptr(dw), ptr(ws), n, cin, cout, i3(*in_dims), i3(*kernel), stream())
-        return dw
+        dw = into if into is not None else torch.empty(wshape, dtype=torch.float32, device=inp.device)
+        LIB.call("bcp_conv_tc_wgrad", ptr(inp), ptr(outgrad), ptr(dw), ptr(ws), n, cin, cout, i3(*in_dims), i3(*kernel), acc, stream())
+        return None if into is not None else dw
     od = [(in_dims[i] + 2 * pad[i] - kernel[i]) // stride[i] + 1 for i in range(3)]
     ws = _f32(LIB.query("bcp_conv_wgrad_workspace_floats", n, cin, cout, i3(*od), i3(*kernel)), inp.device)
-    dw = torch.empty(wshape, dtype=torch.float32, device=inp.device)
+    dw = into if into is not None else torch.empty(wshape, dtype=torch.float32, device=inp.device)
     LIB.call("bcp_conv_direct_wgrad", ptr(inp), ptr(outgrad), ptr(dw), ptr(ws), n, cin, cout, i3(*in_dims), i3(*kernel),
-             i3(*stride), i3(*pad), stream())
-    return dw
+             i3(*stride), i3(*pad), acc, stream())
+    return None if into is not None else dw
+
+
+def _bias_grad(dy, c, is_zero, into=None):
+    """Conv bias gradient = per-channel sum of dy.  When the conv feeds a batch-statistic normalisation, dy is the
+    norm's input gradient and sums to zero per channel identically (sum(g - mean(g) - xhat*mean(g*xhat)) = 0 because
+    sum(xhat) = 0); the reference's value there is fp32 rounding noise (~1e-7 relative).  Skip the reduction then."""
+    if is_zero:
+        return None if into is not None else torch.zeros(c, dtype=torch.float32, device=dy.device)
+    g = _chan_sum(dy, c)
+    if into is not None:
+        into.add_(g)
+        return None
+    return g
 
 
 def _chan_sum(t, c):
@@ -141,12 +178,13 @@ class ConvSame(Function):
     """nn.Conv3d(k=3,p=1) / nn.Conv2d(k=3,p=1 | k=1) on CB8 (networks/VNet.py:17, networks/unet.py:20,24,49)."""
 
     @staticmethod
-    def forward(ctx, a, weight, bias, pack: ConvPack, kernel):
+    def forward(ctx, a, weight, bias, pack: ConvPack, kernel, bias_grad_is_zero=False):
         _require_cuda(a, "conv")
         a = a.contiguous()
         cout = weight.shape[0]
         ctx.save_for_backward(a, weight)
-        ctx.pack, ctx.kernel, ctx.has_bias = pack, tuple(kernel), bias is not None
+        ctx.pack, ctx.kernel, ctx.has_bias, ctx.bz = pack, tuple(kernel), bias is not None, bias_grad_is_zero
+        ctx.bias_ref = bias
         return _conv_same(a, pack.k[0], bias, cout, kernel)
 
     @staticmethod
@@ -159,10 +197,11 @@ class ConvSame(Function):
         if ctx.needs_input_grad[0]:
             da = _conv_same(dy, ctx.pack.k[1], None, cin, k)
         if ctx.needs_input_grad[1]:
-            dw = _wgrad(a, dy, cin, cout, (x, y, z), k, (1, 1, 1), (k[0] // 2, k[1] // 2, k[2] // 2), weight.shape)
+            dw = _wgrad(a, dy, cin, cout, (x, y, z), k, (1, 1, 1), (k[0] // 2, k[1] // 2, k[2] // 2), weight.shape,
+                        into=_direct(weight))
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = _chan_sum(dy, cout)
-        return da, dw, db, None, None
+            db = _bias_grad(dy, cout, ctx.bz, _direct(ctx.bias_ref))
+        return da, dw, db, None, None, None
 
 
 def _s2_fwd(inp, pack: ConvPack, bias, cin, cout, half_dims, mode):
@@ -181,23 +220,26 @@ def _s2_fwd(inp, pack: ConvPack, bias, cin, cout, half_dims, mode):
     return out
 
 
-def _s2_wgrad(full, half, c_full, c_half, half_dims, wshape):
+def _s2_wgrad(full, half, c_full, c_half, half_dims, wshape, into=None):
     """dW[c_half][c_full][8] = sum_i half[i] (x) full[2i+t]."""
     n = full.shape[0]
     hx, hy, hz = half_dims
     if _TC_WGRAD and LIB.query("bcp_conv_tc_s2_wgrad_supported", c_half, c_full, i3(*half_dims)):
         ws = _f32(LIB.query("bcp_conv_tc_s2_wgrad_workspace_floats", n, c_half, c_full, i3(*half_dims)), full.device)
-        dw = torch.empty(wshape, dtype=torch.float32, device=full.device)
-        LIB.call("bcp_conv_tc_s2_wgrad", ptr(full), ptr(half), ptr(dw), ptr(ws), n, c_half, c_full, i3(*half_dims), stream())
-        return dw
-    return _wgrad(full, half, c_full, c_half, (2 * hx, 2 * hy, 2 * hz), (2, 2, 2), (2, 2, 2), (0, 0, 0), wshape, allow_tc=False)
+        dw = into if into is not None else torch.empty(wshape, dtype=torch.float32, device=full.device)
+        LIB.call("bcp_conv_tc_s2_wgrad", ptr(full), ptr(half), ptr(dw), ptr(ws), n, c_half, c_full, i3(*half_dims),
+                 1 if into is not None else 0, stream())
+        return None if into is not None else dw
+    return _wgrad(full, half, c_full, c_half, (2 * hx, 2 * hy, 2 * hz), (2, 2, 2), (2, 2, 2), (0, 0, 0), wshape, allow_tc=False,
+                  into=into)
 
 
 class ConvDown2(Function):
     """nn.Conv3d(k=2, s=2) (networks/VNet.py:74).  weight [Cout][Cin][2,2,2]; packs: kind 0 (fwd), kinds 2/3 (dgrad)."""
 
     @staticmethod
-    def forward(ctx, a, weight, bias, pack: ConvPack):
+    def forward(ctx, a, weight, bias, pack: ConvPack, bias_grad_is_zero=False):
+        ctx.bz, ctx.bias_ref = bias_grad_is_zero, bias
         _require_cuda(a, "conv_down2")
         a = a.contiguous()
         n, cin, x, y, z = act_dims(a)
@@ -217,17 +259,18 @@ class ConvDown2(Function):
         if ctx.needs_input_grad[0]:
             da = _s2_fwd(dy, ctx.pack, None, cout, cin, half, 2)
         if ctx.needs_input_grad[1]:
-            dw = _s2_wgrad(a, dy, cin, cout, half, weight.shape)
+            dw = _s2_wgrad(a, dy, cin, cout, half, weight.shape, into=_direct(weight))
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = _chan_sum(dy, cout)
-        return da, dw, db, None
+            db = _bias_grad(dy, cout, ctx.bz, _direct(ctx.bias_ref))
+        return da, dw, db, None, None
 
 
 class ConvUp2(Function):
     """nn.ConvTranspose3d(k=2, s=2) (networks/VNet.py:101).  weight [Cin][Cout][2,2,2]; packs: kinds 2/3 (fwd), kind 0 (dgrad)."""
 
     @staticmethod
-    def forward(ctx, a, weight, bias, pack: ConvPack):
+    def forward(ctx, a, weight, bias, pack: ConvPack, bias_grad_is_zero=False):
+        ctx.bz, ctx.bias_ref = bias_grad_is_zero, bias
         _require_cuda(a, "conv_up2")
         a = a.contiguous()
         n, cin, x, y, z = act_dims(a)
@@ -246,17 +289,18 @@ class ConvUp2(Function):
         if ctx.needs_input_grad[0]:
             da = _s2_fwd(dy, ctx.pack, None, cout, cin, (x, y, z), 1)
         if ctx.needs_input_grad[1]:
-            dw = _s2_wgrad(dy, a, cout, cin, (x, y, z), weight.shape)     # half = layer input, full = dy
+            dw = _s2_wgrad(dy, a, cout, cin, (x, y, z), weight.shape, into=_direct(weight))     # half = layer input, full = dy
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = _chan_sum(dy, cout)
-        return da, dw, db, None
+            db = _bias_grad(dy, cout, ctx.bz, _direct(ctx.bias_ref))
+        return da, dw, db, None, None
 
 
 class ConvFirst(Function):
     """First layer, Cin = 1, planar fp32 input (networks/VNet.py:151 block_one, networks/unet.py:72 in_conv)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, bias_grad_is_zero=False):
+        ctx.bz, ctx.bias_ref = bias_grad_is_zero, bias
         _require_cuda(x, "conv_first")
         x = x.contiguous().float()
         assert x.shape[1] == 1, "conv_first takes single-channel input"
@@ -280,11 +324,15 @@ class ConvFirst(Function):
         dw = db = None
         if ctx.needs_input_grad[1]:
             ws = _f32(LIB.query("bcp_conv_first_wgrad_workspace_floats", n, cout, i3(*dims), i3(*kernel)), x.device)
-            dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)
-            LIB.call("bcp_conv_first_wgrad", ptr(x), ptr(dy), ptr(dw), ptr(ws), n, cout, i3(*dims), i3(*kernel), stream())
+            into = _direct(weight)
+            dw = into if into is not None else torch.empty(weight.shape, dtype=torch.float32, device=x.device)
+            LIB.call("bcp_conv_first_wgrad", ptr(x), ptr(dy), ptr(dw), ptr(ws), n, cout, i3(*dims), i3(*kernel),
+                     1 if into is not None else 0, stream())
+            if into is not None:
+                dw = None
         if has_bias and ctx.needs_input_grad[2]:
-            db = _chan_sum(dy, cout)
-        return None, dw, db
+            db = _bias_grad(dy, cout, ctx.bz, _direct(ctx.bias_ref))
+        return None, dw, db, None
 
 
 class Head(Function):
@@ -304,6 +352,7 @@ class Head(Function):
         LIB.call("bcp_head_fwd", ptr(a), ptr(w), ptr(bias), ptr(out), n, cin, ncls, i3(x, y, z), i3(*kernel), stream())
         ctx.save_for_backward(a, weight)
         ctx.meta = (n, cin, ncls, (x, y, z), kernel, bias is not None)
+        ctx.bias_ref = bias
         return out
 
     @staticmethod
@@ -318,9 +367,14 @@ class Head(Function):
             LIB.call("bcp_head_dgrad", ptr(dlog), ptr(w), ptr(da), n, cin, ncls, i3(*dims), i3(*kernel), stream())
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
             ws = _f32(LIB.query("bcp_head_wgrad_workspace_floats", n, cin, ncls, i3(*dims), i3(*kernel)), a.device)
-            dw = torch.empty(weight.shape, dtype=torch.float32, device=a.device)
-            db = torch.empty(ncls, dtype=torch.float32, device=a.device) if has_bias else None
-            LIB.call("bcp_head_wgrad", ptr(a), ptr(dlog), ptr(dw), ptr(db), ptr(ws), n, cin, ncls, i3(*dims), i3(*kernel), stream())
+            iw, ib = _direct(weight), _direct(ctx.bias_ref)
+            direct = iw is not None and (ib is not None or not has_bias)
+            dw = iw if direct else torch.empty(weight.shape, dtype=torch.float32, device=a.device)
+            db = (ib if direct else torch.empty(ncls, dtype=torch.float32, device=a.device)) if has_bias else None
+            LIB.call("bcp_head_wgrad", ptr(a), ptr(dlog), ptr(dw), ptr(db), ptr(ws), n, cin, ncls, i3(*dims), i3(*kernel),
+                     1 if direct else 0, stream())
+            if direct:
+                dw = db = None
         return da, dw, db, None
 
 
@@ -350,7 +404,7 @@ class NormAct(Function):
         if mode == "batch":
             ws = _f32(LIB.query("bcp_norm_workspace_floats", n, c, s), dev)
             LIB.call("bcp_norm_stats", ptr(y), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), ptr(nbt),
-                     ptr(stat), ptr(coef), ptr(ws), n, c, s, spg, float(eps), float(momentum), stream())
+                     ptr(stat), ptr(coef), ptr(ws), ptr(_counter(dev)), n, c, s, spg, float(eps), float(momentum), stream())
         elif mode == "eval":
             LIB.call("bcp_norm_eval_coef", ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), ptr(stat), ptr(coef),
                      c, groups, float(eps), stream())
@@ -367,6 +421,7 @@ class NormAct(Function):
         ctx.save_for_backward(y, stat, coef, chan_scale, elem_keep)
         ctx.meta = (n, c, s, spg, float(slope), float(elem_scale), mode, gamma is not None, beta is not None,
                     residual is not None)
+        ctx.affine_refs = (gamma, beta)
         return out
 
     @staticmethod
@@ -377,12 +432,17 @@ class NormAct(Function):
         dev = y.device
         dy = torch.empty_like(y)
         need_affine = mode != "none" and (has_g or has_b)
-        dgamma = torch.empty(c, dtype=torch.float32, device=dev) if need_affine else None
-        dbeta = torch.empty(c, dtype=torch.float32, device=dev) if need_affine else None
+        ig, ib = _direct(ctx.affine_refs[0]), _direct(ctx.affine_refs[1])
+        direct = need_affine and ig is not None and ib is not None
+        dgamma = (ig if direct else torch.empty(c, dtype=torch.float32, device=dev)) if need_affine else None
+        dbeta = (ib if direct else torch.empty(c, dtype=torch.float32, device=dev)) if need_affine else None
         sums = torch.empty(n // spg, c, 2, dtype=torch.float32, device=dev)
         ws = _f32(LIB.query("bcp_norm_workspace_floats", n, c, s), dev)
         LIB.call("bcp_norm_bwd", ptr(da), ptr(y), ptr(dy), ptr(stat), ptr(coef), ptr(chan_scale), ptr(elem_keep), elem_scale,
-                 ptr(dgamma), ptr(dbeta), ptr(sums), ptr(ws), n, c, s, spg, slope, 1 if mode == "batch" else 0, stream())
+                 ptr(dgamma), ptr(dbeta), ptr(sums), ptr(ws), ptr(_counter(dev)), n, c, s, spg, slope,
+                 1 if mode == "batch" else 0, 1 if direct else 0, stream())
+        if direct:
+            dgamma = dbeta = None
         return (dy, dgamma if has_g else None, dbeta if has_b else None, None, None, None, None, None, None, None, None,
                 None, None, None, da if has_res else None)
 

@@ -126,13 +126,17 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = [0.0]
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         out = None
+        h0 = time.perf_counter()
         for _ in range(steps):
             out = fn()
+        host_ms[0] = (time.perf_counter() - h0) * 1e3 / steps        # CPU time to ENQUEUE a step (no sync inside)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -159,6 +163,7 @@ def run_native(args):
     l0 = LIB.launches
     ms, r = timed(step_resident, args.steps)
     launches = LIB.launches - l0
+    host_enqueue_ms = host_ms[0]
     clocks = sampler.stop() if rank == 0 else None
     loss = float(r["loss"])
     ms_e2e, _ = timed(step_e2e, args.steps)
@@ -180,7 +185,7 @@ def run_native(args):
                                "4 mixed student patches (BASELINE configs[1]); random-init weights",
                    "parallelism": "dp%d" % world, "per_gpu_student_patches": 4,
                    "l2": "per-step working set (>2 GB of activations) exceeds the 126 MB L2; no explicit flush"},
-        "loss": loss, "gpu_launches": launches, "clocks": clocks,
+        "loss": loss, "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks,
         "e2e": {"value": e2e, "unit": "patches/s", "h2d_bytes_per_step": vol_h.numel() * 4 + lab_h.numel(),
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
         "step_flops": FLOP_PER_STEP, "step_tflops": world * FLOP_PER_STEP * args.steps / (ms / 1e3) / 1e12,

@@ -103,11 +103,13 @@ int bcp_cb8_to_planar(const void* in, float* out, int n, int c, long long s, cud
 /* ---- normalisation (train-mode nn.BatchNorm3d/2d: networks/VNet.py:19, networks/unet.py:21,25;
  * nn.InstanceNorm3d: pancreas/Vnet.py:25,49,76) fused with ReLU/LeakyReLU, Dropout3d/Dropout and the skip add.
  * groups of `spg` consecutive samples share statistics (BatchNorm of one reference forward call = one group;
- * InstanceNorm: spg = 1).  stat/coef: fp32 [n/spg][c][2] = {mean, invstd} / {scale, shift}. */
+ * InstanceNorm: spg = 1).  stat/coef: fp32 [n/spg][c][2] = {mean, invstd} / {scale, shift}.
+ * `counter`: one device int, zero before the first call; the last block of the reduction grid finalises in fixed order
+ * and resets it (deterministic; lets one launch replace partial + finalize kernels). */
 int bcp_norm_chunks(long long s);
 long long bcp_norm_workspace_floats(int n, int c, long long s);
 int bcp_norm_stats(const void* y, const float* gamma, const float* beta, float* running_mean, float* running_var,
-                   long long* num_batches_tracked, float* stat, float* coef, float* workspace,
+                   long long* num_batches_tracked, float* stat, float* coef, float* workspace, int* counter,
                    int n, int c, long long s, int spg, float eps, float momentum, cudaStream_t stream);
 int bcp_norm_eval_coef(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                        float* stat, float* coef, int c, int groups, float eps, cudaStream_t stream);
@@ -116,32 +118,36 @@ int bcp_norm_apply(const void* y, void* out, const float* coef, const float* cha
                    cudaStream_t stream);
 int bcp_norm_bwd(const void* dact, const void* y, void* dy, const float* stat, const float* coef, const float* chan_scale,
                  const unsigned char* elem_keep, float elem_scale, float* dgamma, float* dbeta, float* sums,
-                 float* workspace, int n, int c, long long s, int spg, float slope, int stats_grad, cudaStream_t stream);
+                 float* workspace, int* counter, int n, int c, long long s, int spg, float slope, int stats_grad,
+                 int accumulate, cudaStream_t stream);
 
 /* ---- convolutions (nn.Conv3d / nn.Conv2d / nn.ConvTranspose3d call sites: networks/VNet.py:17,74,101,210;
  * networks/unet.py:20,24,49,102; pancreas/Vnet.py:19,43,70,128).  dims/kernel/stride/pad are int[3] (x,y,z).
  * conv_tc_*: tcgen05 + TMA implicit GEMM for 3x3x3 / 1x3x3, stride 1, 'same' padding, channels % 16 == 0.
- * conv_direct_*: CUDA-core kernels for everything else (see csrc/conv_direct.cu). */
+ * conv_direct_*: CUDA-core kernels for everything else (see csrc/conv_direct.cu).
+ * Every weight-gradient entry point takes `accumulate`: 0 = overwrite dw, 1 = dw += (lets the host point dw straight
+ * into the flat gradient arena instead of adding a temporary). */
 int bcp_conv_direct_fwd(const void* in, const void* wpack, const float* bias, void* out, int n, int cin, int cout,
                         const int* in_dims, const int* kernel, const int* stride, const int* pad, int transposed,
                         cudaStream_t stream);
 long long bcp_conv_wgrad_workspace_floats(int n, int cin, int cout, const int* out_dims, const int* kernel);
 int bcp_conv_direct_wgrad(const void* in, const void* outgrad, float* dw, float* workspace, int n, int cin, int cout,
-                          const int* in_dims, const int* kernel, const int* stride, const int* pad, cudaStream_t stream);
+                          const int* in_dims, const int* kernel, const int* stride, const int* pad, int accumulate,
+                          cudaStream_t stream);
 long long bcp_chan_sum_workspace_floats(int n, int c, long long s);
 int bcp_chan_sum(const void* x, float* out, float* workspace, int n, int c, long long s, cudaStream_t stream);
 int bcp_conv_first_fwd(const float* in, const float* w, const float* bias, void* out, int n, int cout,
                        const int* dims, const int* kernel, cudaStream_t stream);
 long long bcp_conv_first_wgrad_workspace_floats(int n, int cout, const int* dims, const int* kernel);
 int bcp_conv_first_wgrad(const float* in, const void* outgrad, float* dw, float* workspace, int n, int cout,
-                         const int* dims, const int* kernel, cudaStream_t stream);
+                         const int* dims, const int* kernel, int accumulate, cudaStream_t stream);
 int bcp_head_fwd(const void* in, const float* w, const float* bias, float* logits, int n, int cin, int ncls,
                  const int* dims, const int* kernel, cudaStream_t stream);
 int bcp_head_dgrad(const float* dlogits, const float* w, void* din, int n, int cin, int ncls, const int* dims,
                    const int* kernel, cudaStream_t stream);
 long long bcp_head_wgrad_workspace_floats(int n, int cin, int ncls, const int* dims, const int* kernel);
 int bcp_head_wgrad(const void* in, const float* dlogits, float* dw, float* db, float* workspace, int n, int cin, int ncls,
-                   const int* dims, const int* kernel, cudaStream_t stream);
+                   const int* dims, const int* kernel, int accumulate, cudaStream_t stream);
 
 /* tcgen05 implicit-GEMM convolution, stride 1, 'same' zero padding, kernel (kx,3,3) with kx in {1,3}.
  * wpack is the kind-0 (forward) or kind-1 (dgrad) pack.  Returns -2 for shapes it does not take. */
@@ -155,7 +161,7 @@ int bcp_conv_tc_fwd(const void* in, const void* wpack, const float* bias, void* 
 int bcp_conv_tc_wgrad_supported(int cin, int cout, const int* dims, const int* kernel);
 long long bcp_conv_tc_wgrad_workspace_floats(int n, int cin, int cout, const int* dims, const int* kernel);
 int bcp_conv_tc_wgrad(const void* a, const void* dy, float* dw, float* workspace, int n, int cin, int cout,
-                      const int* dims, const int* kernel, cudaStream_t stream);
+                      const int* dims, const int* kernel, int accumulate, cudaStream_t stream);
 
 /* tcgen05 stride-2 family (nn.Conv3d(k=2,s=2) networks/VNet.py:74, nn.ConvTranspose3d(k=2,s=2) networks/VNet.py:101).
  * half_dims = half-resolution grid.  mode 1 gather: in = full-res [cin], wpack kind 0, out = half-res [cout].
@@ -167,7 +173,7 @@ int bcp_conv_tc_s2_fwd(const void* in, const void* wpack, const float* bias, voi
 int bcp_conv_tc_s2_wgrad_supported(int c_half, int c_full, const int* half_dims);
 long long bcp_conv_tc_s2_wgrad_workspace_floats(int n, int c_half, int c_full, const int* half_dims);
 int bcp_conv_tc_s2_wgrad(const void* full, const void* half, float* dw, float* workspace, int n, int c_half, int c_full,
-                         const int* half_dims, cudaStream_t stream);
+                         const int* half_dims, int accumulate, cudaStream_t stream);
 
 /* ---- resampling (networks/unet.py:37 MaxPool2d(2); :50 Upsample(bilinear, align_corners=True);
  * networks/VNet.py:249 MaxPool3d(3, stride=2)).  planes = n * ceil(c/8) * X. */
