@@ -22,6 +22,7 @@
 #include "../../include/bcp_b200.h"
 #include <cuda.h>
 #include <mutex>
+#include <stdlib.h>
 
 namespace bcp {
 
@@ -502,6 +503,7 @@ struct WgParams {
   int T, TP, npass_t, MH, PL;     // taps, taps per pass, tap passes, M halves, dy planes loaded per brick
   int S, splits, tmem_cols;
   int s2;                         // 1: stride-2 family (B bricks are per-tap strided gathers of the full-res tensor)
+  int MM, m64map;                 // MMA M (128 or 64) and the TMEM row->lane map assumed for M = 64
   unsigned a_tx_bytes, dy_tx_bytes, a_alloc_bytes, dy_alloc_bytes, slot_bytes, offBar, tap_bytes;
 };
 
@@ -581,7 +583,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   } else if (warp == 1) {
     if (has_work) {
       // M = 128, N = Cin, both operands MN-major (bits 15, 16)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.Cin >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.Cin >> 3) << 17) | ((uint32_t)(p.MM >> 4) << 24);
       // constant descriptor parts; per MMA only the 16-byte-unit start address changes
       const uint64_t adesc0 = make_desc(0, 128u, (uint32_t)p.rows_dy * 16u);
       const uint64_t bdesc0 = make_desc(0, 128u, (uint32_t)p.rows_a * 16u);
@@ -626,7 +628,15 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     }
   } else {
     const int q = warp & 3;
-    const int co = mh * 128 + q * 32 + lane;
+    int co = mh * 128 + q * 32 + lane;
+    if (p.MM == 64) {
+      // M = 64 accumulators occupy 64 of the 128 TMEM lanes; m64map selects the row -> lane convention
+      //   0: row r at lane (r & 15) + 32 * (r >> 4)      1: row r at lane r      2: row r at lane (r & 31) + 64 * (r >> 5)
+      const int l = q * 32 + lane;
+      if (p.m64map == 0) co = ((l & 31) < 16) ? ((l >> 5) * 16 + (l & 15)) : (1 << 30);
+      else if (p.m64map == 1) co = (l < 64) ? l : (1 << 30);
+      else co = ((l & 63) < 32) ? ((l >> 6) * 32 + (l & 31)) : (1 << 30);
+    }
     if (has_work) {
       mbar_wait(tmem_full, 0);
       tc_fence_after();
@@ -734,11 +744,16 @@ static bool plan(TcParams& p, int nsm) {
           if (MT * Ns > 512) break;
           const long long rows_alloc = (long long)MT * 128 + ((long long)(p.kx - 1) * HY + 2) * HZ + 2;
           const long long slotA = ((rows_h + (rows_alloc > rows_h ? rows_alloc : rows_h)) * 16 + 127) / 128 * 128;
+          // A slots: 2..3 (one (brick, 16-channel) chunk each); the rest of shared memory goes to weight stages, whose
+          // depth hides the L2 latency of the cp.async.bulk stream (3..8 stages)
           int SB = 3;
           long long avail = (long long)SMEM_BUDGET - 1024 - (long long)SB * stageB;
           int SA = (int)(avail / slotA);
           if (SA < 2) break;
-          if (SA > 4) SA = 4;
+          if (SA > 3) SA = 3;
+          SB = (int)(((long long)SMEM_BUDGET - 1024 - (long long)SA * slotA) / stageB);
+          if (SB > 8) SB = 8;
+          if (SB < 3) SB = 3;
           const int nbx = (p.X + BX - 1) / BX, nby = (p.Y + BY - 1) / BY, nbz = (p.Z + BZ - 1) / BZ;
           const long long nb = (long long)p.N * nbx * nby * nbz;
           const long long items = nb * NS;
@@ -851,6 +866,17 @@ static bool s2_plan(S2Params& p) {
   return true;
 }
 
+// M = 64 accumulate mode for the weight-gradient kernels (output channels <= 64): halves the A-operand shared-memory
+// traffic.  BCP_WG_M64 = -1 disables it, 0/1/2 pick the TMEM row->lane map (validated on the GPU by the parity tests).
+static int wg_m64_mode() {
+  static int mode = -2;
+  if (mode == -2) {
+    const char* e = getenv("BCP_WG_M64");
+    mode = e ? atoi(e) : -1;
+  }
+  return mode;
+}
+
 static bool wg_shape_ok(int cin, int cout, const int* dims, const int* kernel) {
   if (!shape_ok(cin, cout, dims, kernel)) return false;
   if (dims[2] + 2 > 256) return false;                 // one z-line (+halo) must fit a TMA box
@@ -865,6 +891,8 @@ static bool wg_plan(WgParams& p, int nsm) {
   p.npass_t = (p.T + p.TP - 1) / p.TP;
   p.MH = (p.Cout > 128) ? 2 : 1;
   p.PL = (p.Cout / 8 < 16) ? p.Cout / 8 : 16;
+  p.MM = (p.Cout <= 64 && wg_m64_mode() >= 0) ? 64 : 128;
+  p.m64map = wg_m64_mode() < 0 ? 0 : wg_m64_mode();
   p.HZ = p.Z + 2;
   p.ZP = (p.Z + 15) / 16 * 16;
   const int npass = p.npass_t * p.MH;
@@ -883,7 +911,7 @@ static bool wg_plan(WgParams& p, int nsm) {
       const long long rows_a = (long long)HX * HY * p.HZ, rows_dy = (long long)BX * BY * p.ZP;
       if (rows_a >= 16384 || rows_dy >= 16384) break;
       const long long a_tx = rows_a * 16 * Cib, dy_tx = rows_dy * 16 * p.PL;
-      const long long a_alloc = (a_tx + 256 + 127) / 128 * 128, dy_alloc = (rows_dy * 16 * 16 + 127) / 128 * 128;
+      const long long a_alloc = (a_tx + 256 + 127) / 128 * 128, dy_alloc = (rows_dy * 16 * (p.MM / 8) + 127) / 128 * 128;
       const long long slot = a_alloc + dy_alloc;
       int S = (int)((SMEM_BUDGET - 1024) / slot);
       if (S < 2) break;
@@ -1074,6 +1102,8 @@ static bool wg_s2_plan(WgParams& p, int nsm) {
   p.npass_t = (8 + p.TP - 1) / p.TP;
   p.MH = (p.Cout > 128) ? 2 : 1;
   p.PL = (p.Cout / 8 < 16) ? p.Cout / 8 : 16;
+  p.MM = (p.Cout <= 64 && wg_m64_mode() >= 0) ? 64 : 128;
+  p.m64map = wg_m64_mode() < 0 ? 0 : wg_m64_mode();
   p.ZP = (p.Z + 15) / 16 * 16;
   if (p.ZP > 128) return false;
   p.HX = p.HY = p.HZ = 0; p.s2 = 1; p.kx = 2;
@@ -1087,7 +1117,7 @@ static bool wg_s2_plan(WgParams& p, int nsm) {
       const long long rows = (long long)BX * BY * p.ZP;
       if (rows >= 16384) break;
       const long long tap_bytes = rows * 16 * Cib, a_alloc = ((long long)p.TP * tap_bytes + 127) / 128 * 128;
-      const long long dy_tx = rows * 16 * p.PL, dy_alloc = (rows * 256 + 127) / 128 * 128;
+      const long long dy_tx = rows * 16 * p.PL, dy_alloc = (rows * 16 * (p.MM / 8) + 127) / 128 * 128;
       const long long slot = a_alloc + dy_alloc;
       int S = (int)((SMEM_BUDGET - 1024) / slot);
       if (S < 2) break;
