@@ -1,7 +1,8 @@
 // Largest-connected-component filter on the GPU (replaces the reference's per-sample
 // GPU->CPU->GPU round trip through skimage.measure.label: LA_BCP_train.py:65-77,
 // pancreas/pancreas_utils.py:284-296, ACDC_BCP_train.py:89-109).
-//   * label-equivalence union-find (atomicMin hooks, roots = smallest raster index of a component)
+//   * two-phase union-find: tile-local labelling in shared memory, then unions across tile borders only
+//     (CAS hooks of the larger root under the smaller: roots = smallest raster index of a component)
 //   * integer histogram of component sizes (atomicAdd on ints: order-independent result)
 //   * per (sample, class) arg-max with ties -> smallest root == first component in raster order,
 //     which is what np.argmax(np.bincount(labels.flat)[1:]) + 1 picks from skimage's raster labelling
@@ -47,17 +48,79 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
   }
 }
 
-__global__ void cc_init_kernel(const unsigned char* __restrict__ seg, int* __restrict__ L, int* __restrict__ cnt,
-                               unsigned long long* __restrict__ best, long long total, int V, int nbest) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    L[i] = seg[i] ? (int)(i % V) : -1;
-    cnt[i] = 0;
+// ---- phase 1: tile-local labelling in shared memory (tile = 4 x 4 x 32 voxels, one thread per voxel).  Local
+// indices are monotone in the global raster order, so a local root is the first voxel of its local component; it is
+// written out as a GLOBAL index, which makes phase 2 a plain continuation of the same union-find forest.
+constexpr int TX = 4, TY = 4, TZ = 32, TV = TX * TY * TZ;
+
+__device__ __forceinline__ int sfind(volatile int* L, int v) {
+  int curr = L[v];
+  if (curr != v) {
+    int prev = v, next;
+    while (curr > (next = L[curr])) { L[prev] = next; prev = curr; curr = next; }
   }
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nbest; i += stride) best[i] = 0ull;
+  return curr;
+}
+__device__ __forceinline__ void sunion(int* L, int a, int b) {
+  int ra = sfind(L, a), rb = sfind(L, b);
+  while (ra != rb) {
+    if (ra < rb) { const int t = ra; ra = rb; rb = t; }
+    const int seen = atomicCAS(&L[ra], ra, rb);
+    if (seen == ra) return;
+    ra = seen;
+  }
 }
 
-__global__ void cc_merge_kernel(const unsigned char* __restrict__ seg, int* __restrict__ L, int N, int X, int Y, int Z, int conn) {
+__global__ void __launch_bounds__(TV) cc_local_kernel(const unsigned char* __restrict__ seg, int* __restrict__ L,
+                                                      int* __restrict__ cnt, unsigned long long* __restrict__ best,
+                                                      int N, int X, int Y, int Z, int conn, int nbest) {
+  __shared__ int Ls[TV];
+  __shared__ unsigned char Ss[TV];
+  const int tilesz = (Z + TZ - 1) / TZ, tilesy = (Y + TY - 1) / TY, tilesx = (X + TX - 1) / TX;
+  int b = blockIdx.x;
+  const int tz = b % tilesz; b /= tilesz;
+  const int ty = b % tilesy; b /= tilesy;
+  const int tx = b % tilesx;
+  const int n = b / tilesx;
+  const int l = threadIdx.x;
+  const int lz = l % TZ, ly = (l / TZ) % TY, lx = l / (TZ * TY);
+  const int x = tx * TX + lx, y = ty * TY + ly, z = tz * TZ + lz;
+  const bool inside = x < X && y < Y && z < Z;
+  const long long V = (long long)X * Y * Z;
+  const long long gi = (long long)n * V + ((long long)x * Y + y) * Z + z;
+  const unsigned char c = inside ? seg[gi] : 0;
+  Ss[l] = c;
+  Ls[l] = l;
+  if (blockIdx.x == 0 && l < nbest) best[l] = 0ull;
+  __syncthreads();
+  if (c) {
+    for (int dx = -1; dx <= 0; ++dx)
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dz = -1; dz <= 1; ++dz) {
+          const int off = (dx * TY + dy) * TZ + dz;
+          if (off >= 0) continue;
+          if (abs(dx) + abs(dy) + abs(dz) > conn) continue;
+          const int xx = lx + dx, yy = ly + dy, zz = lz + dz;
+          if (xx < 0 || yy < 0 || yy >= TY || zz < 0 || zz >= TZ) continue;   // other tile: phase 2
+          if (Ss[l + off] == c) sunion(Ls, l, l + off);
+        }
+  }
+  __syncthreads();
+  if (inside) {
+    int out = -1;
+    if (c) {
+      int r = Ls[l], nx;
+      while (r > (nx = Ls[r])) r = nx;                                          // read-only root lookup
+      const int rz = r % TZ, ry = (r / TZ) % TY, rx = r / (TZ * TY);
+      out = ((tx * TX + rx) * Y + (ty * TY + ry)) * Z + (tz * TZ + rz);
+    }
+    L[gi] = out;
+    cnt[gi] = 0;
+  }
+}
+
+// ---- phase 2: unions across tile borders only (global forest)
+__global__ void cc_border_kernel(const unsigned char* __restrict__ seg, int* __restrict__ L, int N, int X, int Y, int Z, int conn) {
   const int V = X * Y * Z;
   const long long total = (long long)N * V;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -66,21 +129,23 @@ __global__ void cc_merge_kernel(const unsigned char* __restrict__ seg, int* __re
     if (!c) continue;
     const int n = (int)(gi / V), i = (int)(gi - (long long)n * V);
     const int z = i % Z, y = (i / Z) % Y, x = i / (Z * Y);
+    const int lx = x % TX, ly = y % TY, lz = z % TZ;
+    if (lx != 0 && ly != 0 && ly != TY - 1 && lz != 0 && lz != TZ - 1) continue;  // interior: no backward neighbour leaves the tile
     int* Ls = L + (long long)n * V;
     const unsigned char* ss = seg + (long long)n * V;
-    for (int dx = -1; dx <= 0; ++dx) {
-      for (int dy = -1; dy <= 1; ++dy) {
+    for (int dx = -1; dx <= 0; ++dx)
+      for (int dy = -1; dy <= 1; ++dy)
         for (int dz = -1; dz <= 1; ++dz) {
           const int off = (dx * Y + dy) * Z + dz;
-          if (off >= 0) continue;                                   // visit each undirected pair once
+          if (off >= 0) continue;
           if (abs(dx) + abs(dy) + abs(dz) > conn) continue;
           const int xx = x + dx, yy = y + dy, zz = z + dz;
           if (xx < 0 || yy < 0 || yy >= Y || zz < 0 || zz >= Z) continue;
+          const int tlx = lx + dx, tly = ly + dy, tlz = lz + dz;
+          if (tlx >= 0 && tly >= 0 && tly < TY && tlz >= 0 && tlz < TZ) continue;   // same tile: done in phase 1
           const int j = i + off;
           if (ss[j] == c) uf_union(Ls, i, j);
         }
-      }
-    }
   }
 }
 
@@ -153,8 +218,10 @@ int bcp_largest_cc(const unsigned char* seg, unsigned char* out_u8, float* out_f
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
   const int g = (int)blocks;
-  cc_init_kernel<<<g, 256, 0, stream>>>(seg, L, cnt, best, total, V, n * 4);
-  cc_merge_kernel<<<g, 256, 0, stream>>>(seg, L, n, X, Y, Z, connectivity);
+  const int tiles = n * ((X + TX - 1) / TX) * ((Y + TY - 1) / TY) * ((Z + TZ - 1) / TZ);
+  BCP_REQUIRE(n * 4 <= TV, "largest_cc: batch too large");
+  cc_local_kernel<<<tiles, TV, 0, stream>>>(seg, L, cnt, best, n, X, Y, Z, connectivity, n * 4);
+  cc_border_kernel<<<g, 256, 0, stream>>>(seg, L, n, X, Y, Z, connectivity);
   cc_count_kernel<<<g, 256, 0, stream>>>(seg, L, cnt, n, V);
   cc_best_kernel<<<g, 256, 0, stream>>>(seg, L, cnt, best, n, V);
   cc_select_kernel<<<g, 256, 0, stream>>>(seg, L, best, out_u8, out_f32, n, V);

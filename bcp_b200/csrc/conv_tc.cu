@@ -72,6 +72,12 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
@@ -120,8 +126,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 constexpr int TC_THREADS = 192;
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16* __restrict__ wpack, const float* __restrict__ bias,
-               uint4* __restrict__ out, const TcParams p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_w,
+               const float* __restrict__ bias, uint4* __restrict__ out, const TcParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
   const uint32_t sbase = smem_u32(smem);
@@ -139,6 +145,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16* __
     for (int i = 0; i < p.AS; ++i) { mbar_init(tmem_full + 8 * i, 1); mbar_init(tmem_empty + 8 * i, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(p.tmem_cols) : "memory");
@@ -179,18 +186,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16* __
             const uint32_t sb = ib % p.SB, pb = (ib / p.SB) & 1;
             mbar_wait(empty_b + 8 * sb, pb ^ 1);
             if (elect_one()) {
+              // ONE 4-D TMA box {8, Ns channels, 2 planes, TG taps} of the operand pack [T][Cin/8][Cout][8] per stage
+              // (per-tap bulk copies of 1-2 KB each made the TMA unit's per-operation cost the bottleneck on deep layers)
               mbar_expect_tx(full_b + 8 * sb, p.stageB_bytes);
-              const uint32_t tap_bytes = p.stageB_bytes / p.TG;
-              for (int g = 0; g < p.TG; ++g) {
-                const __nv_bfloat16* src = wpack + (((size_t)(t + g) * Cib + 2 * c) * (size_t)p.Cout + n0) * 8;
-                const uint32_t dst = b_base + sb * p.stageB_bytes + g * tap_bytes;
-                if (p.NS == 1) {
-                  bulk_load(dst, src, tap_bytes, full_b + 8 * sb);
-                } else {                                  // a channel slice is contiguous per 8-channel plane only
-                  bulk_load(dst, src, tap_bytes / 2, full_b + 8 * sb);
-                  bulk_load(dst + tap_bytes / 2, src + (size_t)p.Cout * 8, tap_bytes / 2, full_b + 8 * sb);
-                }
-              }
+              tma_load_4d(b_base + sb * p.stageB_bytes, &tmap_w, full_b + 8 * sb, 0, n0, 2 * c, t);
             }
             __syncwarp();
             ++ib;
@@ -872,7 +871,7 @@ static int wg_m64_mode() {
   static int mode = -2;
   if (mode == -2) {
     const char* e = getenv("BCP_WG_M64");
-    mode = e ? atoi(e) : -1;
+    mode = e ? atoi(e) : 0;       // map 0 validated against torch on B200 (tools/debug_conv_tc.py, profiles/)
   }
   return mode;
 }
@@ -986,12 +985,23 @@ int bcp_conv_tc_fwd(const void* in, const void* wpack, const float* bias, void* 
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) { set_last_error("conv_tc_fwd: cuTensorMapEncodeTiled failed (%d)", (int)cr); return BCP_ERR_CUDA; }
 
+  CUtensorMap tmap_w;
+  {
+    const cuuint64_t wdim[4] = {8, (cuuint64_t)cout, (cuuint64_t)(cin / 8), (cuuint64_t)p.T};
+    const cuuint64_t wstr[3] = {16, (cuuint64_t)cout * 16, (cuuint64_t)cout * 16 * (cin / 8)};
+    const cuuint32_t wbox[4] = {8, (cuuint32_t)p.Ns, 2, (cuuint32_t)p.TG};
+    const cuuint32_t wes[4] = {1, 1, 1, 1};
+    const CUresult cw = enc(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(wpack), wdim, wstr, wbox, wes,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cw != CUDA_SUCCESS) { set_last_error("conv_tc_fwd: weight tensor map failed (%d)", (int)cw); return BCP_ERR_CUDA; }
+  }
   const size_t smem = (size_t)p.offBar + 8 * (2 * p.SA + 2 * p.SB + 2 * p.AS) + 16 + 128;
   static std::once_flag attr_once;
   std::call_once(attr_once, [] { cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
   const int nitems = p.nbricks * p.NS;
   const int grid = nitems < nsm ? nitems : nsm;
-  conv_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(tmap, (const __nv_bfloat16*)wpack, bias, (uint4*)out, p);
+  conv_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(tmap, tmap_w, bias, (uint4*)out, p);
   return check_launch("conv_tc_fwd");
 }
 

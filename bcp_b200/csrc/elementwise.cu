@@ -11,8 +11,12 @@ namespace bcp {
 // ACDC_BCP_train.py:372-373, train_pancreas.py:155-156).  Computed literally with two multiplies and
 // one add (no select, no FMA) so -0.0 / inf / NaN behave like the reference's tensor expression.
 // ------------------------------------------------------------------------------------------
+// The box {x0,y0,z0,px,py,pz} lives in device memory so a captured CUDA graph can be replayed with a new box each step;
+// it is clipped to the volume like Python slicing (mask[w:w+px, ...]).
 __global__ void mask_mix_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
-                                long long total, int X, int Y, int Z, int bx0, int by0, int bz0, int bx1, int by1, int bz1) {
+                                long long total, int X, int Y, int Z, const int* __restrict__ box) {
+  const int bx0 = __ldg(box), by0 = __ldg(box + 1), bz0 = __ldg(box + 2);
+  const int bx1 = min(bx0 + __ldg(box + 3), X), by1 = min(by0 + __ldg(box + 4), Y), bz1 = min(bz0 + __ldg(box + 5), Z);
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     long long r = i;
@@ -26,8 +30,10 @@ __global__ void mask_mix_kernel(const float* __restrict__ a, const float* __rest
 }
 
 __global__ void label_mix_kernel(const unsigned char* __restrict__ a, const unsigned char* __restrict__ b,
-                                 unsigned char* __restrict__ out, long long total, int X, int Y, int Z, int bx0, int by0,
-                                 int bz0, int bx1, int by1, int bz1) {
+                                 unsigned char* __restrict__ out, long long total, int X, int Y, int Z,
+                                 const int* __restrict__ box) {
+  const int bx0 = __ldg(box), by0 = __ldg(box + 1), bz0 = __ldg(box + 2);
+  const int bx1 = min(bx0 + __ldg(box + 3), X), by1 = min(by0 + __ldg(box + 4), Y), bz1 = min(bz0 + __ldg(box + 5), Z);
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     long long r = i;
@@ -263,22 +269,19 @@ using namespace bcp;
 extern "C" {
 
 int bcp_mask_mix(const float* a, const float* b, float* out, int n, int c, int X, int Y, int Z,
-                 int bx, int by, int bz, int px, int py, int pz, cudaStream_t stream) {
-  BCP_REQUIRE(a && b && out, "mask_mix: null pointer");
+                 const int* box6_dev, cudaStream_t stream) {
+  BCP_REQUIRE(a && b && out && box6_dev, "mask_mix: null pointer");
   BCP_REQUIRE(n > 0 && c > 0 && X > 0 && Y > 0 && Z > 0, "mask_mix: bad shape");
   const long long total = (long long)n * c * X * Y * Z;
-  // the reference slices mask[w:w+px,...]: python slicing clips at the volume edge
-  const int bx1 = min(bx + px, X), by1 = min(by + py, Y), bz1 = min(bz + pz, Z);
-  mask_mix_kernel<<<grid_for(total, 256), 256, 0, stream>>>(a, b, out, total, X, Y, Z, bx, by, bz, bx1, by1, bz1);
+  mask_mix_kernel<<<grid_for(total, 256), 256, 0, stream>>>(a, b, out, total, X, Y, Z, box6_dev);
   return check_launch("mask_mix");
 }
 
 int bcp_label_mix(const unsigned char* a, const unsigned char* b, unsigned char* out, int n, int X, int Y, int Z,
-                  int bx, int by, int bz, int px, int py, int pz, cudaStream_t stream) {
-  BCP_REQUIRE(a && b && out && n > 0 && X > 0 && Y > 0 && Z > 0, "label_mix: bad args");
+                  const int* box6_dev, cudaStream_t stream) {
+  BCP_REQUIRE(a && b && out && box6_dev && n > 0 && X > 0 && Y > 0 && Z > 0, "label_mix: bad args");
   const long long total = (long long)n * X * Y * Z;
-  const int bx1 = min(bx + px, X), by1 = min(by + py, Y), bz1 = min(bz + pz, Z);
-  label_mix_kernel<<<grid_for(total, 256), 256, 0, stream>>>(a, b, out, total, X, Y, Z, bx, by, bz, bx1, by1, bz1);
+  label_mix_kernel<<<grid_for(total, 256), 256, 0, stream>>>(a, b, out, total, X, Y, Z, box6_dev);
   return check_launch("label_mix");
 }
 

@@ -20,6 +20,15 @@ struct BoxArgs {
   int X, Y, Z, x0, y0, z0, x1, y1, z1;
 };
 
+// box {x0,y0,z0,px,py,pz} in device memory (replayable CUDA graphs); clipped like Python slicing
+__device__ __forceinline__ BoxArgs load_box(const int* __restrict__ box, int X, int Y, int Z) {
+  BoxArgs b;
+  b.X = X; b.Y = Y; b.Z = Z;
+  b.x0 = __ldg(box); b.y0 = __ldg(box + 1); b.z0 = __ldg(box + 2);
+  b.x1 = min(b.x0 + __ldg(box + 3), X); b.y1 = min(b.y0 + __ldg(box + 4), Y); b.z1 = min(b.z0 + __ldg(box + 5), Z);
+  return b;
+}
+
 __device__ __forceinline__ int in_box(long long v, const BoxArgs& b) {
   const int z = (int)(v % b.Z);
   const long long r = v / b.Z;
@@ -34,8 +43,10 @@ __global__ void __launch_bounds__(LT) mix_loss_fwd_kernel(const float* __restric
                                                            const unsigned char* __restrict__ lab_img,
                                                            const unsigned char* __restrict__ lab_patch,
                                                            const unsigned char* __restrict__ mask,
-                                                           float* __restrict__ partial, long long V, BoxArgs box) {
+                                                           float* __restrict__ partial, long long V, int X, int Y, int Z,
+                                                           const int* __restrict__ box_dev) {
   constexpr int K = 2 * C * 3 + 4;
+  const BoxArgs box = load_box(box_dev, X, Y, Z);
   const int n = blockIdx.y, blocks = gridDim.x;
   const long long per = (V + blocks - 1) / blocks;
   const long long v0 = (long long)blockIdx.x * per, v1 = min(V, v0 + per);
@@ -184,7 +195,9 @@ __global__ void __launch_bounds__(LT) mix_loss_bwd_kernel(const float* __restric
                                                            const unsigned char* __restrict__ lab_patch,
                                                            const unsigned char* __restrict__ mask,
                                                            const float* __restrict__ ctx, const float* __restrict__ grad3,
-                                                           float* __restrict__ dlogits, int N, long long V, BoxArgs box) {
+                                                           float* __restrict__ dlogits, int N, long long V, int X, int Y, int Z,
+                                                           const int* __restrict__ box_dev) {
+  const BoxArgs box = load_box(box_dev, X, Y, Z);
   // outputs were {loss=(dice+ce)/2, dice, ce}: fold the three upstream gradients
   const float gd = grad3[1] + 0.5f * grad3[0], gc = grad3[2] + 0.5f * grad3[0];
   const long long total = (long long)N * V;
@@ -228,16 +241,6 @@ static inline int loss_blocks(long long V) {
   return (int)b;
 }
 
-static BoxArgs make_box(int X, int Y, int Z, const int* box, long long* vol) {
-  BoxArgs b;
-  b.X = X; b.Y = Y; b.Z = Z;
-  b.x0 = box[0]; b.y0 = box[1]; b.z0 = box[2];
-  b.x1 = min(box[0] + box[3], X); b.y1 = min(box[1] + box[4], Y); b.z1 = min(box[2] + box[5], Z);
-  long long dx = max(0, b.x1 - max(b.x0, 0)), dy = max(0, b.y1 - max(b.y0, 0)), dz = max(0, b.z1 - max(b.z0, 0));
-  *vol = dx * dy * dz;
-  return b;
-}
-
 }  // namespace bcp
 
 using namespace bcp;
@@ -256,12 +259,10 @@ int bcp_mix_loss_fwd(const float* logits, const unsigned char* lab_img, const un
   BCP_REQUIRE(form == 0 || form == 1, "mix_loss_fwd: form");
   BCP_REQUIRE(n > 0 && X > 0 && Y > 0 && Z > 0, "mix_loss_fwd: bad shape");
   const long long V = (long long)X * Y * Z;
-  long long vol;
-  const BoxArgs b = make_box(X, Y, Z, box6, &vol);
   const int blocks = loss_blocks(V);
   dim3 grid(blocks, n);
 #define LAUNCH(CC, FF)                                                                                         \
-  mix_loss_fwd_kernel<CC, FF><<<grid, LT, 0, stream>>>(logits, lab_img, lab_patch, mask, workspace, V, b);     \
+  mix_loss_fwd_kernel<CC, FF><<<grid, LT, 0, stream>>>(logits, lab_img, lab_patch, mask, workspace, V, X, Y, Z, box6);     \
   mix_loss_finalize_kernel<CC, FF><<<1, 32, 0, stream>>>(workspace, ctx, n, blocks, w_img, w_patch);
   if (c == 2 && form == 0) { LAUNCH(2, 0) }
   else if (c == 4 && form == 0) { LAUNCH(4, 0) }
@@ -277,15 +278,13 @@ int bcp_mix_loss_bwd(const float* logits, const unsigned char* lab_img, const un
   BCP_REQUIRE(logits && lab_img && lab_patch && ctx && grad3 && dlogits && box6, "mix_loss_bwd: null pointer");
   BCP_REQUIRE(c == 2 || c == 4, "mix_loss_bwd: %d classes unsupported", c);
   const long long V = (long long)X * Y * Z;
-  long long vol;
-  const BoxArgs b = make_box(X, Y, Z, box6, &vol);
   long long blocks = ((long long)n * V + LT - 1) / LT;
   const long long cap = (long long)sm_count() * 8;
   if (blocks > cap) blocks = cap;
   if (c == 2)
-    mix_loss_bwd_kernel<2><<<(int)blocks, LT, 0, stream>>>(logits, lab_img, lab_patch, mask, ctx, grad3, dlogits, n, V, b);
+    mix_loss_bwd_kernel<2><<<(int)blocks, LT, 0, stream>>>(logits, lab_img, lab_patch, mask, ctx, grad3, dlogits, n, V, X, Y, Z, box6);
   else
-    mix_loss_bwd_kernel<4><<<(int)blocks, LT, 0, stream>>>(logits, lab_img, lab_patch, mask, ctx, grad3, dlogits, n, V, b);
+    mix_loss_bwd_kernel<4><<<(int)blocks, LT, 0, stream>>>(logits, lab_img, lab_patch, mask, ctx, grad3, dlogits, n, V, X, Y, Z, box6);
   return check_launch("mix_loss_bwd");
 }
 

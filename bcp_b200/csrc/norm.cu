@@ -288,10 +288,15 @@ __global__ void __launch_bounds__(NT) bn_bwd_apply_kernel(const uint4* __restric
   }
 }
 
-static inline int pick_chunks(long long S) {
-  long long c = (S + 16383) / 16384;   // >= 16K voxels (256 KB of bf16x8) per block
+// Reduction grid = chunks x (C/8) x N blocks.  Aim at ~4 blocks per SM so mid-size layers are not latency-bound on a
+// handful of blocks, but keep at least 1024 voxels (16 KB) per block and at most 256 partials per (n, c/8) plane.
+static inline int pick_chunks(long long S, int planes) {
+  const long long target = 4LL * sm_count();
+  long long c = (target + planes - 1) / planes;
+  const long long cmax = (S + 1023) / 1024;
+  if (c > cmax) c = cmax;
+  if (c > 256) c = 256;
   if (c < 1) c = 1;
-  if (c > 64) c = 64;
   return (int)c;
 }
 
@@ -301,10 +306,10 @@ using namespace bcp;
 
 extern "C" {
 
-int bcp_norm_chunks(long long s) { return pick_chunks(s); }
+int bcp_norm_chunks(int n, int c, long long s) { return pick_chunks(s, n * ((c + 7) / 8)); }
 
 long long bcp_norm_workspace_floats(int n, int c, long long s) {
-  return (long long)n * ((c + 7) / 8) * pick_chunks(s) * 16;
+  return (long long)n * ((c + 7) / 8) * pick_chunks(s, n * ((c + 7) / 8)) * 16;
 }
 
 int bcp_norm_stats(const void* y, const float* gamma, const float* beta, float* running_mean, float* running_var,
@@ -312,7 +317,7 @@ int bcp_norm_stats(const void* y, const float* gamma, const float* beta, float* 
                    int n, int c, long long s, int spg, float eps, float momentum, cudaStream_t stream) {
   BCP_REQUIRE(y && stat && coef && workspace && counter, "norm_stats: null pointer");
   BCP_REQUIRE(n > 0 && c > 0 && s > 0 && spg > 0 && n % spg == 0, "norm_stats: bad shape n=%d spg=%d", n, spg);
-  const int chunks = pick_chunks(s), Cb = (c + 7) / 8;
+  const int Cb = (c + 7) / 8, chunks = pick_chunks(s, n * Cb);
   dim3 grid(chunks, Cb, n);
   bn_stats_kernel<<<grid, NT, 0, stream>>>((const uint4*)y, workspace, s, chunks, counter, gamma, beta, running_mean, running_var,
                                            num_batches_tracked, stat, coef, n, c, spg, eps, momentum);
@@ -346,7 +351,7 @@ int bcp_norm_bwd(const void* dact, const void* y, void* dy, const float* stat, c
                  int accumulate, cudaStream_t stream) {
   BCP_REQUIRE(dact && y && dy && stat && coef && sums && workspace && counter, "norm_bwd: null pointer");
   BCP_REQUIRE(n > 0 && c > 0 && s > 0 && spg > 0 && n % spg == 0, "norm_bwd: bad shape");
-  const int chunks = pick_chunks(s), Cb = (c + 7) / 8;
+  const int Cb = (c + 7) / 8, chunks = pick_chunks(s, n * Cb);
   if (stats_grad || dgamma || dbeta) {
     dim3 grid(chunks, Cb, n);
     bn_bwd_reduce_kernel<<<grid, NT, 0, stream>>>((const uint4*)dact, (const uint4*)y, stat, coef, chan_scale, elem_keep,

@@ -497,6 +497,18 @@ def maxpool3d_k3s2(a, c):
 # ----------------------------------------------------------------------------------------------
 # step primitives
 # ----------------------------------------------------------------------------------------------
+def box_tensor(box, device):
+    """{x0,y0,z0,px,py,pz} int32 on the device.  Accepts a 6-/4-tuple (2-D boxes get z0=0,pz=1) or an int32 device tensor
+    (used as is -- the captured-graph path keeps one static tensor and refreshes it before each replay)."""
+    if torch.is_tensor(box):
+        assert box.dtype == torch.int32 and box.numel() == 6 and box.is_cuda
+        return box
+    box = tuple(int(v) for v in box)
+    if len(box) == 4:
+        box = (box[0], box[1], 0, box[2], box[3], 1)
+    return torch.tensor(box, dtype=torch.int32).to(device, non_blocking=True)
+
+
 def _dims3(t, lead):
     sp = tuple(t.shape[lead:])
     return (sp[0], sp[1], 1) if len(sp) == 2 else sp
@@ -507,11 +519,11 @@ def mask_mix(a: torch.Tensor, b: torch.Tensor, box, out: torch.Tensor | None = N
     _require_cuda(a, "mask_mix")
     a, b = a.contiguous().float(), b.contiguous().float()
     X, Y, Z = _dims3(a, 2)
-    box = tuple(box) if len(box) == 6 else (box[0], box[1], 0, box[2], box[3], 1)
+    bt = box_tensor(box, a.device)
     if out is None:
         out = torch.empty_like(a)
     assert out.is_contiguous() and out.shape == a.shape and out.dtype == torch.float32
-    LIB.call("bcp_mask_mix", ptr(a), ptr(b), ptr(out), a.shape[0], a.shape[1], X, Y, Z, *[int(v) for v in box], stream())
+    LIB.call("bcp_mask_mix", ptr(a), ptr(b), ptr(out), a.shape[0], a.shape[1], X, Y, Z, ptr(bt), stream())
     return out
 
 
@@ -520,9 +532,9 @@ def label_mix(a: torch.Tensor, b: torch.Tensor, box) -> torch.Tensor:
     _require_cuda(a, "label_mix")
     a, b = to_u8_labels(a).contiguous(), to_u8_labels(b).contiguous()
     X, Y, Z = _dims3(a, 1)
-    box = tuple(box) if len(box) == 6 else (box[0], box[1], 0, box[2], box[3], 1)
+    bt = box_tensor(box, a.device)
     out = torch.empty_like(a)
-    LIB.call("bcp_label_mix", ptr(a), ptr(b), ptr(out), a.shape[0], X, Y, Z, *[int(v) for v in box], stream())
+    LIB.call("bcp_label_mix", ptr(a), ptr(b), ptr(out), a.shape[0], X, Y, Z, ptr(bt), stream())
     return out
 
 
@@ -564,7 +576,7 @@ class MixLoss(Function):
         X, Y, Z = _dims3(logits, 2)
         if box is None:
             box = (0, 0, 0, 0, 0, 0)
-        box6 = tuple(box) if len(box) == 6 else (box[0], box[1], 0, box[2], box[3], 1)
+        box6 = box_tensor(box, logits.device)
         if mask_u8 is not None:
             mask_u8 = mask_u8.contiguous()
             assert mask_u8.dtype == torch.uint8 and mask_u8.numel() == n * X * Y * Z
@@ -574,20 +586,20 @@ class MixLoss(Function):
         dev = logits.device
         cbuf = _f32(LIB.query("bcp_mix_loss_ctx_floats", n, c), dev)
         ws = _f32(LIB.query("bcp_mix_loss_workspace_floats", n, c, X * Y * Z), dev)
-        LIB.call("bcp_mix_loss_fwd", ptr(logits), ptr(li), ptr(lp), ptr(mask_u8), ptr(cbuf), ptr(ws), n, c, X, Y, Z, i6(box6),
+        LIB.call("bcp_mix_loss_fwd", ptr(logits), ptr(li), ptr(lp), ptr(mask_u8), ptr(cbuf), ptr(ws), n, c, X, Y, Z, ptr(box6),
                  int(form), float(w_img), float(w_patch), stream())
-        ctx.save_for_backward(logits, li, lp, cbuf, mask_u8)
-        ctx.meta = (n, c, X, Y, Z, box6)
+        ctx.save_for_backward(logits, li, lp, cbuf, mask_u8, box6)
+        ctx.meta = (n, c, X, Y, Z)
         return cbuf[:3].clone()
 
     @staticmethod
     def backward(ctx, g3):
-        logits, li, lp, cbuf, mask_u8 = ctx.saved_tensors
-        n, c, X, Y, Z, box6 = ctx.meta
+        logits, li, lp, cbuf, mask_u8, box6 = ctx.saved_tensors
+        n, c, X, Y, Z = ctx.meta
         g3 = g3.contiguous().float()
         dlog = torch.empty_like(logits)
         LIB.call("bcp_mix_loss_bwd", ptr(logits), ptr(li), ptr(lp), ptr(mask_u8), ptr(cbuf), ptr(g3), ptr(dlog), n, c, X, Y, Z,
-                 i6(box6), stream())
+                 ptr(box6), stream())
         return dlog, None, None, None, None, None, None, None
 
 

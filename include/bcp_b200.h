@@ -33,13 +33,15 @@ int bcp_device_sm_count(void);
 
 /* ---- box mask-mix: out = a*M + b*(1-M), M = 0 inside box [b, b+p) else 1.  Bit-exact vs the tensor
  * expression at LA_BCP_train.py:155,248-249; ACDC_BCP_train.py:244,372-373; pancreas/train_pancreas.py:86,155-156.
- * a, b, out: fp32 [n][c][X][Y][Z].  The box is clipped to the volume like Python slicing. */
+ * a, b, out: fp32 [n][c][X][Y][Z].  box6_dev = {x0,y0,z0,px,py,pz} int32 in DEVICE memory (so a captured CUDA graph can
+ * be replayed with a fresh box); it is clipped to the volume like Python slicing.  Same convention for label_mix and
+ * mix_loss (box6). */
 int bcp_mask_mix(const float* a, const float* b, float* out, int n, int c, int X, int Y, int Z,
-                 int bx, int by, int bz, int px, int py, int pz, cudaStream_t stream);
+                 const int* box6_dev, cudaStream_t stream);
 
 /* uint8 label maps mixed with the same box (label_batch at LA_BCP_train.py:156, ACDC_BCP_train.py:245). */
 int bcp_label_mix(const unsigned char* a, const unsigned char* b, unsigned char* out, int n, int X, int Y, int Z,
-                  int bx, int by, int bz, int px, int py, int pz, cudaStream_t stream);
+                  const int* box6_dev, cudaStream_t stream);
 
 /* ---- pseudo labels from planar fp32 logits [n][c][v] -> uint8 [n][v].
  * mode 0: (softmax(x,1) >= thr)[:,1]     LA_BCP_train.py:57-60, pancreas/pancreas_utils.py:275-278   (c == 2)
@@ -106,7 +108,7 @@ int bcp_cb8_to_planar(const void* in, float* out, int n, int c, long long s, cud
  * InstanceNorm: spg = 1).  stat/coef: fp32 [n/spg][c][2] = {mean, invstd} / {scale, shift}.
  * `counter`: one device int, zero before the first call; the last block of the reduction grid finalises in fixed order
  * and resets it (deterministic; lets one launch replace partial + finalize kernels). */
-int bcp_norm_chunks(long long s);
+int bcp_norm_chunks(int n, int c, long long s);
 long long bcp_norm_workspace_floats(int n, int c, long long s);
 int bcp_norm_stats(const void* y, const float* gamma, const float* beta, float* running_mean, float* running_var,
                    long long* num_batches_tracked, float* stat, float* coef, float* workspace, int* counter,

@@ -23,10 +23,10 @@ def test_library_exports_every_declared_symbol():
 def test_argument_errors_do_not_abort():
     from bcp_b200._native import LIB
     lib = LIB.load()
-    rc = lib.bcp_mask_mix(None, None, None, 1, 1, 4, 4, 4, 0, 0, 0, 1, 1, 1, None)
+    rc = lib.bcp_mask_mix(None, None, None, 1, 1, 4, 4, 4, None, None)
     assert rc == -1 and b"null" in lib.bcp_last_error()
     assert lib.bcp_mix_loss_ctx_floats(2, 2) == 6 + 2 * 2 * 2 * 3
-    assert lib.bcp_norm_chunks(10) == 1
+    assert lib.bcp_norm_chunks(2, 16, 10) == 1
 
 
 def test_product_fails_loudly_without_gpu():
