@@ -273,6 +273,7 @@ __global__ void __launch_bounds__(128) conv_first_fwd_kernel(const float* __rest
   }
 }
 
+constexpr int FIRST_WG_CHUNK = 16384;
 // dW[co][t]: grid (chunks, Cob, kx); thread acc[ky*kz <= 9][8]; partial[chunk][cob][tx][9][8]
 __global__ void __launch_bounds__(128) conv_first_wgrad_partial_kernel(const float* __restrict__ in, const uint4* __restrict__ og,
                                                                         float* __restrict__ partial, Geom g, int Cout) {
@@ -280,17 +281,20 @@ __global__ void __launch_bounds__(128) conv_first_wgrad_partial_kernel(const flo
   const int cob = blockIdx.y, tx = blockIdx.z;
   const long long So = (long long)g.Xo * g.Yo * g.Zo;
   const long long total = (long long)g.N * So;
-  const long long o0 = (long long)blockIdx.x * 4096, o1 = min(total, o0 + 4096);
+  const long long o0 = (long long)blockIdx.x * FIRST_WG_CHUNK, o1 = min(total, o0 + FIRST_WG_CHUNK);
   float acc[9][8];
 #pragma unroll
   for (int i = 0; i < 9; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  const int YZ = g.Yo * g.Zo;
   for (long long o = o0 + threadIdx.x; o < o1; o += 128) {
-    int n, x, y, z;
-    decompose(o, g, n, x, y, z);
+    // 32-bit index math (a sample has < 2^31 voxels); 64-bit only for the sample split
+    const int n = (int)(o / So);
+    const int sp = (int)(o - (long long)n * So);
+    const int x = sp / YZ, r2 = sp - x * YZ, y = r2 / g.Zo, z = r2 - y * g.Zo;
     float d[8];
-    unpack8(__ldg(og + ((long long)n * Cob + cob) * So + (o - (long long)n * So)), d);
+    unpack8(__ldg(og + ((long long)n * Cob + cob) * So + sp), d);
     const int ix = x + tx - g.px;
     if (ix < 0 || ix >= g.Xi) continue;
 #pragma unroll
@@ -578,7 +582,7 @@ int bcp_conv_first_fwd(const float* in, const float* w, const float* bias, void*
 
 long long bcp_conv_first_wgrad_workspace_floats(int n, int cout, const int* dims, const int* kernel) {
   const long long total = (long long)n * dims[0] * dims[1] * dims[2];
-  return ((total + 4095) / 4096) * ((cout + 7) / 8) * kernel[0] * 72;
+  return ((total + FIRST_WG_CHUNK - 1) / FIRST_WG_CHUNK) * ((cout + 7) / 8) * kernel[0] * 72;
 }
 
 int bcp_conv_first_wgrad(const float* in, const void* outgrad, float* dw, float* workspace, int n, int cout,
@@ -591,7 +595,7 @@ int bcp_conv_first_wgrad(const float* in, const void* outgrad, float* dw, float*
   BCP_REQUIRE(g.ky <= 3 && g.kz <= 3, "conv_first_wgrad: kernel too large");
   const int Cob = (cout + 7) / 8;
   const long long total = (long long)n * g.Xo * g.Yo * g.Zo;
-  const int chunks = (int)((total + 4095) / 4096);
+  const int chunks = (int)((total + FIRST_WG_CHUNK - 1) / FIRST_WG_CHUNK);
   dim3 grid(chunks, Cob, g.kx);
   conv_first_wgrad_partial_kernel<<<grid, 128, 0, stream>>>(in, (const uint4*)outgrad, workspace, g, cout);
   const int T = g.kx * g.ky * g.kz;

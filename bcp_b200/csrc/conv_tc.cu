@@ -41,6 +41,7 @@ struct TcParams {
   int tmem_cols;       // power of two >= AS*MT*Cout
   unsigned slotA_bytes, stageB_bytes;
   unsigned offA, offB, offBar;   // shared-memory carve-up (bytes from the 128B-aligned base)
+  int mergedA, mergedB;          // tensor maps use the 8-byte-element "merged inner dimension" form (tma_load_cb8)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -77,6 +78,18 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// CB8 box load.  `merged` maps describe the tensor as 8-byte elements with the (z, 8-channel) pair folded into the
+// innermost dimension, so the TMA unit moves whole z-runs (HZ*16 B) instead of one 16-byte element row at a time.
+__device__ __forceinline__ void tma_load_cb8(uint32_t dst, const CUtensorMap* map, uint32_t bar, int merged, int z, int y, int x, int plane) {
+  if (merged) tma_load_4d(dst, map, bar, 2 * z, y, x, plane);
+  else tma_load_5d(dst, map, bar, 0, z, y, x, plane);
 }
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -125,9 +138,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 
 constexpr int TC_THREADS = 192;
 
+template <bool PROF>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_w,
-               const float* __restrict__ bias, uint4* __restrict__ out, const TcParams p) {
+               const float* __restrict__ bias, uint4* __restrict__ out, const TcParams p, unsigned long long* __restrict__ prof) {
+  // PROF: per-CTA cycle counters for tools/debug_conv_tc.py --prof (never instantiated on the product path)
+  long long t_start = 0, w0 = 0, w1 = 0, w2 = 0;
+  if (PROF) t_start = clock64();
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
   const uint32_t sbase = smem_u32(smem);
@@ -175,21 +192,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         const int x0 = bx * p.BX - (p.kx >> 1), y0 = by * p.BY - 1, z0 = bz * p.BZ - 1;
         for (int c = 0; c < p.nchunks; ++c) {
           const uint32_t sa = ia % p.SA, pa = (ia / p.SA) & 1;
-          mbar_wait(empty_a + 8 * sa, pa ^ 1);
+          { long long t0 = PROF ? clock64() : 0; mbar_wait(empty_a + 8 * sa, pa ^ 1); if (PROF) w0 += clock64() - t0; }
           if (elect_one()) {
             mbar_expect_tx(full_a + 8 * sa, a_bytes);
-            tma_load_5d(a_base + sa * p.slotA_bytes, &tmap, full_a + 8 * sa, 0, z0, y0, x0, n * Cib + 2 * c);
+            tma_load_cb8(a_base + sa * p.slotA_bytes, &tmap, full_a + 8 * sa, p.mergedA, z0, y0, x0, n * Cib + 2 * c);
           }
           __syncwarp();
           ++ia;
           for (int t = 0; t < p.T; t += p.TG) {
             const uint32_t sb = ib % p.SB, pb = (ib / p.SB) & 1;
-            mbar_wait(empty_b + 8 * sb, pb ^ 1);
+            { long long t0 = PROF ? clock64() : 0; mbar_wait(empty_b + 8 * sb, pb ^ 1); if (PROF) w1 += clock64() - t0; }
             if (elect_one()) {
               // ONE 4-D TMA box {8, Ns channels, 2 planes, TG taps} of the operand pack [T][Cin/8][Cout][8] per stage
               // (per-tap bulk copies of 1-2 KB each made the TMA unit's per-operation cost the bottleneck on deep layers)
               mbar_expect_tx(full_b + 8 * sb, p.stageB_bytes);
-              tma_load_4d(b_base + sb * p.stageB_bytes, &tmap_w, full_b + 8 * sb, 0, n0, 2 * c, t);
+              if (p.mergedB) tma_load_3d(b_base + sb * p.stageB_bytes, &tmap_w, full_b + 8 * sb, 2 * n0, 2 * c, t);
+              else tma_load_4d(b_base + sb * p.stageB_bytes, &tmap_w, full_b + 8 * sb, 0, n0, 2 * c, t);
             }
             __syncwarp();
             ++ib;
@@ -197,6 +215,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         }
       }
     }
+    if (PROF && lane == 0) { prof[blockIdx.x * 16 + 1] = w0; prof[blockIdx.x * 16 + 2] = w1; }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (warp-uniform; one elected lane issues)
     {
@@ -209,18 +228,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       uint32_t ia = 0, ib = 0, it = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
         const uint32_t as = it % p.AS, ap = (it / p.AS) & 1;
-        mbar_wait(tmem_empty + 8 * as, ap ^ 1);
+        { long long t0 = PROF ? clock64() : 0; mbar_wait(tmem_empty + 8 * as, ap ^ 1); if (PROF) w2 += clock64() - t0; }
         tc_fence_after();
         const uint32_t d0 = tmem_base + as * (uint32_t)(p.MT * p.Ns);
         for (int c = 0; c < p.nchunks; ++c) {
           const uint32_t sa = ia % p.SA, pa = (ia / p.SA) & 1;
-          mbar_wait(full_a + 8 * sa, pa);
+          { long long t0 = PROF ? clock64() : 0; mbar_wait(full_a + 8 * sa, pa); if (PROF) w0 += clock64() - t0; }
           tc_fence_after();
           const uint64_t a_slot = adesc0 + (uint64_t)((a_base + sa * p.slotA_bytes) >> 4);
           int tx = 0, ty = 0, tz = 0;
           for (int t = 0; t < p.T; t += p.TG) {
             const uint32_t sb = ib % p.SB, pb = (ib / p.SB) & 1;
-            mbar_wait(full_b + 8 * sb, pb);
+            { long long t0 = PROF ? clock64() : 0; mbar_wait(full_b + 8 * sb, pb); if (PROF) w1 += clock64() - t0; }
             tc_fence_after();
             uint64_t bdesc = bdesc0 + (uint64_t)((b_base + sb * p.stageB_bytes) >> 4);
             const bool leader = elect_one();
@@ -249,6 +268,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         if (elect_one()) umma_commit(tmem_full + 8 * as);
         __syncwarp();
       }
+      if (PROF && lane == 0) { prof[blockIdx.x * 16 + 3] = w0; prof[blockIdx.x * 16 + 4] = w1; prof[blockIdx.x * 16 + 5] = w2; prof[blockIdx.x * 16 + 8] = clock64() - t_start; prof[blockIdx.x * 16 + 9] = it; }
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps (TMEM lane quarter = warp % 4)
@@ -263,7 +283,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       const int by = r % p.nby;
       const int bx = r / p.nby;
       const uint32_t as = it % p.AS, ap = (it / p.AS) & 1;
-      mbar_wait(tmem_full + 8 * as, ap);
+      long long t_e0 = 0;
+      { long long t0 = PROF ? clock64() : 0; mbar_wait(tmem_full + 8 * as, ap); if (PROF) { t_e0 = clock64(); w0 += t_e0 - t0; } }
       tc_fence_after();
       const uint32_t d0 = tmem_base + as * (uint32_t)(p.MT * p.Ns) + ((uint32_t)(q * 32) << 16);
       for (int mt = 0; mt < p.MT; ++mt) {
@@ -291,11 +312,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty + 8 * as);
+      if (PROF) w1 += clock64() - t_e0;
     }
+    if (PROF && warp == 2 && lane == 0) { prof[blockIdx.x * 16 + 6] = w0; prof[blockIdx.x * 16 + 7] = w1; }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (PROF && threadIdx.x == 0) prof[blockIdx.x * 16 + 0] = clock64() - t_start;
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
@@ -321,6 +345,7 @@ struct S2Params {
   int TPc, npieces, Npiece;        // taps per piece, pieces, MMA N
   int SA, SB, AS, tmem_cols;
   unsigned slotA_bytes, stageB_bytes, offA, offB, offBar;
+  int mergedA;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -380,7 +405,7 @@ conv_tc_s2_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16*
               tma_load_5d(a_base + sa * p.slotA_bytes, &tmap, full_a + 8 * sa, 0, 2 * bz * p.BZ + (t & 1), 2 * by * p.BY + ((t >> 1) & 1),
                           2 * bx * p.BX + (t >> 2), n * Cib + 2 * c);
             else
-              tma_load_5d(a_base + sa * p.slotA_bytes, &tmap, full_a + 8 * sa, 0, bz * p.BZ, by * p.BY, bx * p.BX, n * Cib + 2 * c);
+              tma_load_cb8(a_base + sa * p.slotA_bytes, &tmap, full_a + 8 * sa, p.mergedA, bz * p.BZ, by * p.BY, bx * p.BX, n * Cib + 2 * c);
             mbar_expect_tx(full_b + 8 * sb, p.stageB_bytes);
             if (p.mode == 1) {
               bulk_load(b_base + sb * p.stageB_bytes, wpack + ((size_t)t * Cib + 2 * c) * (size_t)p.Cout * 8, p.stageB_bytes, full_b + 8 * sb);
@@ -504,6 +529,7 @@ struct WgParams {
   int s2;                         // 1: stride-2 family (B bricks are per-tap strided gathers of the full-res tensor)
   int MM, m64map;                 // MMA M (128 or 64) and the TMEM row->lane map assumed for M = 64
   unsigned a_tx_bytes, dy_tx_bytes, a_alloc_bytes, dy_alloc_bytes, slot_bytes, offBar, tap_bytes;
+  int mergedA, mergedD;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -572,9 +598,9 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           }
         } else {
           mbar_expect_tx(full + 8 * s, p.a_tx_bytes + p.dy_tx_bytes);
-          tma_load_5d(slot, &map_a, full + 8 * s, 0, -1, by * p.BY - 1, bx * p.BX - (p.kx >> 1), n * Cib);
+          tma_load_cb8(slot, &map_a, full + 8 * s, p.mergedA, -1, by * p.BY - 1, bx * p.BX - (p.kx >> 1), n * Cib);
         }
-        tma_load_5d(slot + p.a_alloc_bytes, &map_dy, full + 8 * s, 0, 0, by * p.BY, bx * p.BX, n * Cob + mh * 16);
+        tma_load_cb8(slot + p.a_alloc_bytes, &map_dy, full + 8 * s, p.mergedD, 0, by * p.BY, bx * p.BX, n * Cob + mh * 16);
         }
         __syncwarp();
       }
@@ -701,6 +727,31 @@ static EncodeTiledFn get_encode() {
       fn = (EncodeTiledFn)f;
   });
   return fn;
+}
+
+// Tensor map over a CB8 tensor [planes][X][Y][Z][8] bf16 for a box of (bp planes, bx, by, bz voxels).  When the z-run
+// fits a 256-element box the map is built over 8-byte elements with (z, channel-octet) folded into the innermost
+// dimension: the box's innermost extent becomes bz*16 bytes instead of 16, which is what the TMA unit's throughput
+// depends on (a 16-byte inner box caps a SM's TMA at roughly 8-10 B/clk -- measured on the c64..c256 layers).
+// Out-of-bounds z (the conv padding) still zero-fills because z*2 stays the coordinate of its own dimension.
+static CUresult encode_cb8(EncodeTiledFn enc, CUtensorMap* map, const void* base, long long Z, long long Y, long long X,
+                           long long planes, int bz, int by, int bx, int bp, int* merged) {
+  const int want = (bz <= 128 && !getenv("BCP_TMA_NO_MERGE")) ? 1 : 0;
+  *merged = want;
+  if (want) {
+    const cuuint64_t gdim[4] = {(cuuint64_t)(2 * Z), (cuuint64_t)Y, (cuuint64_t)X, (cuuint64_t)planes};
+    const cuuint64_t gstr[3] = {(cuuint64_t)Z * 16, (cuuint64_t)Z * Y * 16, (cuuint64_t)Z * Y * X * 16};
+    const cuuint32_t box[4] = {(cuuint32_t)(2 * bz), (cuuint32_t)by, (cuuint32_t)bx, (cuuint32_t)bp};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  const cuuint64_t gdim[5] = {8, (cuuint64_t)Z, (cuuint64_t)Y, (cuuint64_t)X, (cuuint64_t)planes};
+  const cuuint64_t gstr[4] = {16, (cuuint64_t)Z * 16, (cuuint64_t)Z * Y * 16, (cuuint64_t)Z * Y * X * 16};
+  const cuuint32_t box[5] = {8, (cuuint32_t)bz, (cuuint32_t)by, (cuuint32_t)bx, (cuuint32_t)bp};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
 constexpr unsigned SMEM_BUDGET = 220 * 1024;   // of the 227 KB a CTA may opt into
@@ -964,6 +1015,10 @@ int bcp_conv_tc_plan(int n, int cin, int cout, const int* dims, const int* kerne
   return BCP_OK;
 }
 
+static unsigned long long* g_tc_prof = nullptr;
+// debug only (tools/debug_conv_tc.py --prof): 16 counters per CTA, see conv_tc_kernel<true>
+int bcp_conv_tc_debug_profile(void* buffer) { g_tc_prof = (unsigned long long*)buffer; return BCP_OK; }
+
 int bcp_conv_tc_fwd(const void* in, const void* wpack, const float* bias, void* out, int n, int cin, int cout,
                     const int* dims, const int* kernel, cudaStream_t stream) {
   BCP_REQUIRE(in && wpack && out && dims && kernel, "conv_tc_fwd: null pointer");
@@ -976,32 +1031,41 @@ int bcp_conv_tc_fwd(const void* in, const void* wpack, const float* bias, void* 
   if (!plan_cached(p, nsm)) { set_last_error("conv_tc_fwd: no brick shape fits shared memory / TMEM"); return BCP_ERR_UNSUPPORTED; }
 
   CUtensorMap tmap;
-  const cuuint64_t gdim[5] = {8, (cuuint64_t)p.Z, (cuuint64_t)p.Y, (cuuint64_t)p.X, (cuuint64_t)n * (cin / 8)};
-  const cuuint64_t gstr[4] = {16, (cuuint64_t)p.Z * 16, (cuuint64_t)p.Z * p.Y * 16, (cuuint64_t)p.Z * p.Y * p.X * 16};
-  const cuuint32_t box[5] = {8, (cuuint32_t)p.HZ, (cuuint32_t)p.HY, (cuuint32_t)p.HX, 2};
-  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  const CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(in), gdim, gstr, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUresult cr = encode_cb8(enc, &tmap, in, p.Z, p.Y, p.X, (long long)n * (cin / 8), p.HZ, p.HY, p.HX, 2, &p.mergedA);
   if (cr != CUDA_SUCCESS) { set_last_error("conv_tc_fwd: cuTensorMapEncodeTiled failed (%d)", (int)cr); return BCP_ERR_CUDA; }
 
   CUtensorMap tmap_w;
   {
-    const cuuint64_t wdim[4] = {8, (cuuint64_t)cout, (cuuint64_t)(cin / 8), (cuuint64_t)p.T};
-    const cuuint64_t wstr[3] = {16, (cuuint64_t)cout * 16, (cuuint64_t)cout * 16 * (cin / 8)};
-    const cuuint32_t wbox[4] = {8, (cuuint32_t)p.Ns, 2, (cuuint32_t)p.TG};
-    const cuuint32_t wes[4] = {1, 1, 1, 1};
-    const CUresult cw = enc(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(wpack), wdim, wstr, wbox, wes,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    // pack [T][Cin/8][Cout][8]: the Ns-channel run of a (tap, plane) is contiguous, so fold (cout, 8) into 8-byte elements
+    p.mergedB = (p.Ns <= 128 && !getenv("BCP_TMA_NO_MERGE")) ? 1 : 0;
+    CUresult cw;
+    if (p.mergedB) {
+      const cuuint64_t wdim[3] = {(cuuint64_t)cout * 2, (cuuint64_t)(cin / 8), (cuuint64_t)p.T};
+      const cuuint64_t wstr[2] = {(cuuint64_t)cout * 16, (cuuint64_t)cout * 16 * (cin / 8)};
+      const cuuint32_t wbox[3] = {(cuuint32_t)p.Ns * 2, 2, (cuuint32_t)p.TG};
+      const cuuint32_t wes[3] = {1, 1, 1};
+      cw = enc(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(wpack), wdim, wstr, wbox, wes, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      const cuuint64_t wdim[4] = {8, (cuuint64_t)cout, (cuuint64_t)(cin / 8), (cuuint64_t)p.T};
+      const cuuint64_t wstr[3] = {16, (cuuint64_t)cout * 16, (cuuint64_t)cout * 16 * (cin / 8)};
+      const cuuint32_t wbox[4] = {8, (cuuint32_t)p.Ns, 2, (cuuint32_t)p.TG};
+      const cuuint32_t wes[4] = {1, 1, 1, 1};
+      cw = enc(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(wpack), wdim, wstr, wbox, wes, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     if (cw != CUDA_SUCCESS) { set_last_error("conv_tc_fwd: weight tensor map failed (%d)", (int)cw); return BCP_ERR_CUDA; }
   }
   const size_t smem = (size_t)p.offBar + 8 * (2 * p.SA + 2 * p.SB + 2 * p.AS) + 16 + 128;
   static std::once_flag attr_once;
-  std::call_once(attr_once, [] { cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  std::call_once(attr_once, [] {
+    cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
   const int nitems = p.nbricks * p.NS;
   const int grid = nitems < nsm ? nitems : nsm;
-  conv_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(tmap, tmap_w, bias, (uint4*)out, p);
+  if (g_tc_prof) conv_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(tmap, tmap_w, bias, (uint4*)out, p, g_tc_prof);
+  else conv_tc_kernel<false><<<grid, TC_THREADS, smem, stream>>>(tmap, tmap_w, bias, (uint4*)out, p, nullptr);
   return check_launch("conv_tc_fwd");
 }
 
@@ -1034,22 +1098,12 @@ int bcp_conv_tc_wgrad(const void* a, const void* dy, float* dw, float* workspace
   WgParams p;
   if (wg_setup(p, n, cin, cout, dims, kernel) != 0) { set_last_error("conv_tc_wgrad: no brick shape fits"); return BCP_ERR_UNSUPPORTED; }
   CUtensorMap map_a, map_dy;
-  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  const cuuint64_t gstr[4] = {16, (cuuint64_t)p.Z * 16, (cuuint64_t)p.Z * p.Y * 16, (cuuint64_t)p.Z * p.Y * p.X * 16};
   {
-    const cuuint64_t gdim[5] = {8, (cuuint64_t)p.Z, (cuuint64_t)p.Y, (cuuint64_t)p.X, (cuuint64_t)n * (cin / 8)};
-    const cuuint32_t box[5] = {8, (cuuint32_t)p.HZ, (cuuint32_t)p.HY, (cuuint32_t)p.HX, (cuuint32_t)(cin / 8)};
-    const CUresult cr = enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(a), gdim, gstr, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult cr = encode_cb8(enc, &map_a, a, p.Z, p.Y, p.X, (long long)n * (cin / 8), p.HZ, p.HY, p.HX, cin / 8, &p.mergedA);
     if (cr != CUDA_SUCCESS) { set_last_error("conv_tc_wgrad: tensor map (a) failed (%d)", (int)cr); return BCP_ERR_CUDA; }
   }
   {
-    const cuuint64_t gdim[5] = {8, (cuuint64_t)p.Z, (cuuint64_t)p.Y, (cuuint64_t)p.X, (cuuint64_t)n * (cout / 8)};
-    const cuuint32_t box[5] = {8, (cuuint32_t)p.ZP, (cuuint32_t)p.BY, (cuuint32_t)p.BX, (cuuint32_t)p.PL};
-    const CUresult cr = enc(&map_dy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(dy), gdim, gstr, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult cr = encode_cb8(enc, &map_dy, dy, p.Z, p.Y, p.X, (long long)n * (cout / 8), p.ZP, p.BY, p.BX, p.PL, &p.mergedD);
     if (cr != CUDA_SUCCESS) { set_last_error("conv_tc_wgrad: tensor map (dy) failed (%d)", (int)cr); return BCP_ERR_CUDA; }
   }
   const size_t smem = (size_t)p.offBar + 8 * (2 * p.S + 1) + 16 + 128 + 128;
@@ -1087,13 +1141,19 @@ int bcp_conv_tc_s2_fwd(const void* in, const void* wpack, const float* bias, voi
   const int f = (mode == 1) ? 2 : 1;      // input resolution factor
   const cuuint64_t X = (cuuint64_t)p.Xh * f, Y = (cuuint64_t)p.Yh * f, Z = (cuuint64_t)p.Zh * f;
   CUtensorMap tmap;
-  const cuuint64_t gdim[5] = {8, Z, Y, X, (cuuint64_t)n * (cin / 8)};
-  const cuuint64_t gstr[4] = {16, Z * 16, Z * Y * 16, Z * Y * X * 16};
-  const cuuint32_t box[5] = {8, (cuuint32_t)(p.BZ * f), (cuuint32_t)(p.BY * f), (cuuint32_t)(p.BX * f), 2};
-  const cuuint32_t estr[5] = {1, (cuuint32_t)f, (cuuint32_t)f, (cuuint32_t)f, 1};
-  const CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(in), gdim, gstr, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult cr;
+  if (mode == 2) {
+    cr = encode_cb8(enc, &tmap, in, (long long)Z, (long long)Y, (long long)X, (long long)n * (cin / 8), p.BZ, p.BY, p.BX, 2, &p.mergedA);
+  } else {
+    p.mergedA = 0;      // stride-2 gather: elementStrides select every other 16-byte voxel, not expressible on a merged dimension
+    const cuuint64_t gdim[5] = {8, Z, Y, X, (cuuint64_t)n * (cin / 8)};
+    const cuuint64_t gstr[4] = {16, Z * 16, Z * Y * 16, Z * Y * X * 16};
+    const cuuint32_t box[5] = {8, (cuuint32_t)(p.BZ * f), (cuuint32_t)(p.BY * f), (cuuint32_t)(p.BX * f), 2};
+    const cuuint32_t estr[5] = {1, (cuuint32_t)f, (cuuint32_t)f, (cuuint32_t)f, 1};
+    cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(in), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   if (cr != CUDA_SUCCESS) { set_last_error("conv_tc_s2_fwd: cuTensorMapEncodeTiled failed (%d)", (int)cr); return BCP_ERR_CUDA; }
   const size_t smem = (size_t)p.offBar + 8 * (2 * p.SA + 2 * p.SB + 2 * p.AS) + 16 + 128;
   static std::once_flag attr_once;
@@ -1196,13 +1256,7 @@ int bcp_conv_tc_s2_wgrad(const void* full, const void* half, float* dw, float* w
     if (cr != CUDA_SUCCESS) { set_last_error("conv_tc_s2_wgrad: tensor map (full) failed (%d)", (int)cr); return BCP_ERR_CUDA; }
   }
   {
-    const cuuint64_t gdim[5] = {8, (cuuint64_t)p.Z, (cuuint64_t)p.Y, (cuuint64_t)p.X, (cuuint64_t)n * (c_half / 8)};
-    const cuuint64_t gstr[4] = {16, (cuuint64_t)p.Z * 16, (cuuint64_t)p.Z * p.Y * 16, (cuuint64_t)p.Z * p.Y * p.X * 16};
-    const cuuint32_t box[5] = {8, (cuuint32_t)p.ZP, (cuuint32_t)p.BY, (cuuint32_t)p.BX, (cuuint32_t)p.PL};
-    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    const CUresult cr = enc(&map_dy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(half), gdim, gstr, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult cr = encode_cb8(enc, &map_dy, half, p.Z, p.Y, p.X, (long long)n * (c_half / 8), p.ZP, p.BY, p.BX, p.PL, &p.mergedD);
     if (cr != CUDA_SUCCESS) { set_last_error("conv_tc_s2_wgrad: tensor map (half) failed (%d)", (int)cr); return BCP_ERR_CUDA; }
   }
   const size_t smem = (size_t)p.offBar + 8 * (2 * p.S + 1) + 16 + 128 + 128;

@@ -158,6 +158,9 @@ int bcp_conv_tc_supported(int cin, int cout, const int* dims, const int* kernel)
 int bcp_conv_tc_plan(int n, int cin, int cout, const int* dims, const int* kernel, int* plan10);
 int bcp_conv_tc_fwd(const void* in, const void* wpack, const float* bias, void* out, int n, int cin, int cout,
                     const int* dims, const int* kernel, cudaStream_t stream);
+/* debug only: when `buffer` (device, 16 x uint64 per CTA, >= 148 CTAs) is non-null, bcp_conv_tc_fwd launches the
+ * instrumented kernel variant that records per-role wait cycles; pass NULL to return to the product kernel. */
+int bcp_conv_tc_debug_profile(void* buffer);
 
 /* tcgen05 weight gradient for the same family: dw[cout][cin][taps] fp32 (PyTorch layout), deterministic. */
 int bcp_conv_tc_wgrad_supported(int cin, int cout, const int* dims, const int* kernel);

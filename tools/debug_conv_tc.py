@@ -59,6 +59,39 @@ def run(n, cin, cout, dims, kernel, mode="rand", verbose=True):
     return e_t
 
 
+def run_prof(n, c, dims, kernel=(3, 3, 3)):
+    """Per-role wait cycles of the instrumented forward kernel (bcp_conv_tc_debug_profile)."""
+    torch.manual_seed(0)
+    x = torch.randn(n, c, *dims, device=dev).to(torch.bfloat16).float()
+    w = (torch.randn(c, c, *kernel, device=dev) / np.sqrt(c * 27)).to(torch.bfloat16).float()
+    b = torch.zeros(c, device=dev)
+    pack = _packs(ops, dev, w, (0, 1))
+    a = cb8_from_planar(x)
+    rc, pl = plan(n, c, c, dims, kernel)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    for _ in range(3):
+        ops._conv_same(a, pack.k[0], b, c, kernel, allow_tc=True)
+    ev[0].record()
+    for _ in range(10):
+        ops._conv_same(a, pack.k[0], b, c, kernel, allow_tc=True)
+    ev[1].record()
+    torch.cuda.synchronize()
+    us = ev[0].elapsed_time(ev[1]) * 100.0
+    flops = 2.0 * n * np.prod(dims) * c * c * 27
+    buf = torch.zeros(160 * 16, dtype=torch.int64, device=dev)
+    LIB.call("bcp_conv_tc_debug_profile", buf.data_ptr())
+    ops._conv_same(a, pack.k[0], b, c, kernel, allow_tc=True)
+    torch.cuda.synchronize()
+    LIB.call("bcp_conv_tc_debug_profile", None)
+    p = buf.cpu().numpy().reshape(160, 16)
+    p = p[p[:, 0] > 0]
+    names = ["total", "prod_wait_emptyA", "prod_wait_emptyB", "mma_wait_fullA", "mma_wait_fullB", "mma_wait_tmem_empty",
+             "epi_wait_tmem_full", "epi_work", "mma_loop_end", "items"]
+    print(f"[prof] n={n} c={c} dims={dims} plan(BX,BY,BZ,MT,SA,NS*100+TG,AS,nb,cols,smem)={pl} {us:.1f} us "
+          f"{flops / us * 1e-6:.1f} TF/s ctas={len(p)}", flush=True)
+    print("       " + "  ".join(f"{nm}={p[:, i].mean():.0f}(max {p[:, i].max()})" for i, nm in enumerate(names)), flush=True)
+
+
 def run_s2(n, c_full, c_half, half):
     """down conv (c_full -> c_half) and transposed conv (c_half -> c_full), fwd + all gradients, tc vs direct vs torch."""
     torch.manual_seed(2)
@@ -141,6 +174,9 @@ if __name__ == "__main__":
                     (2, 128, 256, (3, 4, 2)), (4, 16, 32, (56, 56, 40)), (4, 128, 256, (7, 7, 5))]:
             ws = max(ws, run_s2(*cfg))
         print("WORST s2 tc_vs_torch", ws, flush=True)
+    if "--prof" in sys.argv:
+        for cfg in [(4, 16, (112, 112, 80)), (4, 32, (56, 56, 40)), (4, 64, (28, 28, 20)), (4, 128, (14, 14, 10)), (4, 256, (7, 7, 5))]:
+            run_prof(*cfg)
     if "--wgrad" in sys.argv:
         ww = 0.0
         for cfg in [(1, 16, 16, (4, 6, 8), (3, 3, 3)), (2, 16, 16, (8, 12, 20), (3, 3, 3)), (2, 32, 32, (6, 10, 12), (3, 3, 3)),
