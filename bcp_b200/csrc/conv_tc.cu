@@ -118,6 +118,12 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+// pipeline ring position (slot, phase) advanced incrementally: `i % n` / `i / n` on runtime n are ~100-cycle integer
+// divisions on the single thread whose instruction stream paces the tensor pipe
+struct Ring {
+  uint32_t s = 0, ph = 0;
+  __device__ __forceinline__ void advance(uint32_t n) { if (++s == n) { s = 0; ph ^= 1u; } }
+};
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -180,7 +186,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (warp-uniform; one elected lane issues)
     {
-      uint32_t ia = 0, ib = 0;                       // running item counters -> slot = i % S, phase = (i / S) & 1
+      Ring ra, rb;                                   // (slot, phase) of the A / B rings
       const uint32_t a_bytes = (uint32_t)p.rows_h * 32u;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const int brick = item / p.NS, n0 = (item - brick * p.NS) * p.Ns;
@@ -191,16 +197,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         const int bx = r / p.nby;
         const int x0 = bx * p.BX - (p.kx >> 1), y0 = by * p.BY - 1, z0 = bz * p.BZ - 1;
         for (int c = 0; c < p.nchunks; ++c) {
-          const uint32_t sa = ia % p.SA, pa = (ia / p.SA) & 1;
+          const uint32_t sa = ra.s, pa = ra.ph;
           { long long t0 = PROF ? clock64() : 0; mbar_wait(empty_a + 8 * sa, pa ^ 1); if (PROF) w0 += clock64() - t0; }
           if (elect_one()) {
             mbar_expect_tx(full_a + 8 * sa, a_bytes);
             tma_load_cb8(a_base + sa * p.slotA_bytes, &tmap, full_a + 8 * sa, p.mergedA, z0, y0, x0, n * Cib + 2 * c);
           }
           __syncwarp();
-          ++ia;
+          ra.advance(p.SA);
           for (int t = 0; t < p.T; t += p.TG) {
-            const uint32_t sb = ib % p.SB, pb = (ib / p.SB) & 1;
+            const uint32_t sb = rb.s, pb = rb.ph;
             { long long t0 = PROF ? clock64() : 0; mbar_wait(empty_b + 8 * sb, pb ^ 1); if (PROF) w1 += clock64() - t0; }
             if (elect_one()) {
               // ONE 4-D TMA box {8, Ns channels, 2 planes, TG taps} of the operand pack [T][Cin/8][Cout][8] per stage
@@ -210,79 +216,84 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
               else tma_load_4d(b_base + sb * p.stageB_bytes, &tmap_w, full_b + 8 * sb, 0, n0, 2 * c, t);
             }
             __syncwarp();
-            ++ib;
+            rb.advance(p.SB);
           }
         }
       }
     }
     if (PROF && lane == 0) { prof[blockIdx.x * 16 + 1] = w0; prof[blockIdx.x * 16 + 2] = w1; }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (warp-uniform; one elected lane issues)
-    {
+    // ------------------------------------------------------------------ MMA issuer: ONE elected thread runs the whole role
+    // (waits, issue, commits).  Measured (tools/micro/mma_bench.cu): the tensor pipe retires a M=128,K=16 MMA every
+    // max(N/2, 32+N/4) cycles regardless of accumulator reuse or operand alignment -- but only if the issuing thread
+    // spends a handful of uniform-datapath instructions per MMA.  So: descriptor high words are constants, the nine
+    // (dy,dz) taps of a dx-group are unrolled with immediate row offsets, and only 32-bit low words are updated.
+    if (elect_one()) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Ns >> 3) << 17) | ((128u >> 4) << 24);
-      // descriptors differ only in their 14-bit start-address field (16-byte units): build the constant part once and
-      // add row offsets -- the issuing lane then spends a handful of integer ops per MMA
       const uint64_t adesc0 = make_desc(0, (uint32_t)p.rows_h * 16u, 128u);
       const uint64_t bdesc0 = make_desc(0, (uint32_t)p.Ns * 16u, 128u);
-      const uint32_t tap_rows_b = (p.stageB_bytes / p.TG) >> 4;          // 16-byte units per tap inside a B stage
-      uint32_t ia = 0, ib = 0, it = 0;
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
-        const uint32_t as = it % p.AS, ap = (it / p.AS) & 1;
+      const uint32_t a_hi = (uint32_t)(adesc0 >> 32), b_hi = (uint32_t)(bdesc0 >> 32);
+      const uint32_t a_lo0 = (uint32_t)adesc0, b_lo0 = (uint32_t)bdesc0;
+      const uint32_t bstep = (uint32_t)p.Ns * 2u;                          // 16-byte units per tap inside a B stage
+      const uint32_t HZ = (uint32_t)p.HZ, plane = (uint32_t)(p.HY * p.HZ);
+      const int groups = p.TG / 9;                                          // dx-groups per B stage (TG is 9 or 27)
+      Ring ra, rb, rt;
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it, rt.advance(p.AS)) {
+        const uint32_t as = rt.s, ap = rt.ph;
         { long long t0 = PROF ? clock64() : 0; mbar_wait(tmem_empty + 8 * as, ap ^ 1); if (PROF) w2 += clock64() - t0; }
         tc_fence_after();
         const uint32_t d0 = tmem_base + as * (uint32_t)(p.MT * p.Ns);
         for (int c = 0; c < p.nchunks; ++c) {
-          const uint32_t sa = ia % p.SA, pa = (ia / p.SA) & 1;
+          const uint32_t sa = ra.s, pa = ra.ph;
           { long long t0 = PROF ? clock64() : 0; mbar_wait(full_a + 8 * sa, pa); if (PROF) w0 += clock64() - t0; }
           tc_fence_after();
-          const uint64_t a_slot = adesc0 + (uint64_t)((a_base + sa * p.slotA_bytes) >> 4);
-          int tx = 0, ty = 0, tz = 0;
+          uint32_t a_dx = a_lo0 + ((a_base + sa * p.slotA_bytes) >> 4);   // advances one x-plane per dx-group
           for (int t = 0; t < p.T; t += p.TG) {
-            const uint32_t sb = ib % p.SB, pb = (ib / p.SB) & 1;
+            const uint32_t sb = rb.s, pb = rb.ph;
             { long long t0 = PROF ? clock64() : 0; mbar_wait(full_b + 8 * sb, pb); if (PROF) w1 += clock64() - t0; }
             tc_fence_after();
-            uint64_t bdesc = bdesc0 + (uint64_t)((b_base + sb * p.stageB_bytes) >> 4);
-            const bool leader = elect_one();
-            for (int g = 0; g < p.TG; ++g) {
-              const uint64_t adesc_t = a_slot + (uint64_t)((tx * p.HY + ty) * p.HZ + tz);
-              const uint32_t acc = (c | t | g) ? 1u : 0u;
-              if (leader) {
-                uint32_t d = d0;
-#pragma unroll 4
-                for (int mt = 0; mt < p.MT; ++mt) {
-                  umma_bf16(d, adesc_t + (uint64_t)(mt * 128), bdesc, idesc, acc);
-                  d += (uint32_t)p.Ns;
+            uint32_t b_g = b_lo0 + ((b_base + sb * p.stageB_bytes) >> 4);
+            for (int g = 0; g < groups; ++g) {
+              const uint32_t first = (uint32_t)(c | t | g);                 // 0 only for the very first tap of the item
+              uint32_t d = d0, a_m = a_dx;
+              for (int mt = 0; mt < p.MT; ++mt) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                  const uint32_t a_lo = a_m + (uint32_t)(k / 3) * HZ + (uint32_t)(k % 3);
+                  const uint32_t b_lo = b_g + (uint32_t)k * bstep;
+                  umma_bf16(d, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, idesc, k ? 1u : first);
                 }
+                d += (uint32_t)p.Ns;
+                a_m += 128u;
               }
-              bdesc += tap_rows_b;
-              if (++tz == 3) { tz = 0; if (++ty == 3) { ty = 0; ++tx; } }
+              a_dx += plane;
+              b_g += 9u * bstep;
             }
-            if (leader) umma_commit(empty_b + 8 * sb);
-            __syncwarp();
-            ++ib;
+            umma_commit(empty_b + 8 * sb);
+            rb.advance(p.SB);
           }
-          if (elect_one()) umma_commit(empty_a + 8 * sa);
-          __syncwarp();
-          ++ia;
+          umma_commit(empty_a + 8 * sa);
+          ra.advance(p.SA);
         }
-        if (elect_one()) umma_commit(tmem_full + 8 * as);
-        __syncwarp();
+        umma_commit(tmem_full + 8 * as);
       }
-      if (PROF && lane == 0) { prof[blockIdx.x * 16 + 3] = w0; prof[blockIdx.x * 16 + 4] = w1; prof[blockIdx.x * 16 + 5] = w2; prof[blockIdx.x * 16 + 8] = clock64() - t_start; prof[blockIdx.x * 16 + 9] = it; }
+      if (PROF) { prof[blockIdx.x * 16 + 3] = w0; prof[blockIdx.x * 16 + 4] = w1; prof[blockIdx.x * 16 + 5] = w2; prof[blockIdx.x * 16 + 8] = clock64() - t_start; prof[blockIdx.x * 16 + 9] = it; }
     }
+    __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue warps (TMEM lane quarter = warp % 4)
     const int q = warp & 3;
-    uint32_t it = 0;
+    Ring rt;
     const long long S = (long long)p.X * p.Y * p.Z;
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, rt.advance(p.AS)) {
       const int brick = item / p.NS, n0 = (item - brick * p.NS) * p.Ns;
       const int n = brick / bricks_per_n;
       int r = brick - n * bricks_per_n;
       const int bz = r % p.nbz; r /= p.nbz;
       const int by = r % p.nby;
       const int bx = r / p.nby;
-      const uint32_t as = it % p.AS, ap = (it / p.AS) & 1;
+      const uint32_t as = rt.s, ap = rt.ph;
       long long t_e0 = 0;
       { long long t0 = PROF ? clock64() : 0; mbar_wait(tmem_full + 8 * as, ap); if (PROF) { t_e0 = clock64(); w0 += t_e0 - t0; } }
       tc_fence_after();
@@ -383,7 +394,7 @@ conv_tc_s2_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16*
 
   if (warp == 0) {
     {
-      uint32_t ia = 0, ib = 0;
+      Ring ra, rb;
       const uint32_t a_bytes = (uint32_t)p.rows * 32u;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int brick = tile / p.npieces, piece = tile - brick * p.npieces;
@@ -395,9 +406,9 @@ conv_tc_s2_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16*
         for (int k = 0; k < kitems; ++k) {
           const int c = (p.mode == 1) ? (k >> 3) : k;
           const int t = (p.mode == 1) ? (k & 7) : 0;
-          const uint32_t sa = ia % p.SA, pa = (ia / p.SA) & 1;
+          const uint32_t sa = ra.s, pa = ra.ph;
           mbar_wait(empty_a + 8 * sa, pa ^ 1);
-          const uint32_t sb = ib % p.SB, pb = (ib / p.SB) & 1;
+          const uint32_t sb = rb.s, pb = rb.ph;
           mbar_wait(empty_b + 8 * sb, pb ^ 1);
           if (elect_one()) {
             mbar_expect_tx(full_a + 8 * sa, a_bytes);
@@ -417,55 +428,59 @@ conv_tc_s2_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16*
             }
           }
           __syncwarp();
-          ++ia;
-          ++ib;
+          ra.advance(p.SA);
+          rb.advance(p.SB);
         }
       }
     }
   } else if (warp == 1) {
     {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Npiece >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t lboA = (uint32_t)p.rows * 16u, lboB = (uint32_t)p.Npiece * 16u;
-      uint32_t ia = 0, ib = 0, it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const uint32_t as = it % p.AS, ap = (it / p.AS) & 1;
-        mbar_wait(tmem_empty + 8 * as, ap ^ 1);
-        tc_fence_after();
-        const uint32_t d0 = tmem_base + as * (uint32_t)(p.MT * p.Npiece);
-        for (int k = 0; k < kitems; ++k) {
-          const uint32_t sa = ia % p.SA, pa = (ia / p.SA) & 1;
-          const uint32_t sb = ib % p.SB, pb = (ib / p.SB) & 1;
-          mbar_wait(full_a + 8 * sa, pa);
-          mbar_wait(full_b + 8 * sb, pb);
+      const uint64_t adesc0 = make_desc(0, (uint32_t)p.rows * 16u, 128u), bdesc0 = make_desc(0, (uint32_t)p.Npiece * 16u, 128u);
+      const uint32_t a_hi = (uint32_t)(adesc0 >> 32), b_hi = (uint32_t)(bdesc0 >> 32);
+      const uint32_t a_lo0 = (uint32_t)adesc0, b_lo0 = (uint32_t)bdesc0;
+      if (elect_one()) {                  // one elected thread runs the whole role (see conv_tc_kernel)
+        Ring ra, rb, rt;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, rt.advance(p.AS)) {
+          const uint32_t as = rt.s, ap = rt.ph;
+          mbar_wait(tmem_empty + 8 * as, ap ^ 1);
           tc_fence_after();
-          const uint64_t bdesc = make_desc(b_base + sb * p.stageB_bytes, lboB, 128u);
-          const uint64_t adesc = make_desc(a_base + sa * p.slotA_bytes, lboA, 128u);
-          if (elect_one()) {
-            for (int mt = 0; mt < p.MT; ++mt)
-              umma_bf16(d0 + (uint32_t)(mt * p.Npiece), adesc + (uint64_t)(mt * 128), bdesc, idesc, k ? 1u : 0u);
+          const uint32_t d0 = tmem_base + as * (uint32_t)(p.MT * p.Npiece);
+          for (int k = 0; k < kitems; ++k) {
+            const uint32_t sa = ra.s, pa = ra.ph;
+            const uint32_t sb = rb.s, pb = rb.ph;
+            mbar_wait(full_a + 8 * sa, pa);
+            mbar_wait(full_b + 8 * sb, pb);
+            tc_fence_after();
+            const uint64_t bdesc = ((uint64_t)b_hi << 32) | (b_lo0 + ((b_base + sb * p.stageB_bytes) >> 4));
+            uint32_t a_lo = a_lo0 + ((a_base + sa * p.slotA_bytes) >> 4), d = d0;
+            for (int mt = 0; mt < p.MT; ++mt) {
+              umma_bf16(d, ((uint64_t)a_hi << 32) | a_lo, bdesc, idesc, k ? 1u : 0u);
+              d += (uint32_t)p.Npiece;
+              a_lo += 128u;
+            }
             umma_commit(empty_a + 8 * sa);
             umma_commit(empty_b + 8 * sb);
+            ra.advance(p.SA); rb.advance(p.SB);
           }
-          __syncwarp();
-          ++ia; ++ib;
+          umma_commit(tmem_full + 8 * as);
         }
-        if (elect_one()) umma_commit(tmem_full + 8 * as);
-        __syncwarp();
       }
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;
-    uint32_t it = 0;
+    Ring rt;
     const int Xo = (p.mode == 1) ? p.Xh : 2 * p.Xh, Yo = (p.mode == 1) ? p.Yh : 2 * p.Yh, Zo = (p.mode == 1) ? p.Zh : 2 * p.Zh;
     const long long So = (long long)Xo * Yo * Zo;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, rt.advance(p.AS)) {
       const int brick = tile / p.npieces, piece = tile - brick * p.npieces;
       const int n = brick / bricks_per_n;
       int r = brick - n * bricks_per_n;
       const int bz = r % p.nbz; r /= p.nbz;
       const int by = r % p.nby;
       const int bx = r / p.nby;
-      const uint32_t as = it % p.AS, ap = (it / p.AS) & 1;
+      const uint32_t as = rt.s, ap = rt.ph;
       mbar_wait(tmem_full + 8 * as, ap);
       tc_fence_after();
       const uint32_t d0 = tmem_base + as * (uint32_t)(p.MT * p.Npiece) + ((uint32_t)(q * 32) << 16);
@@ -530,6 +545,11 @@ struct WgParams {
   int MM, m64map;                 // MMA M (128 or 64) and the TMEM row->lane map assumed for M = 64
   unsigned a_tx_bytes, dy_tx_bytes, a_alloc_bytes, dy_alloc_bytes, slot_bytes, offBar, tap_bytes;
   int mergedA, mergedD;
+  // dz-folded mode (3*Cout <= 128): the three dz taps of a (dx,dy) pair ride in the M dimension.  The dy brick is loaded
+  // three times, copy dz shifted by dz rows along z (a TMA coordinate), so ONE MMA per (dx,dy) produces
+  // D[(dz,co)][ci]; a 16-channel layer then issues 9 MMAs per K-step with 48 useful rows instead of 27 with 16.
+  int fz;                         // 1 or 3
+  int KG, ngrp;                   // folded: (dx,dy) groups per pass / in total
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -544,8 +564,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int split = blockIdx.x, pass = blockIdx.y;
   const int mh = pass % p.MH, tg = pass / p.MH;
-  const int t0 = tg * p.TP;
-  const int ntap = min(p.TP, p.T - t0);
+  const int t0 = (p.fz == 3) ? tg * p.KG : tg * p.TP;                           // first tap (folded: first (dx,dy) group)
+  const int ntap = (p.fz == 3) ? min(p.KG, p.ngrp - t0) : min(p.TP, p.T - t0);  // accumulators this CTA owns
   const int Cib = p.Cin >> 3, Cob = p.Cout >> 3;
 
   // zero the regions TMA never writes (unused dy planes, slack rows after the a planes): they feed MMAs
@@ -580,12 +600,12 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 
   if (warp == 0) {
     {
-      uint32_t it = 0;
-      for (int brick = split; brick < p.nbricks; brick += p.splits, ++it) {
+      Ring rs;
+      for (int brick = split; brick < p.nbricks; brick += p.splits, rs.advance(p.S)) {
         const int n = brick / bricks_per_n;
         const int r = brick - n * bricks_per_n;
         const int by = r % p.nby, bx = r / p.nby;
-        const uint32_t s = it % p.S, ph = (it / p.S) & 1;
+        const uint32_t s = rs.s, ph = rs.ph;
         mbar_wait(empty + 8 * s, ph ^ 1);
         const uint32_t slot = sbase + s * p.slot_bytes;
         if (elect_one()) {
@@ -600,7 +620,13 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           mbar_expect_tx(full + 8 * s, p.a_tx_bytes + p.dy_tx_bytes);
           tma_load_cb8(slot, &map_a, full + 8 * s, p.mergedA, -1, by * p.BY - 1, bx * p.BX - (p.kx >> 1), n * Cib);
         }
-        tma_load_cb8(slot + p.a_alloc_bytes, &map_dy, full + 8 * s, p.mergedD, 0, by * p.BY, bx * p.BX, n * Cob + mh * 16);
+        if (p.fz == 3) {
+          const uint32_t copy_bytes = (uint32_t)Cob * (uint32_t)p.rows_dy * 16u;
+          for (int dz = 0; dz < 3; ++dz)
+            tma_load_cb8(slot + p.a_alloc_bytes + (uint32_t)dz * copy_bytes, &map_dy, full + 8 * s, p.mergedD, -dz, by * p.BY, bx * p.BX, n * Cob);
+        } else {
+          tma_load_cb8(slot + p.a_alloc_bytes, &map_dy, full + 8 * s, p.mergedD, 0, by * p.BY, bx * p.BX, n * Cob + mh * 16);
+        }
         }
         __syncwarp();
       }
@@ -612,43 +638,60 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       // constant descriptor parts; per MMA only the 16-byte-unit start address changes
       const uint64_t adesc0 = make_desc(0, 128u, (uint32_t)p.rows_dy * 16u);
       const uint64_t bdesc0 = make_desc(0, 128u, (uint32_t)p.rows_a * 16u);
-      // per-tap row offset of this CTA's taps (same-conv: halo shift; stride-2: separate gathered brick per tap)
+      // per-accumulator B row offset (same-conv: halo shift of the tap; folded: (dx,dy) shift only; stride-2: separate
+      // gathered brick per tap)
       uint32_t* tapoff = reinterpret_cast<uint32_t*>(smem + p.offBar + 8 * (2 * p.S + 1) + 16);
       if (lane < 27) {
         const int t = t0 + lane;
-        const int tz = t % 3, ty = (t / 3) % 3, tx = t / 9;
-        tapoff[lane] = p.s2 ? (uint32_t)lane * (p.tap_bytes >> 4) : (uint32_t)((tx * p.HY + ty) * p.HZ + tz);
+        uint32_t off;
+        if (p.s2) off = (uint32_t)lane * (p.tap_bytes >> 4);
+        else if (p.fz == 3) off = (p.kx == 3) ? (uint32_t)(((t / 3) * p.HY + (t % 3)) * p.HZ) : (uint32_t)(t * p.HZ);
+        else { const int tz = t % 3, ty = (t / 3) % 3, tx = t / 9; off = (uint32_t)((tx * p.HY + ty) * p.HZ + tz); }
+        tapoff[lane] = off;
       }
       __syncwarp();
-      uint32_t it = 0;
-      uint32_t acc = 0;
-      const int row_step_y = p.s2 ? p.ZP : p.HZ;                 // B-row distance between consecutive lines
-      const int row_step_x = p.s2 ? p.BY * p.ZP : p.HY * p.HZ;
-      for (int brick = split; brick < p.nbricks; brick += p.splits, ++it) {
-        const uint32_t s = it % p.S, ph = (it / p.S) & 1;
-        mbar_wait(full + 8 * s, ph);
-        tc_fence_after();
-        const uint32_t a_slot = sbase + s * p.slot_bytes, dy_slot = a_slot + p.a_alloc_bytes;
-        const uint64_t a_slot_d = adesc0 + (uint64_t)(dy_slot >> 4), b_slot_d = bdesc0 + (uint64_t)(a_slot >> 4);
-        const bool leader = elect_one();
-        if (leader)
-        for (int ix = 0; ix < p.BX; ++ix) {
-          for (int iy = 0; iy < p.BY; ++iy) {
-            const uint64_t arow = a_slot_d + (uint64_t)((ix * p.BY + iy) * p.ZP);
-            const uint64_t brow = b_slot_d + (uint64_t)(ix * row_step_x + iy * row_step_y);
-            for (int zc = 0; zc < p.ZP; zc += 16) {
-              const uint64_t adesc = arow + (uint64_t)zc, bz = brow + (uint64_t)zc;
-#pragma unroll 3
-              for (int tl = 0; tl < ntap; ++tl)
-                umma_bf16(tmem_base + (uint32_t)(tl * p.Cin), adesc, bz + (uint64_t)tapoff[tl], idesc, acc);
-              acc = 1;
+      // one elected thread runs the role; descriptor high words are constants, only 32-bit start fields move
+      if (elect_one()) {
+        const uint32_t a_hi = (uint32_t)(adesc0 >> 32), b_hi = (uint32_t)(bdesc0 >> 32);
+        const uint32_t a_lo0 = (uint32_t)adesc0, b_lo0 = (uint32_t)bdesc0;
+        const uint32_t cin = (uint32_t)p.Cin;
+        Ring rs;
+        uint32_t acc = 0;
+        const uint32_t row_step_y = (uint32_t)(p.s2 ? p.ZP : p.HZ);                 // B-row distance between consecutive lines
+        const uint32_t row_step_x = (uint32_t)(p.s2 ? p.BY * p.ZP : p.HY * p.HZ);
+        for (int brick = split; brick < p.nbricks; brick += p.splits, rs.advance(p.S)) {
+          const uint32_t s = rs.s, ph = rs.ph;
+          mbar_wait(full + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t a_slot = sbase + s * p.slot_bytes, dy_slot = a_slot + p.a_alloc_bytes;
+          uint32_t arow_x = a_lo0 + (dy_slot >> 4), brow_x = b_lo0 + (a_slot >> 4);
+          for (int ix = 0; ix < p.BX; ++ix) {
+            uint32_t arow = arow_x, brow = brow_x;
+            for (int iy = 0; iy < p.BY; ++iy) {
+              for (uint32_t zc = 0; zc < (uint32_t)p.ZP; zc += 16) {
+                const uint64_t adesc = ((uint64_t)a_hi << 32) | (arow + zc);
+                const uint32_t bz = brow + zc;
+                if (ntap == 9) {
+#pragma unroll
+                  for (int tl = 0; tl < 9; ++tl)
+                    umma_bf16(tmem_base + (uint32_t)tl * cin, adesc, ((uint64_t)b_hi << 32) | (bz + tapoff[tl]), idesc, acc);
+                } else {
+#pragma unroll 4
+                  for (int tl = 0; tl < ntap; ++tl)
+                    umma_bf16(tmem_base + (uint32_t)tl * cin, adesc, ((uint64_t)b_hi << 32) | (bz + tapoff[tl]), idesc, acc);
+                }
+                acc = 1;
+              }
+              arow += (uint32_t)p.ZP;
+              brow += row_step_y;
             }
+            arow_x += (uint32_t)(p.BY * p.ZP);
+            brow_x += row_step_x;
           }
+          umma_commit(empty + 8 * s);
         }
-        if (leader) umma_commit(empty + 8 * s);
-        __syncwarp();
+        umma_commit(tmem_full);
       }
-      if (elect_one()) umma_commit(tmem_full);
       __syncwarp();
     }
   } else {
@@ -662,12 +705,17 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       else if (p.m64map == 1) co = (l < 64) ? l : (1 << 30);
       else co = ((l & 63) < 32) ? ((l >> 6) * 32 + (l & 31)) : (1 << 30);
     }
+    int dzl = 0;
+    if (p.fz == 3) {                      // accumulator row r = dz * Cout + co
+      const int r = co;
+      if (r < 3 * p.Cout) { dzl = r / p.Cout; co = r - dzl * p.Cout; } else co = 1 << 30;
+    }
     if (has_work) {
       mbar_wait(tmem_full, 0);
       tc_fence_after();
     }
     for (int tl = 0; tl < ntap; ++tl) {
-      const int t = t0 + tl;
+      const int t = (p.fz == 3) ? (t0 + tl) * 3 + dzl : t0 + tl;
       float* dst = partial + (((size_t)split * p.T + t) * p.Cout + co) * p.Cin;
       for (int c16 = 0; c16 < p.Cin; c16 += 16) {
         uint32_t v[16];
@@ -769,15 +817,12 @@ static bool plan(TcParams& p, int nsm) {
     const int bz = (p.Z + d - 1) / d;
     if (bz + 2 <= 256 && (nz == 0 || bz_opts[nz - 1] != bz)) bz_opts[nz++] = bz;
   }
-  for (int NS = 1; NS <= 4; NS *= 2) {
+  for (int NS = 1; NS <= 8; NS *= 2) {
     if (p.Cout % (16 * NS)) break;
     const int Ns = p.Cout / NS;
-    // several taps share one weight stage (fewer barrier round trips for the issuing lane): largest group <= 32 KB
-    const int cands[4] = {T, 9, 3, 1};
-    int TG = 1;
-    for (int i = 0; i < 4; ++i)
-      if (cands[i] <= T && T % cands[i] == 0 && cands[i] * Ns * 32 <= 32 * 1024) { TG = cands[i]; break; }
-    const unsigned stageB = (unsigned)TG * (unsigned)Ns * 32u;
+    if (Ns > 128) continue;            // an N = 128 MMA already runs at the tensor pipe's rate (N/2 cycles); wider buys nothing
+    // a weight stage holds whole dx-groups of nine (dy,dz) taps (the issuer unrolls them): all T taps of a chunk when two
+    // such stages fit next to the A slots (one barrier round trip per chunk), else one dx-group
     const double per_mma = (Ns / 2.0 > 32.0 + Ns / 4.0) ? Ns / 2.0 : 32.0 + Ns / 4.0;
     for (int zi = 0; zi < nz; ++zi) {
       const int BZ = bz_opts[zi], HZ = BZ + 2;
@@ -796,14 +841,17 @@ static bool plan(TcParams& p, int nsm) {
           const long long slotA = ((rows_h + (rows_alloc > rows_h ? rows_alloc : rows_h)) * 16 + 127) / 128 * 128;
           // A slots: 2..3 (one (brick, 16-channel) chunk each); the rest of shared memory goes to weight stages, whose
           // depth hides the L2 latency of the cp.async.bulk stream (3..8 stages)
-          int SB = 3;
-          long long avail = (long long)SMEM_BUDGET - 1024 - (long long)SB * stageB;
+          int TG = T;
+          unsigned stageB = (unsigned)TG * (unsigned)Ns * 32u;
+          if ((long long)SMEM_BUDGET - 1024 - 2 * slotA < 2ll * stageB) { TG = 9; stageB = 9u * (unsigned)Ns * 32u; }
+          const int sb_min = (TG == T) ? 2 : 3;
+          long long avail = (long long)SMEM_BUDGET - 1024 - (long long)sb_min * stageB;
           int SA = (int)(avail / slotA);
           if (SA < 2) break;
           if (SA > 3) SA = 3;
-          SB = (int)(((long long)SMEM_BUDGET - 1024 - (long long)SA * slotA) / stageB);
+          int SB = (int)(((long long)SMEM_BUDGET - 1024 - (long long)SA * slotA) / stageB);
           if (SB > 8) SB = 8;
-          if (SB < 3) SB = 3;
+          if (SB < sb_min) SB = sb_min;
           const int nbx = (p.X + BX - 1) / BX, nby = (p.Y + BY - 1) / BY, nbz = (p.Z + BZ - 1) / BZ;
           const long long nb = (long long)p.N * nbx * nby * nbz;
           const long long items = nb * NS;
@@ -945,6 +993,22 @@ static bool wg_plan(WgParams& p, int nsm) {
   p.m64map = wg_m64_mode() < 0 ? 0 : wg_m64_mode();
   p.HZ = p.Z + 2;
   p.ZP = (p.Z + 15) / 16 * 16;
+  p.fz = 1; p.KG = 0; p.ngrp = 0;
+  static const bool no_fold = getenv("BCP_WG_NO_FOLD") != nullptr;
+  if (!no_fold && 3 * p.Cout <= 128 && (p.Z + 2 + 15) / 16 * 16 <= 256 && p.Cin <= 512 / 3 && (wg_m64_mode() >= 0 || 3 * p.Cout > 64)) {
+    // dz-folded: K runs over the halo'd z-line (Z+2 rows, rounded up to 16); both bricks use that z extent
+    p.fz = 3;
+    p.ZP = (p.Z + 2 + 15) / 16 * 16;
+    p.HZ = p.ZP;
+    p.ngrp = p.T / 3;
+    p.KG = 512 / p.Cin;
+    if (p.KG > p.ngrp) p.KG = p.ngrp;
+    p.npass_t = (p.ngrp + p.KG - 1) / p.KG;
+    p.TP = p.KG;                                  // accumulators per CTA
+    p.MH = 1;
+    p.PL = p.Cout / 8;
+    p.MM = (3 * p.Cout <= 64) ? 64 : 128;
+  }
   const int npass = p.npass_t * p.MH;
   int cols = 32;
   while (cols < p.TP * p.Cin) cols *= 2;
@@ -960,7 +1024,7 @@ static bool wg_plan(WgParams& p, int nsm) {
       if (HX > 256) break;
       const long long rows_a = (long long)HX * HY * p.HZ, rows_dy = (long long)BX * BY * p.ZP;
       if (rows_a >= 16384 || rows_dy >= 16384) break;
-      const long long a_tx = rows_a * 16 * Cib, dy_tx = rows_dy * 16 * p.PL;
+      const long long a_tx = rows_a * 16 * Cib, dy_tx = rows_dy * 16 * p.PL * p.fz;
       const long long a_alloc = (a_tx + 256 + 127) / 128 * 128, dy_alloc = (rows_dy * 16 * (p.MM / 8) + 127) / 128 * 128;
       const long long slot = a_alloc + dy_alloc;
       int S = (int)((SMEM_BUDGET - 1024) / slot);

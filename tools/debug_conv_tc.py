@@ -146,7 +146,16 @@ def run_wgrad(n, cin, cout, dims, kernel):
     d_t = ops._wgrad(a, dy, cin, cout, dims, kernel, (1, 1, 1), pad, w.shape, allow_tc=True)
     torch.cuda.synchronize()
     e_d, e_t = rel_rms(d_d, w.grad), rel_rms(d_t, w.grad)
-    print(f"[wgrad] n={n} cin={cin} cout={cout} dims={dims} k={kernel} direct_vs_torch={e_d:.2e} tc_vs_torch={e_t:.2e}", flush=True)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(5):
+        ops._wgrad(a, dy, cin, cout, dims, kernel, (1, 1, 1), pad, w.shape, allow_tc=True)
+    ev[1].record()
+    torch.cuda.synchronize()
+    us = ev[0].elapsed_time(ev[1]) * 200.0
+    tf = 2.0 * n * np.prod(dims) * cin * cout * np.prod(kernel) / us * 1e-6
+    print(f"[wgrad] n={n} cin={cin} cout={cout} dims={dims} k={kernel} direct_vs_torch={e_d:.2e} tc_vs_torch={e_t:.2e} "
+          f"{us:.1f} us {tf:.1f} TF/s", flush=True)
     if e_t > 1e-2:
         bad = (d_t - w.grad).abs() > 0.05 * w.grad.abs().max()
         print("   bad frac", float(bad.float().mean()), "by tap", bad.float().mean(dim=(0, 1)).flatten().cpu().numpy().round(2))
@@ -182,6 +191,8 @@ if __name__ == "__main__":
         for cfg in [(1, 16, 16, (4, 6, 8), (3, 3, 3)), (2, 16, 16, (8, 12, 20), (3, 3, 3)), (2, 32, 32, (6, 10, 12), (3, 3, 3)),
                     (2, 64, 64, (28, 28, 20), (3, 3, 3)), (2, 128, 128, (14, 14, 10), (3, 3, 3)), (2, 256, 256, (7, 7, 5), (3, 3, 3)),
                     (2, 32, 16, (9, 7, 11), (3, 3, 3)), (2, 16, 64, (5, 5, 5), (3, 3, 3)), (1, 16, 16, (112, 112, 80), (3, 3, 3)),
-                    (3, 16, 16, (1, 64, 64), (1, 3, 3)), (2, 256, 128, (1, 16, 16), (1, 3, 3))]:
+                    (3, 16, 16, (1, 64, 64), (1, 3, 3)), (2, 256, 128, (1, 16, 16), (1, 3, 3)), (2, 64, 32, (6, 10, 12), (3, 3, 3)),
+                    (4, 16, 16, (112, 112, 80), (3, 3, 3)), (4, 32, 32, (56, 56, 40), (3, 3, 3)), (4, 64, 64, (28, 28, 20), (3, 3, 3)),
+                    (4, 128, 128, (14, 14, 10), (3, 3, 3)), (4, 256, 256, (7, 7, 5), (3, 3, 3))]:
             ww = max(ww, run_wgrad(*cfg))
         print("WORST wgrad tc_vs_torch", ww, flush=True)
