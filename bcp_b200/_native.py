@@ -23,8 +23,17 @@ _CT = {
 }
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim)
+def _norm_bwd_kernels(args):
+    # (dact, y, dy, stat, coef, chan_scale, elem_keep, elem_scale, dgamma, dbeta, sums, workspace, counter, n, c, s, spg, slope,
+    #  stats_grad, accumulate, stream): small layers run reduce+apply in one launch (norm.cu SMALL_LIMIT)
+    n, s, stats_grad = int(args[13]), int(args[15]), int(args[18])
+    if n * s <= 2048:
+        return 1
+    return 2 if (stats_grad or args[8] or args[9]) else 1
+
+
 KERNELS_PER_CALL = {
-    "bcp_norm_stats": 1, "bcp_norm_bwd": 2, "bcp_mix_loss_fwd": 2, "bcp_conv_direct_wgrad": 2,
+    "bcp_norm_stats": 1, "bcp_norm_bwd": _norm_bwd_kernels, "bcp_mix_loss_fwd": 2, "bcp_conv_direct_wgrad": 2,
     "bcp_chan_sum": 2, "bcp_conv_first_wgrad": 2, "bcp_head_wgrad": 2, "bcp_largest_cc": 5,
     "bcp_conv_tc_wgrad": 2,
 }
@@ -87,7 +96,8 @@ class _Lib:
         rc = getattr(lib, name)(*args)
         if rc != 0:
             raise RuntimeError("%s failed (%d): %s" % (name, rc, lib.bcp_last_error().decode()))
-        self.launches += KERNELS_PER_CALL.get(name, 1)
+        k = KERNELS_PER_CALL.get(name, 1)
+        self.launches += k(args) if callable(k) else k
 
     def query(self, name: str, *args):
         return getattr(self.load(), name)(*args)

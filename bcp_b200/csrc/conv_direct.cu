@@ -225,12 +225,14 @@ __global__ void chan_sum_finalize_kernel(const float* __restrict__ partial, floa
 // -------------------------------------------------------------------------------------------------
 // first layer: Cin = 1, fp32 planar input [N][X][Y][Z]; weights fp32 [Cout][1][T] (PyTorch layout)
 // -------------------------------------------------------------------------------------------------
+constexpr int FIRST_ZR = 4;       // consecutive z outputs per thread in the first-layer forward
 template <int KX>
 __global__ void __launch_bounds__(128) conv_first_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                               const float* __restrict__ bias, uint4* __restrict__ out,
                                                               Geom g, int Cout) {
-  // kernel KX x 3 x 3, 'same' padding; fully unrolled taps (27 or 9 input values live in registers)
-  constexpr int T = KX * 9;
+  // kernel KX x 3 x 3, 'same' padding.  A thread produces FIRST_ZR consecutive z voxels: the KX*3 input rows it needs are
+  // read once as (FIRST_ZR + 2)-wide windows and every weight fetched from shared memory feeds FIRST_ZR voxels.
+  constexpr int T = KX * 9, ZR = FIRST_ZR;
   extern __shared__ float wsm[];   // [T][Cob*8]
   const int Cob = (Cout + 7) / 8;
   for (int i = threadIdx.x; i < T * Cob * 8; i += 128) {
@@ -238,75 +240,114 @@ __global__ void __launch_bounds__(128) conv_first_fwd_kernel(const float* __rest
     wsm[i] = (c < Cout) ? w[(long long)c * T + t] : 0.f;
   }
   __syncthreads();
+  const int zg = (g.Zo + ZR - 1) / ZR;
   const long long So = (long long)g.Xo * g.Yo * g.Zo;
-  const long long total = (long long)g.N * So;
+  const long long total = (long long)g.N * g.Xo * g.Yo * zg;
   const long long stride = (long long)gridDim.x * 128;
   for (long long o = (long long)blockIdx.x * 128 + threadIdx.x; o < total; o += stride) {
-    int n, x, y, z;
-    decompose(o, g, n, x, y, z);
-    float v[T];
+    const int gz = (int)(o % zg);
+    long long r = o / zg;
+    const int y = (int)(r % g.Yo); r /= g.Yo;
+    const int x = (int)(r % g.Xo);
+    const int n = (int)(r / g.Xo);
+    const int z0 = gz * ZR;
+    float v[KX * 3][ZR + 2];
     const float* base = in + (long long)n * g.Xi * g.Yi * g.Zi;
 #pragma unroll
     for (int tx = 0; tx < KX; ++tx)
 #pragma unroll
-      for (int ty = 0; ty < 3; ++ty)
+      for (int ty = 0; ty < 3; ++ty) {
+        const int ix = x + tx - (KX >> 1), iy = y + ty - 1;
+        const bool rok = ix >= 0 && ix < g.Xi && iy >= 0 && iy < g.Yi;
+        const float* row = base + ((long long)ix * g.Yi + iy) * g.Zi;
 #pragma unroll
-        for (int tz = 0; tz < 3; ++tz) {
-          const int ix = x + tx - (KX >> 1), iy = y + ty - 1, iz = z + tz - 1;
-          const bool ok = ix >= 0 && ix < g.Xi && iy >= 0 && iy < g.Yi && iz >= 0 && iz < g.Zi;
-          v[(tx * 3 + ty) * 3 + tz] = ok ? __ldg(base + ((long long)ix * g.Yi + iy) * g.Zi + iz) : 0.f;
+        for (int k = 0; k < ZR + 2; ++k) {
+          const int iz = z0 + k - 1;
+          v[tx * 3 + ty][k] = (rok && iz >= 0 && iz < g.Zi) ? __ldg(row + iz) : 0.f;
         }
-    const long long so = o - (long long)n * So;
+      }
+    const long long so = ((long long)x * g.Yo + y) * g.Zo + z0;
     for (int cob = 0; cob < Cob; ++cob) {
-      float acc[8];
+      float acc[ZR][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = (bias && cob * 8 + j < Cout) ? bias[cob * 8 + j] : 0.f;
+      for (int k = 0; k < ZR; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[k][j] = (bias && cob * 8 + j < Cout) ? bias[cob * 8 + j] : 0.f;
 #pragma unroll
       for (int t = 0; t < T; ++t) {
         const float4 w0 = *reinterpret_cast<const float4*>(wsm + t * Cob * 8 + cob * 8);
         const float4 w1 = *reinterpret_cast<const float4*>(wsm + t * Cob * 8 + cob * 8 + 4);
-        acc[0] += v[t] * w0.x; acc[1] += v[t] * w0.y; acc[2] += v[t] * w0.z; acc[3] += v[t] * w0.w;
-        acc[4] += v[t] * w1.x; acc[5] += v[t] * w1.y; acc[6] += v[t] * w1.z; acc[7] += v[t] * w1.w;
+#pragma unroll
+        for (int k = 0; k < ZR; ++k) {
+          const float a = v[t / 3][k + (t % 3)];
+          acc[k][0] += a * w0.x; acc[k][1] += a * w0.y; acc[k][2] += a * w0.z; acc[k][3] += a * w0.w;
+          acc[k][4] += a * w1.x; acc[k][5] += a * w1.y; acc[k][6] += a * w1.z; acc[k][7] += a * w1.w;
+        }
       }
-      out[((long long)n * Cob + cob) * So + so] = pack8(acc);
+      uint4* dst = out + ((long long)n * Cob + cob) * So + so;
+#pragma unroll
+      for (int k = 0; k < ZR; ++k)
+        if (z0 + k < g.Zo) dst[k] = pack8(acc[k]);
     }
   }
 }
 
-constexpr int FIRST_WG_CHUNK = 16384;
-// dW[co][t]: grid (chunks, Cob, kx); thread acc[ky*kz <= 9][8]; partial[chunk][cob][tx][9][8]
+constexpr int FIRST_WG_XC = 8;    // x planes per block in the first-layer weight gradient
+// dW[co][t] for Cin = 1.  grid (ztiles * xchunks, N, Cob * kx), 4 warps.  A warp owns 32 consecutive z and a quarter of
+// the y range and walks along y: per step one coalesced 16-byte dy load, three input loads (the new y row of a 3x3
+// register window) and 72 FMAs -- no per-voxel index arithmetic.  partial[chunk][cob][tx][9][8], chunk = (block.x, n).
 __global__ void __launch_bounds__(128) conv_first_wgrad_partial_kernel(const float* __restrict__ in, const uint4* __restrict__ og,
                                                                         float* __restrict__ partial, Geom g, int Cout) {
   const int Cob = (Cout + 7) / 8;
-  const int cob = blockIdx.y, tx = blockIdx.z;
+  const int cob = blockIdx.z / g.kx, tx = blockIdx.z - cob * g.kx;
+  const int n = blockIdx.y;
+  const int nzt = (g.Zo + 31) / 32;
+  const int xchunk = blockIdx.x / nzt, ztile = blockIdx.x - xchunk * nzt;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int z = ztile * 32 + lane;
+  const bool zok = z < g.Zo;
+  const int seg = (g.Yo + 3) / 4;
+  const int y0 = warp * seg, y1 = min(g.Yo, y0 + seg);
   const long long So = (long long)g.Xo * g.Yo * g.Zo;
-  const long long total = (long long)g.N * So;
-  const long long o0 = (long long)blockIdx.x * FIRST_WG_CHUNK, o1 = min(total, o0 + FIRST_WG_CHUNK);
   float acc[9][8];
 #pragma unroll
   for (int i = 0; i < 9; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  const int YZ = g.Yo * g.Zo;
-  for (long long o = o0 + threadIdx.x; o < o1; o += 128) {
-    // 32-bit index math (a sample has < 2^31 voxels); 64-bit only for the sample split
-    const int n = (int)(o / So);
-    const int sp = (int)(o - (long long)n * So);
-    const int x = sp / YZ, r2 = sp - x * YZ, y = r2 / g.Zo, z = r2 - y * g.Zo;
-    float d[8];
-    unpack8(__ldg(og + ((long long)n * Cob + cob) * So + sp), d);
+  const int x_end = min(g.Xo, (xchunk + 1) * FIRST_WG_XC);
+  for (int x = xchunk * FIRST_WG_XC; x < x_end; ++x) {
     const int ix = x + tx - g.px;
-    if (ix < 0 || ix >= g.Xi) continue;
+    if (ix < 0 || ix >= g.Xi || y0 >= y1) continue;
+    const float* plane = in + ((long long)n * g.Xi + ix) * g.Yi * g.Zi;
+    auto load_row = [&](int iy, float* r3) {
+      const bool rok = iy >= 0 && iy < g.Yi;
+      const float* row = plane + (long long)iy * g.Zi;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) {
-      const int ty = i / 3, tz = i % 3;
-      if (ty < g.ky && tz < g.kz) {
-        const int iy = y + ty - g.py, iz = z + tz - g.pz;
-        const bool ok = iy >= 0 && iy < g.Yi && iz >= 0 && iz < g.Zi;
-        const float v = ok ? __ldg(in + ((long long)n * g.Xi + ix) * g.Yi * g.Zi + (long long)iy * g.Zi + iz) : 0.f;
+      for (int k = 0; k < 3; ++k) {
+        const int iz = z + k - 1;
+        r3[k] = (rok && iz >= 0 && iz < g.Zi) ? __ldg(row + iz) : 0.f;
+      }
+    };
+    float win[3][3];
+    load_row(y0 - 1, win[0]);
+    load_row(y0, win[1]);
+    const uint4* dyp = og + ((long long)n * Cob + cob) * So + ((long long)x * g.Yo + y0) * g.Zo + z;
+    for (int y = y0; y < y1; ++y, dyp += g.Zo) {
+      load_row(y + 1, win[2]);
+      float d[8];
+      if (zok) unpack8(__ldg(dyp), d);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        const float v = win[i / 3][i % 3];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] += v * d[j];
       }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { win[0][k] = win[1][k]; win[1][k] = win[2][k]; }
     }
   }
   __shared__ float red[72 * 4];
@@ -317,7 +358,8 @@ __global__ void __launch_bounds__(128) conv_first_wgrad_partial_kernel(const flo
     for (int j = 0; j < 8; ++j) flat[i * 8 + j] = acc[i][j];
   block_sum<72, 128>(flat, red);
   if (threadIdx.x == 0) {
-    float* dst = partial + (((long long)blockIdx.x * Cob + cob) * g.kx + tx) * 72;
+    const long long chunk = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+    float* dst = partial + ((chunk * Cob + cob) * g.kx + tx) * 72;
 #pragma unroll
     for (int k = 0; k < 72; ++k) dst[k] = flat[k];
   }
@@ -568,7 +610,7 @@ int bcp_conv_first_fwd(const float* in, const float* w, const float* bias, void*
   BCP_REQUIRE(make_geom(g, n, dims, kernel, stride, pad, 0) == 0, "conv_first_fwd: bad geometry");
   BCP_REQUIRE((g.kx == 3 || g.kx == 1) && g.ky == 3 && g.kz == 3, "conv_first_fwd: kernel must be 3x3x3 or 1x3x3");
   const int Cob = (cout + 7) / 8;
-  const long long total = (long long)n * g.Xo * g.Yo * g.Zo;
+  const long long total = (long long)n * g.Xo * g.Yo * ((g.Zo + FIRST_ZR - 1) / FIRST_ZR);
   long long blocks = (total + 127) / 128;
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
@@ -581,8 +623,8 @@ int bcp_conv_first_fwd(const float* in, const float* w, const float* bias, void*
 }
 
 long long bcp_conv_first_wgrad_workspace_floats(int n, int cout, const int* dims, const int* kernel) {
-  const long long total = (long long)n * dims[0] * dims[1] * dims[2];
-  return ((total + FIRST_WG_CHUNK - 1) / FIRST_WG_CHUNK) * ((cout + 7) / 8) * kernel[0] * 72;
+  const long long chunks = (long long)n * ((dims[2] + 31) / 32) * ((dims[0] + FIRST_WG_XC - 1) / FIRST_WG_XC);
+  return chunks * ((cout + 7) / 8) * kernel[0] * 72;
 }
 
 int bcp_conv_first_wgrad(const float* in, const void* outgrad, float* dw, float* workspace, int n, int cout,
@@ -592,11 +634,11 @@ int bcp_conv_first_wgrad(const float* in, const void* outgrad, float* dw, float*
   const int pad[3] = {kernel[0] / 2, kernel[1] / 2, kernel[2] / 2};
   Geom g;
   BCP_REQUIRE(make_geom(g, n, dims, kernel, stride, pad, 0) == 0, "conv_first_wgrad: bad geometry");
-  BCP_REQUIRE(g.ky <= 3 && g.kz <= 3, "conv_first_wgrad: kernel too large");
+  BCP_REQUIRE(g.ky == 3 && g.kz == 3 && (g.kx == 1 || g.kx == 3), "conv_first_wgrad: kernel must be 3x3x3 or 1x3x3");
   const int Cob = (cout + 7) / 8;
-  const long long total = (long long)n * g.Xo * g.Yo * g.Zo;
-  const int chunks = (int)((total + FIRST_WG_CHUNK - 1) / FIRST_WG_CHUNK);
-  dim3 grid(chunks, Cob, g.kx);
+  const int per_n = ((g.Zo + 31) / 32) * ((g.Xo + FIRST_WG_XC - 1) / FIRST_WG_XC);
+  const int chunks = per_n * n;
+  dim3 grid(per_n, n, Cob * g.kx);
   conv_first_wgrad_partial_kernel<<<grid, 128, 0, stream>>>(in, (const uint4*)outgrad, workspace, g, cout);
   const int T = g.kx * g.ky * g.kz;
   conv_first_wgrad_finalize_kernel<<<(cout * T + 127) / 128, 128, 0, stream>>>(workspace, dw, chunks, cout, g.kx, g.ky, g.kz, accumulate);

@@ -159,55 +159,46 @@ __global__ void ema_i64_kernel(long long* __restrict__ e, const long long* __res
 //   kind 3: [A/8][T][B][8]  inner = A index            -- stride-2 "scatter" operand of the tcgen05 kernel
 // Channel counts that are not multiples of 8 are zero-padded in the blocked dimension.
 // ------------------------------------------------------------------------------------------
-__global__ void repack_kernel(const float* __restrict__ arena, __nv_bfloat16* __restrict__ packed,
-                              const bcp_repack_job* __restrict__ jobs, int njobs) {
+__global__ void __launch_bounds__(128) repack_kernel(const float* __restrict__ arena, __nv_bfloat16* __restrict__ packed,
+                                                     const bcp_repack_job* __restrict__ jobs, int njobs) {
+  // One 8(a) x 8(b) x T tile of the PyTorch-layout weight [A][B][T] per iteration: read as eight contiguous runs of
+  // 8*T floats, staged in shared memory, written as T runs of 64 bf16 (128 bytes) -- both sides coalesced.
+  //   kind 0: dst [T][ceil(B/8)][A][8]  (inner = b)          kind 3: dst [ceil(A/8)][T][B][8]  (inner = a)
+  //   kind 1/2: dst [T][ceil(A/8)][B][8] (inner = a), kind 1 flips the taps
+  __shared__ float tile[64 * 27];
   for (int j = blockIdx.y; j < njobs; j += gridDim.y) {
     const bcp_repack_job job = jobs[j];
     const float* src = arena + job.src_off;
     __nv_bfloat16* dst = packed + job.dst_off;
     const int A = job.dim_a, B = job.dim_b, T = job.taps;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    if (job.kind == 0) {
-      // dst [T][ceil(B/8)][A][8] with inner = B index; src [A][B][T]
-      const int Bb = (B + 7) / 8;
-      const long long total = (long long)T * Bb * A * 8;
-      for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        long long r = i;
-        const int b8 = (int)(r % 8); r /= 8;
-        const int a = (int)(r % A); r /= A;
-        const int bb = (int)(r % Bb); r /= Bb;
-        const int t = (int)r;
-        const int b = bb * 8 + b8;
-        const float v = (b < B) ? src[((long long)a * B + b) * T + t] : 0.f;
-        dst[i] = __float2bfloat16_rn(v);
+    const int Ab = (A + 7) / 8, Bb = (B + 7) / 8;
+    const int n64 = 64 * T;
+    for (int tl = blockIdx.x; tl < Ab * Bb; tl += gridDim.x) {
+      const int ab = tl / Bb, bb = tl - ab * Bb;
+      __syncthreads();
+      for (int i = threadIdx.x; i < n64; i += 128) {
+        const int pair = i / T, t = i - pair * T;
+        const int a = ab * 8 + (pair >> 3), b = bb * 8 + (pair & 7);
+        tile[i] = (a < A && b < B) ? src[((long long)a * B + b) * T + t] : 0.f;
       }
-    } else if (job.kind == 3) {
-      // dst [ceil(A/8)][T][B][8] with inner = A index; src [A][B][T]
-      const int Ab = (A + 7) / 8;
-      const long long total = (long long)Ab * T * B * 8;
-      for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        long long r = i;
-        const int a8 = (int)(r % 8); r /= 8;
-        const int b = (int)(r % B); r /= B;
-        const int t = (int)(r % T); r /= T;
-        const int a = (int)r * 8 + a8;
-        const float v = (a < A) ? src[((long long)a * B + b) * T + t] : 0.f;
-        dst[i] = __float2bfloat16_rn(v);
-      }
-    } else {
-      // kind 1 / 2: dst [T][ceil(A/8)][B][8] with inner = A index; src [A][B][T]; kind 1 flips taps
-      const int Ab = (A + 7) / 8;
-      const long long total = (long long)T * Ab * B * 8;
-      for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        long long r = i;
-        const int a8 = (int)(r % 8); r /= 8;
-        const int b = (int)(r % B); r /= B;
-        const int ab = (int)(r % Ab); r /= Ab;
-        const int t = (int)r;
-        const int a = ab * 8 + a8;
-        const int ts = (job.kind == 1) ? (T - 1 - t) : t;
-        const float v = (a < A) ? src[((long long)a * B + b) * T + ts] : 0.f;
-        dst[i] = __float2bfloat16_rn(v);
+      __syncthreads();
+      for (int i = threadIdx.x; i < n64; i += 128) {
+        const int t = i >> 6, r = i & 63;
+        long long o;
+        float v;
+        if (job.kind == 0) {                       // r = a_local * 8 + b8
+          v = tile[r * T + t];
+          o = (((long long)t * Bb + bb) * A + ab * 8 + (r >> 3)) * 8 + (r & 7);
+          if (ab * 8 + (r >> 3) >= A) continue;
+        } else {                                   // r = b_local * 8 + a8
+          const int bl = r >> 3, a8 = r & 7;
+          if (bb * 8 + bl >= B) continue;
+          const int ts = (job.kind == 1) ? (T - 1 - t) : t;
+          v = tile[(a8 * 8 + bl) * T + ts];
+          if (job.kind == 3) o = (((long long)ab * T + t) * B + bb * 8 + bl) * 8 + a8;
+          else o = (((long long)t * Ab + ab) * B + bb * 8 + bl) * 8 + a8;
+        }
+        dst[o] = __float2bfloat16_rn(v);
       }
     }
   }
@@ -327,8 +318,10 @@ int bcp_ema_i64(long long* ema, const long long* model, int n, float alpha, floa
 int bcp_weights_repack(const float* arena, void* packed, const bcp_repack_job* jobs_dev, int njobs,
                        cudaStream_t stream) {
   BCP_REQUIRE(arena && packed && jobs_dev && njobs > 0, "weights_repack: bad args");
-  dim3 grid(32, njobs < 512 ? njobs : 512);
-  repack_kernel<<<grid, 256, 0, stream>>>(arena, (__nv_bfloat16*)packed, jobs_dev, njobs);
+  // x covers the 8x8 tiles of the largest layers (256x256 -> 1024 tiles) in a few iterations; blocks beyond a small
+  // layer's tile count exit at once
+  dim3 grid(256, njobs < 512 ? njobs : 512);
+  repack_kernel<<<grid, 128, 0, stream>>>(arena, (__nv_bfloat16*)packed, jobs_dev, njobs);
   return check_launch("weights_repack");
 }
 

@@ -24,14 +24,43 @@ __device__ void bn_finalize_block(const float* __restrict__ partial, const float
   const int G = N / spg;
   if (threadIdx.x == 0 && nbt != nullptr) nbt[0] += G;
   const double M = (double)spg * (double)S;
+  // Layers with many partials per (group, channel) first reduce them cooperatively: one warp per pair, lanes split the
+  // (sample, chunk) list in a fixed pattern and a fixed butterfly combines them.  The double-precision mean / variance /
+  // running-statistics chain then runs one channel per THREAD (a dependent chain of FP64 div/sqrt per warp is slow).
+  __shared__ double sm_s[256], sm_q[256];
+  const int per_group = spg * chunks;
+  const bool coop = per_group > 32 && G * C <= 256;
+  if (coop) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int pair = warp; pair < G * C; pair += nwarps) {
+      const int g = pair / C, c = pair - g * C, cb = c >> 3, k = c & 7;
+      double s = 0.0, q = 0.0;
+      for (int e = lane; e < per_group; e += 32) {
+        const int n = g * spg + e / chunks, ch = e - (e / chunks) * chunks;
+        const float* p = partial + (((long long)n * Cb + cb) * chunks + ch) * 16;
+        s += (double)p[k];
+        q += (double)p[8 + k];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+      }
+      if (lane == 0) { sm_s[pair] = s; sm_q[pair] = q; }
+    }
+  }
+  __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int cb = c >> 3, k = c & 7;
     float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 0.f;
     for (int g = 0; g < G; ++g) {
       double s = 0.0, q = 0.0;
-      for (int n = g * spg; n < (g + 1) * spg; ++n) {
-        const float* p = partial + ((long long)n * Cb + cb) * chunks * 16;
-        for (int ch = 0; ch < chunks; ++ch) { s += (double)p[ch * 16 + k]; q += (double)p[ch * 16 + 8 + k]; }
+      if (coop) { s = sm_s[g * C + c]; q = sm_q[g * C + c]; }
+      else {
+        for (int n = g * spg; n < (g + 1) * spg; ++n) {
+          const float* p = partial + ((long long)n * Cb + cb) * chunks * 16;
+          for (int ch = 0; ch < chunks; ++ch) { s += (double)p[ch * 16 + k]; q += (double)p[ch * 16 + 8 + k]; }
+        }
       }
       const double mean = s / M;
       double var = q / M - mean * mean;
@@ -85,7 +114,20 @@ __global__ void __launch_bounds__(NT) bn_stats_kernel(const uint4* __restrict__ 
   float acc[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) acc[k] = 0.f;
-  for (long long s = s0 + threadIdx.x; s < s1; s += NT) {
+  long long s = s0 + threadIdx.x;
+  for (; s + 3 * NT < s1; s += 4 * NT) {          // four independent 16-byte loads in flight per thread
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = ldg_nc_u4(base + s + u * NT);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      unpack8(v[u], f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { acc[k] += f[k]; acc[8 + k] += f[k] * f[k]; }
+    }
+  }
+  for (; s < s1; s += NT) {
     float f[8];
     unpack8(ldg_nc_u4(base + s), f);
 #pragma unroll
@@ -100,6 +142,63 @@ __global__ void __launch_bounds__(NT) bn_stats_kernel(const uint4* __restrict__ 
   }
   if (last_block_arrives(counter))
     bn_finalize_block(partial, gamma, beta, running_mean, running_var, nbt, stat, coef, N, C, S, chunks, spg, eps, momentum);
+}
+
+// Tiny layers (N*S <= SMALL_LIMIT voxels): ONE block per channel octet walks all samples and finishes the statistics
+// itself -- no partial buffer, no grid-wide arrival counter (their fixed cost dominated the deep layers).
+constexpr long long SMALL_LIMIT = 2048;     // beyond this the C/8 blocks of the single-launch path are latency-bound
+__global__ void __launch_bounds__(NT) bn_stats_small_kernel(const uint4* __restrict__ y, long long S,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                             long long* __restrict__ nbt, float* __restrict__ stat,
+                                                             float* __restrict__ coef, int N, int C, int spg, float eps, float momentum) {
+  const int cb = blockIdx.x, Cb = gridDim.x, G = N / spg;
+  __shared__ float red[16 * (NT / 32)];
+  __shared__ float tot[16];
+  if (blockIdx.x == 0 && threadIdx.x == 0 && nbt != nullptr) nbt[0] += G;
+  const double M = (double)spg * (double)S;
+  const int c = cb * 8 + (int)threadIdx.x;
+  const bool owner = threadIdx.x < 8 && c < C;
+  float rm = (owner && running_mean) ? running_mean[c] : 0.f, rv = (owner && running_var) ? running_var[c] : 0.f;
+  for (int g = 0; g < G; ++g) {
+    float acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+    const long long total = (long long)spg * S;
+    for (long long i = threadIdx.x; i < total; i += NT) {
+      const int n = g * spg + (int)(i / S);
+      const long long sp = i - (i / S) * S;
+      float f[8];
+      unpack8(ldg_nc_u4(y + ((long long)n * Cb + cb) * S + sp), f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { acc[k] += f[k]; acc[8 + k] += f[k] * f[k]; }
+    }
+    block_sum<16, NT>(acc, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) tot[k] = acc[k];
+    }
+    __syncthreads();
+    if (owner) {
+      const double mean = (double)tot[threadIdx.x] / M;
+      double var = (double)tot[8 + threadIdx.x] / M - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+      const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+      const float scale = ga * invstd;
+      stat[((long long)g * C + c) * 2 + 0] = (float)mean;
+      stat[((long long)g * C + c) * 2 + 1] = invstd;
+      coef[((long long)g * C + c) * 2 + 0] = scale;
+      coef[((long long)g * C + c) * 2 + 1] = be - (float)mean * scale;
+      if (running_mean) {
+        const double unbiased = (M > 1.0) ? var * M / (M - 1.0) : var;
+        rm = (1.f - momentum) * rm + momentum * (float)mean;
+        rv = (1.f - momentum) * rv + momentum * (float)unbiased;
+      }
+    }
+    __syncthreads();
+  }
+  if (owner && running_mean) { running_mean[c] = rm; running_var[c] = rv; }
 }
 
 // eval-mode coefficients from running statistics
@@ -194,12 +293,11 @@ __global__ void __launch_bounds__(NT) bn_bwd_reduce_kernel(const uint4* __restri
   float acc[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) acc[k] = 0.f;
-  for (long long s = s0 + threadIdx.x; s < s1; s += NT) {
+  auto accumulate_one = [&](const uint4& vy, const uint4& vd, const uint2& kp) {
     float fy[8], fd[8];
-    unpack8(ldg_nc_u4(y + plane + s), fy);
-    unpack8(ldg_nc_u4(da + plane + s), fd);
-    unsigned char kb[8];
-    if (elem_keep) *reinterpret_cast<uint2*>(kb) = *reinterpret_cast<const uint2*>(elem_keep + (plane + s) * 8);
+    unpack8(vy, fy);
+    unpack8(vd, fd);
+    const unsigned char* kb = reinterpret_cast<const unsigned char*>(&kp);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float pre = fy[k] * sc[k] + sh[k];
@@ -209,6 +307,23 @@ __global__ void __launch_bounds__(NT) bn_bwd_reduce_kernel(const uint4* __restri
       acc[k] += gk;
       acc[8 + k] += gk * ((fy[k] - mu[k]) * is[k]);
     }
+  };
+  long long s = s0 + threadIdx.x;
+  for (; s + NT < s1; s += 2 * NT) {               // two voxels = four independent 16-byte loads in flight per thread
+    const uint4 y0 = ldg_nc_u4(y + plane + s), y1 = ldg_nc_u4(y + plane + s + NT);
+    const uint4 d0 = ldg_nc_u4(da + plane + s), d1 = ldg_nc_u4(da + plane + s + NT);
+    uint2 k0 = make_uint2(0, 0), k1 = make_uint2(0, 0);
+    if (elem_keep) {
+      k0 = *reinterpret_cast<const uint2*>(elem_keep + (plane + s) * 8);
+      k1 = *reinterpret_cast<const uint2*>(elem_keep + (plane + s + NT) * 8);
+    }
+    accumulate_one(y0, d0, k0);
+    accumulate_one(y1, d1, k1);
+  }
+  for (; s < s1; s += NT) {
+    uint2 k0 = make_uint2(0, 0);
+    if (elem_keep) k0 = *reinterpret_cast<const uint2*>(elem_keep + (plane + s) * 8);
+    accumulate_one(ldg_nc_u4(y + plane + s), ldg_nc_u4(da + plane + s), k0);
   }
   __shared__ float red[16 * (NT / 32)];
   block_sum<16, NT>(acc, red);
@@ -226,14 +341,40 @@ __device__ void bn_bwd_finalize_block(const float* __restrict__ partial, float* 
                                       int N, int C, long long S, int chunks, int spg, int accumulate) {
   const int Cb = (C + 7) / 8, G = N / spg;
   const double M = (double)spg * (double)S;
+  __shared__ double sm_a[256], sm_b[256];            // cooperative pre-reduction, see bn_finalize_block
+  const int per_group = spg * chunks;
+  const bool coop = per_group > 32 && G * C <= 256;
+  if (coop) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int pair = warp; pair < G * C; pair += nwarps) {
+      const int g = pair / C, c = pair - g * C, cb = c >> 3, k = c & 7;
+      double a = 0.0, b = 0.0;
+      for (int e = lane; e < per_group; e += 32) {
+        const int n = g * spg + e / chunks, ch = e - (e / chunks) * chunks;
+        const float* p = partial + (((long long)n * Cb + cb) * chunks + ch) * 16;
+        a += (double)p[k];
+        b += (double)p[8 + k];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      if (lane == 0) { sm_a[pair] = a; sm_b[pair] = b; }
+    }
+  }
+  __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int cb = c >> 3, k = c & 7;
     double tg = 0.0, tb = 0.0;
     for (int g = 0; g < G; ++g) {
       double a = 0.0, b = 0.0;
-      for (int n = g * spg; n < (g + 1) * spg; ++n) {
-        const float* p = partial + ((long long)n * Cb + cb) * chunks * 16;
-        for (int ch = 0; ch < chunks; ++ch) { a += (double)p[ch * 16 + k]; b += (double)p[ch * 16 + 8 + k]; }
+      if (coop) { a = sm_a[g * C + c]; b = sm_b[g * C + c]; }
+      else {
+        for (int n = g * spg; n < (g + 1) * spg; ++n) {
+          const float* p = partial + ((long long)n * Cb + cb) * chunks * 16;
+          for (int ch = 0; ch < chunks; ++ch) { a += (double)p[ch * 16 + k]; b += (double)p[ch * 16 + 8 + k]; }
+        }
       }
       sums[((long long)g * C + c) * 2 + 0] = (float)(a / M);
       sums[((long long)g * C + c) * 2 + 1] = (float)(b / M);
@@ -288,6 +429,89 @@ __global__ void __launch_bounds__(NT) bn_bwd_apply_kernel(const uint4* __restric
   }
 }
 
+// Small layers: reduce + apply of the backward in one launch, one block per channel octet (see bn_stats_small_kernel).
+__global__ void __launch_bounds__(NT) bn_bwd_small_kernel(const uint4* __restrict__ da, const uint4* __restrict__ y,
+                                                           uint4* __restrict__ dy, const float* __restrict__ stat,
+                                                           const float* __restrict__ coef, const float* __restrict__ chan_scale,
+                                                           const unsigned char* __restrict__ elem_keep, float elem_scale,
+                                                           float* __restrict__ sums, float* __restrict__ dgamma,
+                                                           float* __restrict__ dbeta, int N, int C, long long S, int spg,
+                                                           float slope, int stats_grad, int reduce, int accumulate) {
+  const int cb = blockIdx.x, Cb = gridDim.x, G = N / spg;
+  __shared__ float red[16 * (NT / 32)];
+  __shared__ float sc[8], sh[8], mu[8], is[8], m1[8], m2[8];
+  const double M = (double)spg * (double)S;
+  const int c = cb * 8 + (int)threadIdx.x;
+  const bool owner = threadIdx.x < 8 && c < C;
+  double tg = 0.0, tb = 0.0;
+  for (int g = 0; g < G; ++g) {
+    __syncthreads();
+    if (threadIdx.x < 8) {
+      sc[threadIdx.x] = owner ? coef[((long long)g * C + c) * 2] : 0.f;
+      sh[threadIdx.x] = owner ? coef[((long long)g * C + c) * 2 + 1] : 0.f;
+      mu[threadIdx.x] = owner ? stat[((long long)g * C + c) * 2] : 0.f;
+      is[threadIdx.x] = owner ? stat[((long long)g * C + c) * 2 + 1] : 0.f;
+      m1[threadIdx.x] = 0.f; m2[threadIdx.x] = 0.f;
+    }
+    __syncthreads();
+    const long long total = (long long)spg * S;
+    auto grad_of = [&](long long i, float* gk, float* xh) {
+      const int n = g * spg + (int)(i / S);
+      const long long off = ((long long)n * Cb + cb) * S + (i - (i / S) * S);
+      float fy[8], fd[8];
+      unpack8(ldg_nc_u4(y + off), fy);
+      unpack8(ldg_nc_u4(da + off), fd);
+      unsigned char kb[8];
+      if (elem_keep) *reinterpret_cast<uint2*>(kb) = *reinterpret_cast<const uint2*>(elem_keep + off * 8);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float pre = fy[k] * sc[k] + sh[k];
+        float v = fd[k] * ((chan_scale && cb * 8 + k < C) ? chan_scale[(long long)n * C + cb * 8 + k] : 1.f);
+        if (elem_keep) v = kb[k] ? v * elem_scale : 0.f;
+        gk[k] = pre > 0.f ? v : v * slope;
+        xh[k] = (fy[k] - mu[k]) * is[k];
+      }
+      return off;
+    };
+    if (reduce) {
+      float acc[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+      for (long long i = threadIdx.x; i < total; i += NT) {
+        float gk[8], xh[8];
+        grad_of(i, gk, xh);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { acc[k] += gk[k]; acc[8 + k] += gk[k] * xh[k]; }
+      }
+      block_sum<16, NT>(acc, red);
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { m1[k] = (float)((double)acc[k] / M); m2[k] = (float)((double)acc[8 + k] / M); }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) red[k] = acc[k];
+      }
+      __syncthreads();
+      if (owner) {
+        sums[((long long)g * C + c) * 2 + 0] = m1[threadIdx.x];
+        sums[((long long)g * C + c) * 2 + 1] = m2[threadIdx.x];
+        tb += (double)red[threadIdx.x];
+        tg += (double)red[8 + threadIdx.x];
+      }
+    }
+    for (long long i = threadIdx.x; i < total; i += NT) {
+      float gk[8], xh[8];
+      const long long off = grad_of(i, gk, xh);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) gk[k] = stats_grad ? sc[k] * (gk[k] - m1[k] - xh[k] * m2[k]) : sc[k] * gk[k];
+      dy[off] = pack8(gk);
+    }
+  }
+  if (owner && reduce) {
+    if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)tg : (float)tg;
+    if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)tb : (float)tb;
+  }
+}
+
 // Reduction grid = chunks x (C/8) x N blocks.  Aim at ~4 blocks per SM so mid-size layers are not latency-bound on a
 // handful of blocks, but keep at least 1024 voxels (16 KB) per block and at most 256 partials per (n, c/8) plane.
 static inline int pick_chunks(long long S, int planes) {
@@ -318,6 +542,11 @@ int bcp_norm_stats(const void* y, const float* gamma, const float* beta, float* 
   BCP_REQUIRE(y && stat && coef && workspace && counter, "norm_stats: null pointer");
   BCP_REQUIRE(n > 0 && c > 0 && s > 0 && spg > 0 && n % spg == 0, "norm_stats: bad shape n=%d spg=%d", n, spg);
   const int Cb = (c + 7) / 8, chunks = pick_chunks(s, n * Cb);
+  if ((long long)n * s <= SMALL_LIMIT) {
+    bn_stats_small_kernel<<<Cb, NT, 0, stream>>>((const uint4*)y, s, gamma, beta, running_mean, running_var, num_batches_tracked,
+                                                  stat, coef, n, c, spg, eps, momentum);
+    return check_launch("norm_stats");
+  }
   dim3 grid(chunks, Cb, n);
   bn_stats_kernel<<<grid, NT, 0, stream>>>((const uint4*)y, workspace, s, chunks, counter, gamma, beta, running_mean, running_var,
                                            num_batches_tracked, stat, coef, n, c, spg, eps, momentum);
@@ -352,6 +581,12 @@ int bcp_norm_bwd(const void* dact, const void* y, void* dy, const float* stat, c
   BCP_REQUIRE(dact && y && dy && stat && coef && sums && workspace && counter, "norm_bwd: null pointer");
   BCP_REQUIRE(n > 0 && c > 0 && s > 0 && spg > 0 && n % spg == 0, "norm_bwd: bad shape");
   const int Cb = (c + 7) / 8, chunks = pick_chunks(s, n * Cb);
+  if ((long long)n * s <= SMALL_LIMIT) {
+    const int reduce = (stats_grad || dgamma || dbeta) ? 1 : 0;
+    bn_bwd_small_kernel<<<Cb, NT, 0, stream>>>((const uint4*)dact, (const uint4*)y, (uint4*)dy, stat, coef, chan_scale, elem_keep,
+                                                elem_scale, sums, dgamma, dbeta, n, c, s, spg, slope, stats_grad, reduce, accumulate);
+    return check_launch("norm_bwd");
+  }
   if (stats_grad || dgamma || dbeta) {
     dim3 grid(chunks, Cb, n);
     bn_bwd_reduce_kernel<<<grid, NT, 0, stream>>>((const uint4*)dact, (const uint4*)y, stat, coef, chan_scale, elem_keep,

@@ -118,7 +118,10 @@ class NetRuntime:
             taps = int(np.prod(w.shape[2:]))
             src = (w.data_ptr() - base) // 4
             views = []
-            for kind in kinds:
+            # a network whose weights never receive gradients (the EMA teacher) never runs the 3x3x3 dgrad, the only user
+            # of the flipped/transposed kind-1 pack (the stride-2 layers' packs serve both directions and stay)
+            use = kinds if w.requires_grad else tuple(k for k in kinds if k != 1)
+            for kind in use:
                 if kind == 0:
                     n = taps * ((b + 7) // 8) * a * 8
                 else:
