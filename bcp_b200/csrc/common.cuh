@@ -83,6 +83,23 @@ __device__ __forceinline__ void block_sum(float (&v)[K], float* smem /* K * THRE
   __syncthreads();
 }
 
+// true in every thread of exactly one block: the last block of the grid to arrive (threadfence-reduction pattern).
+// `counter` must be zero on entry and is reset to zero by the last block => reusable by the next launch on the stream.
+__device__ __forceinline__ bool last_block_arrives(int* counter) {
+  __shared__ int is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int total = gridDim.x * gridDim.y * gridDim.z;
+    const int prev = atomicAdd(counter, 1);
+    is_last = (prev == total - 1);
+    if (is_last) *counter = 0;
+  }
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last != 0;
+}
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 int sm_count();

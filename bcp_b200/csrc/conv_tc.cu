@@ -42,6 +42,21 @@ struct TcParams {
   unsigned slotA_bytes, stageB_bytes;
   unsigned offA, offB, offBar;   // shared-memory carve-up (bytes from the 128B-aligned base)
   int mergedA, mergedB;          // tensor maps use the 8-byte-element "merged inner dimension" form (tma_load_cb8)
+  unsigned reserve, offStats;    // fused-BN-statistics table: bytes kept out of the operand rings / its offset
+};
+
+// Fused train-mode normalisation statistics (conv_tc_kernel<.., true>): the epilogue accumulates per-(group, channel)
+// sum and sum of squares of the bf16-ROUNDED outputs it stores, so the separate pass over y (norm.cu bn_stats_kernel)
+// disappears.  Accumulation is double precision end to end: the statistics do not depend on how bricks were tiled or
+// assigned to CTAs beyond ~1e-16, i.e. batching several reference calls as groups stays reproducible.
+struct StatsArgs {
+  double* partial;               // [gridDim.x][G][Cout][2]
+  int* counter;                  // zero on entry, reset by the last CTA
+  const float* gamma; const float* beta;
+  float* running_mean; float* running_var; long long* nbt;
+  float* stat; float* coef;      // [G][Cout][2]: {mean, invstd}, {scale, shift}
+  int spg, G;
+  float eps, momentum;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -144,10 +159,62 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 
 constexpr int TC_THREADS = 192;
 
-template <bool PROF>
+// one step of the transpose-reduce: NV live values per lane -> NV/2, lanes exchanging with lane ^ OFF.  After the five
+// steps (32,16),(16,8),(8,4),(4,2),(2,1) lane l holds the warp-wide total of value l in acc[0] (fixed order, 31 shuffles).
+template <int NV, int OFF>
+__device__ __forceinline__ void xreduce_step(double (&acc)[32], int lane) {
+  const bool up = (lane & OFF) != 0;
+#pragma unroll
+  for (int i = 0; i < NV / 2; ++i) {
+    const double send = up ? acc[i] : acc[i + NV / 2];
+    const double keep = up ? acc[i + NV / 2] : acc[i];
+    acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+  }
+}
+
+// run by the last CTA of a fused-statistics launch: fixed-order reduce of the per-CTA partials, then the same
+// double-precision mean / variance / running-statistics chain as norm.cu bn_finalize_block
+__device__ void conv_stats_finalize(const StatsArgs& sa, int C, double M, unsigned char* smem) {
+  const int G = sa.G, GC2 = G * C * 2, nct = gridDim.x;
+  double* sc = reinterpret_cast<double*>(smem);          // scratch [G][C][2] in the (now idle) operand slots
+  if (threadIdx.x == 0 && sa.nbt != nullptr) sa.nbt[0] += G;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = warp; i < GC2; i += TC_THREADS / 32) {
+    double v = 0.0;
+    for (int b = lane; b < nct; b += 32) v += sa.partial[(size_t)b * GC2 + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sc[i] = v;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += TC_THREADS) {
+    float rm = sa.running_mean ? sa.running_mean[c] : 0.f, rv = sa.running_var ? sa.running_var[c] : 0.f;
+    for (int g = 0; g < G; ++g) {
+      const double mean = sc[(g * C + c) * 2] / M;
+      double var = sc[(g * C + c) * 2 + 1] / M - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float invstd = (float)(1.0 / sqrt(var + (double)sa.eps));
+      const float ga = sa.gamma ? sa.gamma[c] : 1.f, be = sa.beta ? sa.beta[c] : 0.f;
+      const float scale = ga * invstd;
+      sa.stat[((long long)g * C + c) * 2 + 0] = (float)mean;
+      sa.stat[((long long)g * C + c) * 2 + 1] = invstd;
+      sa.coef[((long long)g * C + c) * 2 + 0] = scale;
+      sa.coef[((long long)g * C + c) * 2 + 1] = be - (float)mean * scale;
+      if (sa.running_mean) {
+        const double unbiased = (M > 1.0) ? var * M / (M - 1.0) : var;
+        rm = (1.f - sa.momentum) * rm + sa.momentum * (float)mean;
+        rv = (1.f - sa.momentum) * rv + sa.momentum * (float)unbiased;
+      }
+    }
+    if (sa.running_mean) { sa.running_mean[c] = rm; sa.running_var[c] = rv; }
+  }
+}
+
+template <bool PROF, bool STATS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_w,
-               const float* __restrict__ bias, uint4* __restrict__ out, const TcParams p, unsigned long long* __restrict__ prof) {
+               const float* __restrict__ bias, uint4* __restrict__ out, const TcParams p, unsigned long long* __restrict__ prof,
+               const StatsArgs sa) {
   // PROF: per-CTA cycle counters for tools/debug_conv_tc.py --prof (never instantiated on the product path)
   long long t_start = 0, w0 = 0, w1 = 0, w2 = 0;
   if (PROF) t_start = clock64();
@@ -173,6 +240,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (STATS) {            // per-epilogue-warp tables [4][G][Cout][2] of doubles
+    double* tbl = reinterpret_cast<double*>(smem + p.offStats);
+    for (int i = threadIdx.x; i < 4 * sa.G * p.Cout * 2; i += TC_THREADS) tbl[i] = 0.0;
   }
   tc_fence_before();
   __syncthreads();
@@ -298,6 +369,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       { long long t0 = PROF ? clock64() : 0; mbar_wait(tmem_full + 8 * as, ap); if (PROF) { t_e0 = clock64(); w0 += t_e0 - t0; } }
       tc_fence_after();
       const uint32_t d0 = tmem_base + as * (uint32_t)(p.MT * p.Ns) + ((uint32_t)(q * 32) << 16);
+      if (STATS) {
+        // channel-group outer, tile inner: 32 double accumulators live per thread; one transpose-reduce per (item, group)
+        double* tbl = reinterpret_cast<double*>(smem + p.offStats) + (size_t)q * sa.G * p.Cout * 2;
+        const int g = n / sa.spg;
+        for (int c16 = 0; c16 < p.Ns; c16 += 16) {
+          double acc[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) acc[k] = 0.0;
+          for (int mt = 0; mt < p.MT; ++mt) {
+            const int L = mt * 128 + q * 32 + lane;
+            const int iz = L % p.HZ;
+            const int ry = L / p.HZ;
+            const int iy = ry % p.HY, ix = ry / p.HY;
+            const int x = bx * p.BX + ix, y = by * p.BY + iy, z = bz * p.BZ + iz;
+            const bool valid = (ix < p.BX) && (iy < p.BY) && (iz < p.BZ) && (x < p.X) && (y < p.Y) && (z < p.Z);
+            const long long sp = ((long long)x * p.Y + y) * p.Z + z;
+            uint32_t v[16];
+            tmem_ld16(d0 + (uint32_t)(mt * p.Ns + c16), v);
+            tmem_ld_wait();
+            if (valid) {
+              float f[16];
+#pragma unroll
+              for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v[k]) + (bias ? __ldg(bias + n0 + c16 + k) : 0.f);
+              const uint4 p0 = pack8(f), p1 = pack8(f + 8);
+              uint4* dst = out + ((long long)n * Cob + ((n0 + c16) >> 3)) * S + sp;
+              dst[0] = p0;
+              dst[S] = p1;
+              unpack8(p0, f);                    // the statistics are those of the stored (bf16-rounded) tensor
+              unpack8(p1, f + 8);
+#pragma unroll
+              for (int k = 0; k < 16; ++k) { const double d = (double)f[k]; acc[k] += d; acc[16 + k] += d * d; }
+            }
+          }
+          xreduce_step<32, 16>(acc, lane);
+          xreduce_step<16, 8>(acc, lane);
+          xreduce_step<8, 4>(acc, lane);
+          xreduce_step<4, 2>(acc, lane);
+          xreduce_step<2, 1>(acc, lane);
+          tbl[((size_t)g * p.Cout + n0 + c16 + (lane & 15)) * 2 + (lane >> 4)] += acc[0];
+        }
+      } else {
       for (int mt = 0; mt < p.MT; ++mt) {
         const int L = mt * 128 + q * 32 + lane;
         const int iz = L % p.HZ;
@@ -320,6 +432,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           }
         }
       }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty + 8 * as);
@@ -333,6 +446,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   if (PROF && threadIdx.x == 0) prof[blockIdx.x * 16 + 0] = clock64() - t_start;
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+  if (STATS) {
+    // this CTA's totals (the four epilogue warps' tables, fixed order) -> global; the last CTA to arrive finalises
+    const int GC2 = sa.G * p.Cout * 2;
+    const double* t0 = reinterpret_cast<const double*>(smem + p.offStats);
+    for (int i = threadIdx.x; i < GC2; i += TC_THREADS)
+      sa.partial[(size_t)blockIdx.x * GC2 + i] = ((t0[i] + t0[GC2 + i]) + t0[2 * GC2 + i]) + t0[3 * GC2 + i];
+    if (last_block_arrives(sa.counter))
+      conv_stats_finalize(sa, p.Cout, (double)sa.spg * (double)p.X * (double)p.Y * (double)p.Z, smem);
   }
 }
 
@@ -843,13 +965,13 @@ static bool plan(TcParams& p, int nsm) {
           // depth hides the L2 latency of the cp.async.bulk stream (3..8 stages)
           int TG = T;
           unsigned stageB = (unsigned)TG * (unsigned)Ns * 32u;
-          if ((long long)SMEM_BUDGET - 1024 - 2 * slotA < 2ll * stageB) { TG = 9; stageB = 9u * (unsigned)Ns * 32u; }
+          if ((long long)SMEM_BUDGET - (long long)p.reserve - 1024 - 2 * slotA < 2ll * stageB) { TG = 9; stageB = 9u * (unsigned)Ns * 32u; }
           const int sb_min = (TG == T) ? 2 : 3;
-          long long avail = (long long)SMEM_BUDGET - 1024 - (long long)sb_min * stageB;
+          long long avail = (long long)SMEM_BUDGET - (long long)p.reserve - 1024 - (long long)sb_min * stageB;
           int SA = (int)(avail / slotA);
           if (SA < 2) break;
           if (SA > 3) SA = 3;
-          int SB = (int)(((long long)SMEM_BUDGET - 1024 - (long long)SA * slotA) / stageB);
+          int SB = (int)(((long long)SMEM_BUDGET - (long long)p.reserve - 1024 - (long long)SA * slotA) / stageB);
           if (SB > 8) SB = 8;
           if (SB < sb_min) SB = sb_min;
           const int nbx = (p.X + BX - 1) / BX, nby = (p.Y + BY - 1) / BY, nbz = (p.Z + BZ - 1) / BZ;
@@ -890,8 +1012,8 @@ static bool plan(TcParams& p, int nsm) {
 }
 
 struct PlanKey {
-  int v[7];
-  bool operator==(const PlanKey& o) const { for (int i = 0; i < 7; ++i) if (v[i] != o.v[i]) return false; return true; }
+  int v[8];
+  bool operator==(const PlanKey& o) const { for (int i = 0; i < 8; ++i) if (v[i] != o.v[i]) return false; return true; }
 };
 // immutable plans memoised per shape (pure function of the key; guarded by a mutex)
 static bool plan_cached(TcParams& p, int nsm) {
@@ -899,7 +1021,7 @@ static bool plan_cached(TcParams& p, int nsm) {
   static PlanKey keys[256];
   static TcParams vals[256];
   static int count = 0;
-  const PlanKey k = {{p.N, p.X, p.Y, p.Z, p.Cin, p.Cout, p.kx}};
+  const PlanKey k = {{p.N, p.X, p.Y, p.Z, p.Cin, p.Cout, p.kx, (int)p.reserve}};
   {
     std::lock_guard<std::mutex> g(mu);
     for (int i = 0; i < count; ++i) if (keys[i] == k) { p = vals[i]; return true; }
@@ -1083,14 +1205,25 @@ static unsigned long long* g_tc_prof = nullptr;
 // debug only (tools/debug_conv_tc.py --prof): 16 counters per CTA, see conv_tc_kernel<true>
 int bcp_conv_tc_debug_profile(void* buffer) { g_tc_prof = (unsigned long long*)buffer; return BCP_OK; }
 
-int bcp_conv_tc_fwd(const void* in, const void* wpack, const float* bias, void* out, int n, int cin, int cout,
-                    const int* dims, const int* kernel, cudaStream_t stream) {
+// fused-statistics eligibility: big layers only (on the deep ones the standalone statistics launch is a few microseconds
+// and the per-CTA partial reduce would cost as much), table of 4 x G x Cout x 2 doubles <= 16 KB
+static unsigned stats_table_bytes(int n, int cout, const int* dims, int spg) {
+  if (spg <= 0 || n % spg) return 0;
+  const long long S = (long long)dims[0] * dims[1] * dims[2];
+  const int G = n / spg;
+  if (S < 8192 || G * cout > 128) return 0;
+  return (unsigned)(4 * G * cout * 2 * sizeof(double));
+}
+
+static int conv_tc_launch(const void* in, const void* wpack, const float* bias, void* out, int n, int cin, int cout,
+                          const int* dims, const int* kernel, const StatsArgs* sa, cudaStream_t stream) {
   BCP_REQUIRE(in && wpack && out && dims && kernel, "conv_tc_fwd: null pointer");
   if (!shape_ok(cin, cout, dims, kernel)) { set_last_error("conv_tc_fwd: unsupported shape cin=%d cout=%d", cin, cout); return BCP_ERR_UNSUPPORTED; }
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_last_error("conv_tc_fwd: cuTensorMapEncodeTiled unavailable"); return BCP_ERR_CUDA; }
   TcParams p{};
   p.N = n; p.X = dims[0]; p.Y = dims[1]; p.Z = dims[2]; p.Cin = cin; p.Cout = cout; p.kx = kernel[0];
+  p.reserve = sa ? stats_table_bytes(n, cout, dims, sa->spg) + 128 : 0;
   const int nsm = sm_count();
   if (!plan_cached(p, nsm)) { set_last_error("conv_tc_fwd: no brick shape fits shared memory / TMEM"); return BCP_ERR_UNSUPPORTED; }
 
@@ -1120,17 +1253,55 @@ int bcp_conv_tc_fwd(const void* in, const void* wpack, const float* bias, void* 
     }
     if (cw != CUDA_SUCCESS) { set_last_error("conv_tc_fwd: weight tensor map failed (%d)", (int)cw); return BCP_ERR_CUDA; }
   }
-  const size_t smem = (size_t)p.offBar + 8 * (2 * p.SA + 2 * p.SB + 2 * p.AS) + 16 + 128;
+  size_t smem = (size_t)p.offBar + 8 * (2 * p.SA + 2 * p.SB + 2 * p.AS) + 16 + 128;
+  if (sa) {
+    p.offStats = (unsigned)((p.offBar + 8 * (2 * p.SA + 2 * p.SB + 2 * p.AS) + 16 + 127) / 128 * 128);
+    smem = (size_t)p.offStats + (p.reserve - 128) + 128;
+  }
+  BCP_REQUIRE(smem <= 227 * 1024, "conv_tc_fwd: shared memory plan overflow (%zu bytes)", smem);
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   const int nitems = p.nbricks * p.NS;
   const int grid = nitems < nsm ? nitems : nsm;
-  if (g_tc_prof) conv_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(tmap, tmap_w, bias, (uint4*)out, p, g_tc_prof);
-  else conv_tc_kernel<false><<<grid, TC_THREADS, smem, stream>>>(tmap, tmap_w, bias, (uint4*)out, p, nullptr);
+  if (sa) conv_tc_kernel<false, true><<<grid, TC_THREADS, smem, stream>>>(tmap, tmap_w, bias, (uint4*)out, p, nullptr, *sa);
+  else if (g_tc_prof) conv_tc_kernel<true, false><<<grid, TC_THREADS, smem, stream>>>(tmap, tmap_w, bias, (uint4*)out, p, g_tc_prof, StatsArgs{});
+  else conv_tc_kernel<false, false><<<grid, TC_THREADS, smem, stream>>>(tmap, tmap_w, bias, (uint4*)out, p, nullptr, StatsArgs{});
   return check_launch("conv_tc_fwd");
+}
+
+int bcp_conv_tc_fwd(const void* in, const void* wpack, const float* bias, void* out, int n, int cin, int cout,
+                    const int* dims, const int* kernel, cudaStream_t stream) {
+  return conv_tc_launch(in, wpack, bias, out, n, cin, cout, dims, kernel, nullptr, stream);
+}
+
+long long bcp_conv_tc_stats_workspace_bytes(int n, int cin, int cout, const int* dims, const int* kernel, int spg) {
+  if (!dims || !kernel || !shape_ok(cin, cout, dims, kernel) || get_encode() == nullptr) return 0;
+  static const bool off = getenv("BCP_NO_FUSED_STATS") != nullptr;
+  if (off) return 0;
+  const unsigned tb = stats_table_bytes(n, cout, dims, spg);
+  if (!tb) return 0;
+  TcParams p{};
+  p.N = n; p.X = dims[0]; p.Y = dims[1]; p.Z = dims[2]; p.Cin = cin; p.Cout = cout; p.kx = kernel[0];
+  p.reserve = tb + 128;
+  if (!plan_cached(p, sm_count())) return 0;
+  return (long long)sm_count() * (n / spg) * cout * 2 * (long long)sizeof(double);
+}
+
+int bcp_conv_tc_fwd_stats(const void* in, const void* wpack, const float* bias, void* out, int n, int cin, int cout,
+                          const int* dims, const int* kernel, const float* gamma, const float* beta, float* running_mean,
+                          float* running_var, long long* num_batches_tracked, float* stat, float* coef, void* workspace,
+                          int* counter, int spg, float eps, float momentum, cudaStream_t stream) {
+  BCP_REQUIRE(stat && coef && workspace && counter && dims, "conv_tc_fwd_stats: null pointer");
+  if (!stats_table_bytes(n, cout, dims, spg)) { set_last_error("conv_tc_fwd_stats: layer not eligible for fused statistics"); return BCP_ERR_UNSUPPORTED; }
+  StatsArgs sa{};
+  sa.partial = (double*)workspace; sa.counter = counter; sa.gamma = gamma; sa.beta = beta;
+  sa.running_mean = running_mean; sa.running_var = running_var; sa.nbt = num_batches_tracked;
+  sa.stat = stat; sa.coef = coef; sa.spg = spg; sa.G = n / spg; sa.eps = eps; sa.momentum = momentum;
+  return conv_tc_launch(in, wpack, bias, out, n, cin, cout, dims, kernel, &sa, stream);
 }
 
 int bcp_conv_tc_wgrad_supported(int cin, int cout, const int* dims, const int* kernel) {

@@ -82,23 +82,6 @@ __device__ void bn_finalize_block(const float* __restrict__ partial, const float
   }
 }
 
-// true in every thread of exactly one block: the last block of the grid to arrive (threadfence-reduction pattern).
-// `counter` must be zero on entry and is reset to zero by the last block => reusable by the next launch on the stream.
-__device__ __forceinline__ bool last_block_arrives(int* counter) {
-  __shared__ int is_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const int total = gridDim.x * gridDim.y * gridDim.z;
-    const int prev = atomicAdd(counter, 1);
-    is_last = (prev == total - 1);
-    if (is_last) *counter = 0;
-  }
-  __syncthreads();
-  if (is_last) __threadfence();
-  return is_last != 0;
-}
-
 // partial[((n*Cb + cb)*chunks + chunk)*16 + {0..7: sum, 8..15: sumsq}]; the last block finalises
 __global__ void __launch_bounds__(NT) bn_stats_kernel(const uint4* __restrict__ y, float* __restrict__ partial,
                                                        long long S, int chunks, int* __restrict__ counter,

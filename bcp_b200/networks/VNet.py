@@ -62,7 +62,20 @@ class _Stage3d(nn.Module):
             else:
                 rt.register_conv(conv, (0, 2, 3))
 
-    def _norm_act(self, y, norm, chan_scale=None, residual=None):
+    def _stats_req(self, norm, n):
+        """Description of the batch-statistic normalisation that follows a conv, for the fused-statistics epilogue."""
+        if norm is None or isinstance(norm, nn.GroupNorm):
+            return None
+        if isinstance(norm, nn.BatchNorm3d):
+            if not (norm.training or not norm.track_running_stats):
+                return None
+            return dict(gamma=norm.weight, beta=norm.bias, running_mean=norm.running_mean, running_var=norm.running_var,
+                        nbt=norm.num_batches_tracked, spg=self._rt.spg or n, eps=norm.eps,
+                        momentum=norm.momentum if norm.momentum is not None else 0.1)
+        return dict(gamma=norm.weight, beta=norm.bias, running_mean=None, running_var=None, nbt=None, spg=1, eps=norm.eps,
+                    momentum=0.0)
+
+    def _norm_act(self, y, norm, chan_scale=None, residual=None, precomputed=None):
         rt = self._rt
         n = y.shape[0]
         if norm is None:
@@ -75,12 +88,13 @@ class _Stage3d(nn.Module):
                 spg = rt.spg or n
                 mom = norm.momentum if norm.momentum is not None else 0.1
                 return ops.NormAct.apply(y, norm.weight, norm.bias, norm.running_mean, norm.running_var,
-                                         norm.num_batches_tracked, "batch", spg, norm.eps, mom, 0.0, chan_scale, None, 1.0, residual)
+                                         norm.num_batches_tracked, "batch", spg, norm.eps, mom, 0.0, chan_scale, None, 1.0, residual,
+                                         precomputed)
             return ops.NormAct.apply(y, norm.weight, norm.bias, norm.running_mean, norm.running_var, None, "eval", n,
                                      norm.eps, 0.0, 0.0, chan_scale, None, 1.0, residual)
         # InstanceNorm3d(affine=False, track_running_stats=False): per-sample statistics in train and eval
         return ops.NormAct.apply(y, norm.weight, norm.bias, None, None, None, "batch", 1, norm.eps, 0.0, 0.0, chan_scale,
-                                 None, 1.0, residual)
+                                 None, 1.0, residual, precomputed)
 
     def forward(self, a, chan_scale=None, residual=None):
         """a: CB8 activation, or the planar fp32 network input for the first block.
@@ -90,6 +104,7 @@ class _Stage3d(nn.Module):
             conv = self.conv[i * self._per]
             norm = self.conv[i * self._per + 1] if self._per == 3 else None
             last = i == self._n - 1
+            req = None
             # a conv that feeds batch-statistic normalisation has an identically-zero bias gradient (ops._bias_grad)
             bz = norm is not None and not isinstance(norm, nn.GroupNorm) and (
                 not isinstance(norm, nn.BatchNorm3d) or norm.training or not norm.track_running_stats)
@@ -100,12 +115,14 @@ class _Stage3d(nn.Module):
                     else:
                         raise NotImplementedError("first layer with n_channels != 1")
                 else:
-                    y = ops.ConvSame.apply(a, conv.weight, conv.bias, rt.pack(conv), (3, 3, 3), bz)
+                    req = self._stats_req(norm, a.shape[0])
+                    y = ops.ConvSame.apply(a, conv.weight, conv.bias, rt.pack(conv), (3, 3, 3), bz, req)
             elif self.kind == "down":
                 y = ops.ConvDown2.apply(a, conv.weight, conv.bias, rt.pack(conv), bz)
             else:
                 y = ops.ConvUp2.apply(a, conv.weight, conv.bias, rt.pack(conv), bz)
-            a = self._norm_act(y, norm, chan_scale if last else None, residual if last else None)
+            a = self._norm_act(y, norm, chan_scale if last else None, residual if last else None,
+                               req.get("out") if req else None)
         return a
 
 

@@ -31,13 +31,21 @@ class ConvBlock(nn.Module):
             conv = self.conv_conv[i]
             rt.register_conv(conv, None if conv.in_channels % 8 else (0, 1))
 
-    def _bn_act(self, y, bn, slope, keep=None, keep_scale=1.0):
+    def _stats_req(self, bn, n):
+        """the batch-statistic BatchNorm that follows a conv, for the fused-statistics conv epilogue (ops.ConvSame)"""
+        if not (bn.training or not bn.track_running_stats):
+            return None
+        return dict(gamma=bn.weight, beta=bn.bias, running_mean=bn.running_mean, running_var=bn.running_var,
+                    nbt=bn.num_batches_tracked, spg=self._rt.spg or n, eps=bn.eps,
+                    momentum=bn.momentum if bn.momentum is not None else 0.1)
+
+    def _bn_act(self, y, bn, slope, keep=None, keep_scale=1.0, precomputed=None):
         rt = self._rt
         n = y.shape[0]
         if bn.training or not bn.track_running_stats:
             mom = bn.momentum if bn.momentum is not None else 0.1
             return ops.NormAct.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked, "batch",
-                                     rt.spg or n, bn.eps, mom, slope, None, keep, keep_scale, None)
+                                     rt.spg or n, bn.eps, mom, slope, None, keep, keep_scale, None, precomputed)
         return ops.NormAct.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, None, "eval", n, bn.eps, 0.0, slope,
                                  None, keep, keep_scale, None)
 
@@ -46,19 +54,22 @@ class ConvBlock(nn.Module):
         c0, bn0, act0, drop, c1, bn1, act1 = self.conv_conv
         bz0 = bn0.training or not bn0.track_running_stats       # batch-stat BN next: bias gradient is identically zero
         bz1 = bn1.training or not bn1.track_running_stats
+        req0 = None
         if a.dtype != torch.bfloat16:
             if c0.in_channels != 1:
                 raise NotImplementedError("first layer with in_chns != 1")
             y = ops.ConvFirst.apply(a, c0.weight, c0.bias, bz0)
         else:
-            y = ops.ConvSame.apply(a, c0.weight, c0.bias, rt.pack(c0), (1, 3, 3), bz0)
+            req0 = self._stats_req(bn0, a.shape[0])
+            y = ops.ConvSame.apply(a, c0.weight, c0.bias, rt.pack(c0), (1, 3, 3), bz0, req0)
         keep, scale = None, 1.0
         if drop.training:
             n, cb, x, yy, z, _ = y.shape
             keep, scale = NetRuntime.element_dropout_keep(drop, n, cb * 8, (x, yy, z), y.device, rt.spg)
-        a = self._bn_act(y, bn0, act0.negative_slope, keep, scale)
-        y = ops.ConvSame.apply(a, c1.weight, c1.bias, rt.pack(c1), (1, 3, 3), bz1)
-        return self._bn_act(y, bn1, act1.negative_slope)
+        a = self._bn_act(y, bn0, act0.negative_slope, keep, scale, req0.get("out") if req0 else None)
+        req1 = self._stats_req(bn1, a.shape[0])
+        y = ops.ConvSame.apply(a, c1.weight, c1.bias, rt.pack(c1), (1, 3, 3), bz1, req1)
+        return self._bn_act(y, bn1, act1.negative_slope, precomputed=req1.get("out") if req1 else None)
 
 
 class DownBlock(nn.Module):

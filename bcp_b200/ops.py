@@ -18,6 +18,7 @@ BF16 = torch.bfloat16
 # debugging switches (kernel selection only -- both settings run hand-written sm_100a kernels)
 _TC_FWD = os.environ.get("BCP_DISABLE_TC", "0") != "1"
 _TC_WGRAD = _TC_FWD and os.environ.get("BCP_DISABLE_TC_WGRAD", "0") != "1"
+_FUSE_STATS = os.environ.get("BCP_NO_FUSED_STATS", "0") != "1"     # conv epilogue produces the following norm's statistics
 
 
 def _require_cuda(t: torch.Tensor, what: str):
@@ -134,6 +135,29 @@ def _conv_same(a, wpack, bias, cout, kernel, allow_tc=True):
     return out
 
 
+def _conv_same_stats(a, wpack, bias, cout, kernel, req):
+    """conv + fused train-mode normalisation statistics (bcp_conv_tc_fwd_stats); None when the layer is not eligible."""
+    n, cin, x, y, z = act_dims(a)
+    dims, k = i3(x, y, z), i3(*kernel)
+    spg = int(req["spg"])
+    if not LIB.query("bcp_conv_tc_supported", cin, cout, dims, k):
+        return None
+    wsb = LIB.query("bcp_conv_tc_stats_workspace_bytes", n, cin, cout, dims, k, spg)
+    if wsb <= 0:
+        return None
+    dev = a.device
+    out = torch.empty(cb8_shape(n, cout, x, y, z), dtype=BF16, device=dev)
+    groups = n // spg
+    stat = torch.empty(groups, cout, 2, dtype=torch.float32, device=dev)
+    coef = torch.empty(groups, cout, 2, dtype=torch.float32, device=dev)
+    ws = torch.empty(wsb // 8, dtype=torch.float64, device=dev)
+    LIB.call("bcp_conv_tc_fwd_stats", ptr(a), ptr(wpack), ptr(bias), ptr(out), n, cin, cout, dims, k, ptr(req["gamma"]),
+             ptr(req["beta"]), ptr(req["running_mean"]), ptr(req["running_var"]), ptr(req["nbt"]), ptr(stat), ptr(coef), ptr(ws),
+             ptr(_counter(dev)), spg, float(req["eps"]), float(req["momentum"]), stream())
+    req["out"] = (stat, coef)
+    return out
+
+
 def _wgrad(inp, outgrad, cin, cout, in_dims, kernel, stride, pad, wshape, allow_tc=True, into=None):
     """Weight gradient [cout][cin][taps].  ``into``: accumulate into this tensor (flat-arena view) and return None."""
     n = inp.shape[0]
@@ -178,13 +202,20 @@ class ConvSame(Function):
     """nn.Conv3d(k=3,p=1) / nn.Conv2d(k=3,p=1 | k=1) on CB8 (networks/VNet.py:17, networks/unet.py:20,24,49)."""
 
     @staticmethod
-    def forward(ctx, a, weight, bias, pack: ConvPack, kernel, bias_grad_is_zero=False):
+    def forward(ctx, a, weight, bias, pack: ConvPack, kernel, bias_grad_is_zero=False, stats_req=None):
+        """stats_req: optional dict(gamma, beta, running_mean, running_var, nbt, spg, eps, momentum) describing the
+        train-mode normalisation that follows; when the layer is eligible the statistics are produced by the conv
+        epilogue and returned as stats_req["out"] = (stat, coef) for NormAct(precomputed=...)."""
         _require_cuda(a, "conv")
         a = a.contiguous()
         cout = weight.shape[0]
         ctx.save_for_backward(a, weight)
         ctx.pack, ctx.kernel, ctx.has_bias, ctx.bz = pack, tuple(kernel), bias is not None, bias_grad_is_zero
         ctx.bias_ref = bias
+        if stats_req is not None and _TC_FWD and _FUSE_STATS:
+            y = _conv_same_stats(a, pack.k[0], bias, cout, kernel, stats_req)
+            if y is not None:
+                return y
         return _conv_same(a, pack.k[0], bias, cout, kernel)
 
     @staticmethod
@@ -201,7 +232,7 @@ class ConvSame(Function):
                         into=_direct(weight))
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = _bias_grad(dy, cout, ctx.bz, _direct(ctx.bias_ref))
-        return da, dw, db, None, None, None
+        return da, dw, db, None, None, None, None
 
 
 def _s2_fwd(inp, pack: ConvPack, bias, cin, cout, half_dims, mode):
@@ -390,7 +421,8 @@ class NormAct(Function):
 
     @staticmethod
     def forward(ctx, y, gamma, beta, running_mean, running_var, nbt, mode, spg, eps, momentum, slope,
-                chan_scale, elem_keep, elem_scale, residual):
+                chan_scale, elem_keep, elem_scale, residual, precomputed=None):
+        """precomputed: (stat, coef) already produced by the convolution's epilogue (ConvSame stats_req) for mode 'batch'."""
         _require_cuda(y, "norm_act")
         y = y.contiguous()
         n, c, x, yy, z = act_dims(y)
@@ -399,9 +431,14 @@ class NormAct(Function):
         if mode != "batch":
             spg = n
         groups = n // spg
-        stat = torch.empty(groups, c, 2, dtype=torch.float32, device=dev)
-        coef = torch.empty(groups, c, 2, dtype=torch.float32, device=dev)
-        if mode == "batch":
+        if mode == "batch" and precomputed is not None:
+            stat, coef = precomputed
+        else:
+            stat = torch.empty(groups, c, 2, dtype=torch.float32, device=dev)
+            coef = torch.empty(groups, c, 2, dtype=torch.float32, device=dev)
+        if mode == "batch" and precomputed is not None:
+            pass
+        elif mode == "batch":
             ws = _f32(LIB.query("bcp_norm_workspace_floats", n, c, s), dev)
             LIB.call("bcp_norm_stats", ptr(y), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), ptr(nbt),
                      ptr(stat), ptr(coef), ptr(ws), ptr(_counter(dev)), n, c, s, spg, float(eps), float(momentum), stream())
@@ -444,7 +481,7 @@ class NormAct(Function):
         if direct:
             dgamma = dbeta = None
         return (dy, dgamma if has_g else None, dbeta if has_b else None, None, None, None, None, None, None, None, None,
-                None, None, None, da if has_res else None)
+                None, None, None, da if has_res else None, None)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -209,9 +209,17 @@ def run_native(args):
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample()
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without tearing the communicator down: destroy_process_group() on a communicator whose all-reduce sits
+        # inside a live CUDA graph never returned on the 2-GPU box (the JSON line had long been printed).  Everything
+        # measured is already reported; synchronise, meet at a barrier, and exit the process directly.
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def conv_roofline(LIB, step_fn):
@@ -229,7 +237,9 @@ def conv_roofline(LIB, step_fn):
             n, cin, cout, dims, kernel = a[4], a[5], a[6], a[7], a[8]
             vox = n * dims[0] * dims[1] * dims[2]
             taps = kernel[0] * kernel[1] * kernel[2]
-            recs.append((name, e0, e1, 2.0 * vox * taps * cin * cout, cin, cout))
+            # algorithmic bytes: both activation tensors once (bf16) + the weights (bf16 pack or fp32 gradient)
+            ab = 2.0 * vox * (cin + cout) + taps * cin * cout * (2.0 if name == "bcp_conv_tc_fwd" else 4.0)
+            recs.append((name, e0, e1, 2.0 * vox * taps * cin * cout, cin, cout, ab))
         else:
             orig(name, *a)
     LIB.call = wrapped
@@ -240,25 +250,51 @@ def conv_roofline(LIB, step_fn):
         LIB.call = orig
     if not recs:
         return None
-    tot_ms = sum(e0.elapsed_time(e1) for _, e0, e1, _, _, _ in recs)
-    tot_fl = sum(f for *_, f, _, _ in recs)
+    tot_ms = sum(r[1].elapsed_time(r[2]) for r in recs)
+    tot_fl = sum(r[3] for r in recs)
     per = {}
-    for name, e0, e1, f, cin, cout in recs:
+    for name, e0, e1, f, cin, cout, _ in recs:
         k = "%s_c%d_%d" % (name.replace("bcp_conv_", ""), cin, cout)
         d = per.setdefault(k, [0.0, 0.0, 0])
         d[0] += e0.elapsed_time(e1)
         d[1] += f
         d[2] += 1
-    return {"kernel": "conv_tc (tcgen05 implicit GEMM, fwd+dgrad)", "launches": len(recs), "avg_launch_ms": tot_ms / len(recs),
-            "achieved": tot_fl / (tot_ms / 1e3) / 1e12, "traffic": None,
+    # DRAM bytes per launch of the same kernels from the committed ncu capture (profiles/, tools/traffic_from_ncu.py);
+    # null when no capture has been committed for this build
+    traffic, tsrc = None, None
+    tp = os.path.join(ROOT, "profiles", "conv_traffic.json")
+    if os.path.exists(tp):
+        t = json.load(open(tp))
+        ks = [t[k] for k in ("conv_tc_kernel", "conv_tc_wgrad_kernel") if k in t]
+        if ks:
+            traffic = sum(k["dram_bytes_per_launch"] * k["launches"] for k in ks) / sum(k["launches"] for k in ks)
+            tsrc = "profiles/conv_traffic.json (ncu dram__bytes_read+write, mean over the conv_tc + conv_tc_wgrad launches of one step)"
+    alg_bytes = sum(r[6] for r in recs) / len(recs)
+    return {"kernel": "conv_tc + conv_tc_wgrad (tcgen05 implicit GEMM: fwd, dgrad, wgrad)", "launches": len(recs),
+            "avg_launch_ms": tot_ms / len(recs),
+            "achieved": tot_fl / (tot_ms / 1e3) / 1e12, "traffic": traffic, "traffic_source": tsrc,
+            "algorithmic_bytes_per_launch": alg_bytes,
             "per_shape_tflops": {k: round(v[1] / (v[0] / 1e3) / 1e12, 1) for k, v in per.items()},
             "kernel_ms_per_step": tot_ms}
+
+
+def set_cpu_threads():
+    """All the host threads the process may run on (its CPU affinity mask, which honours cpusets; os.cpu_count() counts
+    the machine's logical CPUs and oversubscribed the 128-thread GPU box); BCP_CPU_THREADS overrides."""
+    n = int(os.environ.get("BCP_CPU_THREADS", "0"))
+    if n <= 0:
+        try:
+            n = len(os.sched_getaffinity(0))
+        except AttributeError:
+            n = os.cpu_count() or 1
+        n = max(1, min(n, 64))        # PyTorch's conv/BN kernels stop scaling (and start thrashing) long before 128 threads
+    torch.set_num_threads(n)
 
 
 def oracle_step_runner():
     """The reference algorithm's CPU path (oracle/bcp_oracle.py: fp32 PyTorch restatement pinned to the reference)."""
     from oracle import bcp_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
+    set_cpu_threads()
     torch.manual_seed(1337)
     model, ema = O.net_factory("VNet", 1, 2, "train"), O.net_factory("VNet", 1, 2, "train")
     for p in ema.parameters():
@@ -279,7 +315,7 @@ def cpu_baseline_sample():
     """Bounded sample of the same workload: ONE self-training step at half the batch (labeled_bs 2: 4 loaded volumes,
     2 mixed student patches instead of 8 / 4), so the default bench run stays within a few minutes on the host CPU."""
     from oracle import bcp_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
+    set_cpu_threads()
     torch.manual_seed(1337)
     model, ema = O.net_factory("VNet", 1, 2, "train"), O.net_factory("VNet", 1, 2, "train")
     for p in ema.parameters():

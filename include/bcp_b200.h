@@ -158,6 +158,15 @@ int bcp_conv_tc_supported(int cin, int cout, const int* dims, const int* kernel)
 int bcp_conv_tc_plan(int n, int cin, int cout, const int* dims, const int* kernel, int* plan10);
 int bcp_conv_tc_fwd(const void* in, const void* wpack, const float* bias, void* out, int n, int cin, int cout,
                     const int* dims, const int* kernel, cudaStream_t stream);
+/* The same convolution with the train-mode normalisation statistics of its OUTPUT fused into the epilogue (replaces a
+ * following bcp_norm_stats call: identical stat/coef/running-statistic semantics, statistics taken over the bf16-rounded
+ * tensor that is stored).  bcp_conv_tc_stats_workspace_bytes returns 0 when the layer is not eligible (then call
+ * bcp_conv_tc_fwd + bcp_norm_stats); `counter` as for bcp_norm_stats. */
+long long bcp_conv_tc_stats_workspace_bytes(int n, int cin, int cout, const int* dims, const int* kernel, int spg);
+int bcp_conv_tc_fwd_stats(const void* in, const void* wpack, const float* bias, void* out, int n, int cin, int cout,
+                          const int* dims, const int* kernel, const float* gamma, const float* beta, float* running_mean,
+                          float* running_var, long long* num_batches_tracked, float* stat, float* coef, void* workspace,
+                          int* counter, int spg, float eps, float momentum, cudaStream_t stream);
 /* debug only: when `buffer` (device, 16 x uint64 per CTA, >= 148 CTAs) is non-null, bcp_conv_tc_fwd launches the
  * instrumented kernel variant that records per-role wait cycles; pass NULL to return to the product kernel. */
 int bcp_conv_tc_debug_profile(void* buffer);

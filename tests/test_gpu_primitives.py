@@ -410,3 +410,48 @@ def test_pool_and_upsample(ops, dev):
     assert rel_rms(planar_from_cb8(xcb.grad, 16)[:, :, 0], xr.grad) <= 6e-3
     x5 = torch.randn(2, 32, 7, 7, 5, device=dev).to(torch.bfloat16).float()
     assert torch.equal(ops.maxpool3d_k3s2(cb8_from_planar(x5), 32), F.max_pool3d(x5, 3, stride=2))
+
+
+@pytest.mark.parametrize("cin,cout,dims,kernel,spg", [(16, 16, (24, 24, 16), (3, 3, 3), 2), (32, 64, (20, 22, 20), (3, 3, 3), 2),
+                                                        (16, 32, (1, 96, 96), (1, 3, 3), 3)])
+def test_conv_fused_norm_statistics(ops, dev, cin, cout, dims, kernel, spg):
+    """bcp_conv_tc_fwd_stats: the statistics produced by the conv epilogue equal those of the separate pass over the
+    stored tensor (same stat/coef up to fp32 rounding of a double sum, identical running statistics semantics)."""
+    torch.manual_seed(cin + cout)
+    n = 2 * spg
+    x = torch.randn(n, cin, *dims, device=dev).to(torch.bfloat16).float()
+    w = (torch.randn(cout, cin, *kernel, device=dev) / np.sqrt(cin * np.prod(kernel))).to(torch.bfloat16).float()
+    b = 0.1 * torch.randn(cout, device=dev)
+    pack = _packs(ops, dev, w, (0, 1))
+    a = cb8_from_planar(x)
+    gamma, beta = 1 + 0.1 * torch.randn(cout, device=dev), 0.1 * torch.randn(cout, device=dev)
+
+    def run(fused):
+        rm, rv = torch.zeros(cout, device=dev), torch.ones(cout, device=dev)
+        nbt = torch.zeros((), dtype=torch.int64, device=dev)
+        req = dict(gamma=gamma, beta=beta, running_mean=rm, running_var=rv, nbt=nbt, spg=spg, eps=1e-5, momentum=0.1)
+        old = ops._FUSE_STATS
+        ops._FUSE_STATS = fused
+        try:
+            y = ops.ConvSame.apply(a, w, b, pack, kernel, False, req)
+        finally:
+            ops._FUSE_STATS = old
+        assert ("out" in req) == fused, "layer expected to be eligible for the fused-statistics epilogue"
+        out = ops.NormAct.apply(y, gamma, beta, rm, rv, nbt, "batch", spg, 1e-5, 0.1, 0.0, None, None, 1.0, None, req.get("out"))
+        torch.cuda.synchronize()
+        return y, out, rm, rv, int(nbt), req.get("out")
+
+    y0, o0, rm0, rv0, nbt0, _ = run(False)
+    y1, o1, rm1, rv1, nbt1, (stat, coef) = run(True)
+    assert torch.equal(y0, y1)
+    assert nbt0 == nbt1 == n // spg
+    assert torch.allclose(rm0, rm1, rtol=1e-5, atol=1e-7) and torch.allclose(rv0, rv1, rtol=1e-5, atol=1e-7)
+    # reference statistics of the stored tensor in double
+    yp = planar_from_cb8(y1, cout).double().reshape(n // spg, spg, cout, -1)
+    mean = yp.mean(dim=(1, 3))
+    var = yp.var(dim=(1, 3), unbiased=False)
+    assert torch.allclose(stat[..., 0].double(), mean, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(stat[..., 1].double(), 1 / torch.sqrt(var + 1e-5), rtol=1e-5)
+    e = rel_rms(planar_from_cb8(o1, cout), planar_from_cb8(o0, cout))
+    record("fused_stats_out_rel_rms_c%d" % cout, e)
+    assert e <= 1e-3            # a 1-ulp difference of scale/shift flips a handful of bf16 roundings
