@@ -47,8 +47,9 @@ struct TcParams {
 
 // Fused train-mode normalisation statistics (conv_tc_kernel<.., true>): the epilogue accumulates per-(group, channel)
 // sum and sum of squares of the bf16-ROUNDED outputs it stores, so the separate pass over y (norm.cu bn_stats_kernel)
-// disappears.  Accumulation is double precision end to end: the statistics do not depend on how bricks were tiled or
-// assigned to CTAs beyond ~1e-16, i.e. batching several reference calls as groups stays reproducible.
+// disappears.  A thread sums its (at most MT) rows of one item in fp32; every combination across lanes, items, warps and
+// CTAs is double precision in a fixed order (deterministic run to run; a different brick tiling regroups only those
+// short fp32 sums, i.e. moves the statistics by ~1e-8 relative).
 struct StatsArgs {
   double* partial;               // [gridDim.x][G][Cout][2]
   int* counter;                  // zero on entry, reset by the last CTA
@@ -178,13 +179,27 @@ __device__ void conv_stats_finalize(const StatsArgs& sa, int C, double M, unsign
   const int G = sa.G, GC2 = G * C * 2, nct = gridDim.x;
   double* sc = reinterpret_cast<double*>(smem);          // scratch [G][C][2] in the (now idle) operand slots
   if (threadIdx.x == 0 && sa.nbt != nullptr) sa.nbt[0] += G;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = warp; i < GC2; i += TC_THREADS / 32) {
-    double v = 0.0;
-    for (int b = lane; b < nct; b += 32) v += sa.partial[(size_t)b * GC2 + i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) sc[i] = v;
+  // column-parallel reduce of partial[nct][GC2]: thread = (segment of the CTA range, output column); consecutive threads
+  // read consecutive doubles, each keeps several loads in flight; segments are combined in fixed order afterwards
+  const int W = GC2 < TC_THREADS ? GC2 : TC_THREADS;
+  const int SEG = TC_THREADS / W;
+  const int seg = threadIdx.x / W, col = threadIdx.x - seg * W;
+  const int per = (nct + SEG - 1) / SEG;
+  for (int i0 = 0; i0 < GC2; i0 += W) {
+    const int i = i0 + col;
+    if (seg < SEG && i < GC2) {
+      const int b0 = seg * per, b1 = (b0 + per < nct) ? b0 + per : nct;
+      double v = 0.0;
+#pragma unroll 8
+      for (int b = b0; b < b1; ++b) v += sa.partial[(size_t)b * GC2 + i];
+      sc[(size_t)seg * GC2 + i] = v;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < GC2; i += TC_THREADS) {
+    double v = sc[i];
+    for (int k = 1; k < SEG; ++k) v += sc[(size_t)k * GC2 + i];
+    sc[i] = v;
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += TC_THREADS) {
@@ -374,9 +389,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         double* tbl = reinterpret_cast<double*>(smem + p.offStats) + (size_t)q * sa.G * p.Cout * 2;
         const int g = n / sa.spg;
         for (int c16 = 0; c16 < p.Ns; c16 += 16) {
-          double acc[32];
-#pragma unroll
-          for (int k = 0; k < 32; ++k) acc[k] = 0.0;
+          float facc[32];              // fp32 over this thread's <= MT rows of the item (FP64 here cost more than the
+#pragma unroll                         // separate statistics pass saved); everything across threads / items is double
+          for (int k = 0; k < 32; ++k) facc[k] = 0.f;
           for (int mt = 0; mt < p.MT; ++mt) {
             const int L = mt * 128 + q * 32 + lane;
             const int iz = L % p.HZ;
@@ -399,9 +414,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
               unpack8(p0, f);                    // the statistics are those of the stored (bf16-rounded) tensor
               unpack8(p1, f + 8);
 #pragma unroll
-              for (int k = 0; k < 16; ++k) { const double d = (double)f[k]; acc[k] += d; acc[16 + k] += d * d; }
+              for (int k = 0; k < 16; ++k) { facc[k] += f[k]; facc[16 + k] = fmaf(f[k], f[k], facc[16 + k]); }
             }
           }
+          double acc[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) acc[k] = (double)facc[k];
           xreduce_step<32, 16>(acc, lane);
           xreduce_step<16, 8>(acc, lane);
           xreduce_step<8, 4>(acc, lane);
@@ -1258,13 +1276,20 @@ static int conv_tc_launch(const void* in, const void* wpack, const float* bias, 
     p.offStats = (unsigned)((p.offBar + 8 * (2 * p.SA + 2 * p.SB + 2 * p.AS) + 16 + 127) / 128 * 128);
     smem = (size_t)p.offStats + (p.reserve - 128) + 128;
   }
-  BCP_REQUIRE(smem <= 227 * 1024, "conv_tc_fwd: shared memory plan overflow (%zu bytes)", smem);
+  // dynamic + static shared memory share the 227 KB opt-in limit; the statistics variant has a few static bytes, so
+  // every variant opts into 226 KB of dynamic memory (plans stay below SMEM_BUDGET + barriers ~ 221 KB)
+  constexpr int kMaxDyn = 226 * 1024;
+  BCP_REQUIRE(smem <= (size_t)kMaxDyn, "conv_tc_fwd: shared memory plan overflow (%zu bytes)", smem);
   static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
+    attr_err = e;
+    if (e != cudaSuccess) cudaGetLastError();
   });
+  if (attr_err != cudaSuccess) { set_last_error("conv_tc_fwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err)); return BCP_ERR_CUDA; }
   const int nitems = p.nbricks * p.NS;
   const int grid = nitems < nsm ? nitems : nsm;
   if (sa) conv_tc_kernel<false, true><<<grid, TC_THREADS, smem, stream>>>(tmap, tmap_w, bias, (uint4*)out, p, nullptr, *sa);
@@ -1280,8 +1305,6 @@ int bcp_conv_tc_fwd(const void* in, const void* wpack, const float* bias, void* 
 
 long long bcp_conv_tc_stats_workspace_bytes(int n, int cin, int cout, const int* dims, const int* kernel, int spg) {
   if (!dims || !kernel || !shape_ok(cin, cout, dims, kernel) || get_encode() == nullptr) return 0;
-  static const bool off = getenv("BCP_NO_FUSED_STATS") != nullptr;
-  if (off) return 0;
   const unsigned tb = stats_table_bytes(n, cout, dims, spg);
   if (!tb) return 0;
   TcParams p{};

@@ -18,7 +18,9 @@ BF16 = torch.bfloat16
 # debugging switches (kernel selection only -- both settings run hand-written sm_100a kernels)
 _TC_FWD = os.environ.get("BCP_DISABLE_TC", "0") != "1"
 _TC_WGRAD = _TC_FWD and os.environ.get("BCP_DISABLE_TC_WGRAD", "0") != "1"
-_FUSE_STATS = os.environ.get("BCP_NO_FUSED_STATS", "0") != "1"     # conv epilogue produces the following norm's statistics
+# conv epilogue produces the following norm's statistics (bcp_conv_tc_fwd_stats).  Opt-in: parity-tested, but on the LA step
+# the fused epilogue + last-CTA finalize cost about what the (now 4-loads-in-flight) standalone statistics pass costs.
+_FUSE_STATS = os.environ.get("BCP_FUSED_STATS", "0") == "1"
 
 
 def _require_cuda(t: torch.Tensor, what: str):

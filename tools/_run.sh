@@ -1,10 +1,9 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q --timeout 600 --timeout-method thread > gpurun_out/pytest_gpu.log 2>&1; tail -4 gpurun_out/pytest_gpu.log | cut -c1-300
 if ! grep -q " passed" gpurun_out/pytest_gpu.log || grep -q "failed" gpurun_out/pytest_gpu.log; then
-  BCP_NO_FUSED_STATS=1 timeout 900 python -m pytest tests -m gpu -q --timeout 600 --timeout-method thread > gpurun_out/pytest_gpu_nofuse.log 2>&1; echo NOFUSE; tail -3 gpurun_out/pytest_gpu_nofuse.log | cut -c1-300
+  BCP_FUSED_STATS=0 timeout 900 python -m pytest tests -m gpu -q --timeout 600 --timeout-method thread > gpurun_out/pytest_gpu_nofuse.log 2>&1; echo NOFUSE; tail -3 gpurun_out/pytest_gpu_nofuse.log | cut -c1-300
 fi
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log | cut -c1-300
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_graph.log 2>&1; tail -1 gpurun_out/bench_graph.log | cut -c1-250
-BCP_NO_FUSED_STATS=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_nofuse.log 2>&1; tail -1 gpurun_out/bench_nofuse.log | cut -c1-250
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches_r01g.csv python bench.py --steps 2 --warmup 1 --profile > gpurun_out/ncu_list.log 2>&1; tail -1 gpurun_out/ncu_list.log | cut -c1-200
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 36 -c 4 -f -o gpurun_out/conv_tc_r01c python bench.py --steps 1 --warmup 1 --profile > gpurun_out/ncu_full.log 2>&1; tail -1 gpurun_out/ncu_full.log | cut -c1-200
+
