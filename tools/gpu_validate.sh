@@ -1,3 +1,4 @@
+# GPU-box validation used in round 1:  gpurun --timeout 1000 -- "bash tools/gpu_validate.sh"  (logs land in gpurun_out/)
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q --timeout 600 --timeout-method thread > gpurun_out/pytest_gpu.log 2>&1; tail -4 gpurun_out/pytest_gpu.log | cut -c1-300
 if ! grep -q " passed" gpurun_out/pytest_gpu.log || grep -q "failed" gpurun_out/pytest_gpu.log; then
