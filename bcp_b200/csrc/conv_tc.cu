@@ -4,8 +4,10 @@
 //
 // Design ("halo brick + shifted views"):
 //   * The output volume is cut into bricks of BX x BY x BZ voxels.  For a 16-channel chunk of the input, ONE
-//     5-D TMA box load brings the brick plus its one-voxel halo into shared memory (out-of-bounds = zero fill =
-//     the convolution's zero padding) as two 8-channel planes of [HX*HY*HZ rows][8 ch] = 16 bytes per row.
+//     TMA box load brings the brick plus its one-voxel halo into shared memory (out-of-bounds = zero fill =
+//     the convolution's zero padding) as two 8-channel planes of [HX*HY*HZ rows][8 ch] = 16 bytes per row.  The
+//     tensor map describes the CB8 tensor as 8-byte elements with (z, 8 channels) merged into the innermost
+//     dimension (encode_cb8), so a box row is a whole z-run, not a 16-byte voxel.
 //   * That is exactly the UMMA "K-major, no swizzle" canonical layout with 16-byte rows (SBO = 128 B between
 //     8-row groups, LBO = plane stride between the two K chunks).  A filter tap (dx,dy,dz) is therefore nothing
 //     but a start-address offset of ((dx*HY+dy)*HZ+dz)*16 bytes in the A descriptor: all 27 taps are MMAs over
@@ -14,10 +16,14 @@
 //     (efficiency BY*BZ/((BY+2)*(BZ+2)) per x-slab, chosen per layer by a small cost model).
 //   * M = 128 rows per MMA, N = Cout (16..256), K = 16; accumulators live in TMEM (MT tiles of N columns,
 //     double-buffered when 2*MT*N <= 512) and are drained by four epilogue warps with tcgen05.ld.
-//   * Warp roles: warp 0 = TMA producer (A bricks through a ring of 16-channel slots, per-tap weight tiles
-//     through a second ring via cp.async.bulk), warp 1 = MMA issuer (one elected lane), warps 2..5 = epilogue
-//     (TMEM -> registers -> +bias -> bf16 -> 16-byte coalesced stores).  All hand-offs are mbarriers.
-//   * Persistent grid: one CTA per SM, bricks assigned round-robin (static => deterministic).
+//   * Warp roles: warp 0 = TMA producer (A bricks through a ring of 16-channel slots; the weights of a chunk --
+//     all taps, or one dx-group of nine -- as one TMA box per stage of a second ring), warp 1 = MMA issuer (ONE
+//     elected thread runs the whole role: the tensor pipe is paced by that thread's instruction stream, see the
+//     comment at the issuer and tools/micro/mma_bench.cu), warps 2..5 = epilogue (TMEM -> registers -> +bias ->
+//     bf16 -> 16-byte coalesced stores; optionally the following normalisation's batch statistics).  All hand-offs
+//     are mbarriers.
+//   * Work item = (brick, slice of Cout/NS output channels); persistent grid, one CTA per SM, items assigned
+//     round-robin (static => deterministic).
 #include "common.cuh"
 #include "../../include/bcp_b200.h"
 #include <cuda.h>
@@ -980,7 +986,7 @@ static bool plan(TcParams& p, int nsm) {
           const long long rows_alloc = (long long)MT * 128 + ((long long)(p.kx - 1) * HY + 2) * HZ + 2;
           const long long slotA = ((rows_h + (rows_alloc > rows_h ? rows_alloc : rows_h)) * 16 + 127) / 128 * 128;
           // A slots: 2..3 (one (brick, 16-channel) chunk each); the rest of shared memory goes to weight stages, whose
-          // depth hides the L2 latency of the cp.async.bulk stream (3..8 stages)
+          // depth hides the L2 latency of the weight stream
           int TG = T;
           unsigned stageB = (unsigned)TG * (unsigned)Ns * 32u;
           if ((long long)SMEM_BUDGET - (long long)p.reserve - 1024 - 2 * slotA < 2ll * stageB) { TG = 9; stageB = 9u * (unsigned)Ns * 32u; }

@@ -1,8 +1,8 @@
 """BCP training-step bodies on the sm_100a kernels.
 
-la_self_train_step / la_pre_train_step   <- LA_BCP_train.py:234-270 / :146-171
-acdc_self_train_step                      <- ACDC_BCP_train.py:354-390
-pan_self_train_step                       <- pancreas/train_pancreas.py:144-174
+la_self_train_step / la_pre_train_step     <- LA_BCP_train.py:234-270 / :146-171
+acdc_self_train_step / acdc_pre_train_step <- ACDC_BCP_train.py:354-390 / :237-255
+pan_self_train_step / pan_pre_train_step   <- pancreas/train_pancreas.py:144-174 / :82-99
 
 Differences from the reference that do not change the arithmetic: the two teacher forwards (and the two student
 forwards) of a step run as ONE batched call with per-call BatchNorm groups; the box mask is never materialised;
@@ -92,6 +92,26 @@ def la_pre_train_step(model, optimizer, volume, label, labeled_bs=4, mask_ratio=
     return dict(loss=loss.detach(), loss_dice=r[1].detach(), loss_ce=r[2].detach(), box=box, out=out.detach())
 
 
+def acdc_pre_train_step(model, optimizer, volume, label, labeled_bs=12, box=None):
+    """ACDC_BCP_train.py:237-255: the two labeled sub-batches mixed through the box; mix_loss(u_weight=1.0, unlab=True),
+    i.e. both regions weighted 1.  volume [B,1,H,W] fp32, label [B,H,W] uint8 on the GPU."""
+    sub = labeled_bs // 2
+    label = ops.to_u8_labels(label)
+    vol, lab = volume[:labeled_bs], label[:labeled_bs]
+    img_a, img_b, lab_a, lab_b = vol[:sub], vol[sub:], lab[:sub], lab[sub:]
+    if box is None:
+        box = _acdc_box(img_a.shape)
+    with torch.no_grad():
+        net_input = ops.mask_mix(img_a, img_b, box)                        # :244
+    out = model(net_input)
+    r = ops.MixLoss.apply(out, lab_a, lab_b, box, None, 1, 1.0, 1.0)        # :249
+    loss = (r[1] + r[2]) / 2
+    optimizer.zero_grad()
+    loss.backward()
+    optimizer.step()
+    return dict(loss=loss.detach(), loss_dice=r[1].detach(), loss_ce=r[2].detach(), box=box, out=out.detach())
+
+
 def acdc_self_train_step(model, ema_model, optimizer, volume, label, labeled_bs=12, u_weight=0.5, nms=1, box=None,
                          plab_override=None):
     """volume [B,1,H,W] fp32, label [B,H,W] uint8 on the GPU."""
@@ -126,6 +146,24 @@ def acdc_self_train_step(model, ema_model, optimizer, volume, label, labeled_bs=
     optimizer.step()                                                        # SGD + state_dict EMA, fused
     return dict(loss=loss.detach(), loss_dice=loss_dice.detach(), loss_ce=loss_ce.detach(), box=box, plab=plab_own,
                 mixed=mixed, out=out.detach())
+
+
+def pan_pre_train_step(net, optimizer, img_a, lab_a, img_b, lab_b, patch_size=64, box=None):
+    """pancreas/train_pancreas.py:82-99: image and label mixed through the box, unmasked CE + Dice on the mixed label."""
+    lab_a, lab_b = ops.to_u8_labels(lab_a), ops.to_u8_labels(lab_b)
+    if box is None:
+        box = _pan_box(patch_size)
+    with torch.no_grad():
+        img = ops.mask_mix(img_a, img_b, box)
+    out = net(img)[0]
+    lab = ops.label_mix(lab_a, lab_b, box)
+    # one region (empty box), both terms on the mixed label: the same reduction la_pre_train_step uses
+    r = ops.MixLoss.apply(out, lab, lab, (0, 0, 0, 0, 0, 0), None, 0, 1.0, 0.0)
+    loss = r[0]
+    optimizer.zero_grad()
+    loss.backward()
+    optimizer.step()
+    return dict(loss=loss.detach(), loss_dice=r[1].detach(), loss_ce=r[2].detach(), box=box, out=out.detach())
 
 
 def pan_self_train_step(net, ema_net, optimizer, img_a, lab_a, img_b, lab_b, unimg_a, unimg_b, patch_size=64,

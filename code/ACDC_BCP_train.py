@@ -68,27 +68,17 @@ def make_loader(args, device, rank):
 
 
 def pre_train(args, snapshot_path, device, rank):
-    from bcp_b200 import ops
     from bcp_b200.networks.net_factory import BCP_net
     from bcp_b200.optim import FusedSGD_EMA
-    from bcp_b200.step import _acdc_box
+    from bcp_b200.step import acdc_pre_train_step
     model = BCP_net(in_chns=1, class_num=args.num_classes)
     optimizer = FusedSGD_EMA(model, None, lr=args.base_lr, momentum=0.9, weight_decay=0.0001)
     model.train()
-    sub = args.labeled_bs // 2
     iters = args.pre_iterations if not args.max_steps else min(args.max_steps, args.pre_iterations)
     it = 0
     for batch in make_loader(args, device, rank):
-        vol, lab = batch['image'][:args.labeled_bs], batch['label'][:args.labeled_bs]
-        img_a, img_b, lab_a, lab_b = vol[:sub], vol[sub:], lab[:sub], lab[sub:]
-        box = _acdc_box(img_a.shape)
-        net_input = ops.mask_mix(img_a, img_b, box)                                   # ACDC_BCP_train.py:244
-        out = model(net_input)
-        r = ops.MixLoss.apply(out, lab_a, lab_b, box, None, 1, 1.0, 1.0)              # mix_loss(u_weight=1.0, unlab=True) :249
-        loss = (r[1] + r[2]) / 2
-        optimizer.zero_grad()
-        loss.backward()
-        optimizer.step()
+        res = acdc_pre_train_step(model, optimizer, batch['image'], batch['label'], args.labeled_bs)   # ACDC_BCP_train.py:237-255
+        loss, r = res["loss"], (None, res["loss_dice"], res["loss_ce"])
         it += 1
         if it % args.log_every == 0 and rank == 0:
             logging.info('iteration %d: loss: %f, mix_dice: %f, mix_ce: %f' % (it, float(loss), float(r[1]), float(r[2])))

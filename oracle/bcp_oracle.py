@@ -492,6 +492,37 @@ def acdc_self_train_step(model, ema_model, optimizer, volume, label, labeled_bs=
                 plab_a=plab_a, plab_b=plab_b, in_unl=in_unl, in_l=in_l, out_unl=out_unl.detach(), out_l=out_l.detach())
 
 
+def acdc_pre_train_step(model, optimizer, volume, label, labeled_bs=12, rng=np.random):
+    """ACDC_BCP_train.py:237-255: two labeled sub-batches mixed through the box, mix_loss(u_weight=1.0, unlab=True)."""
+    sub = labeled_bs // 2
+    img_a, img_b = volume[:sub], volume[sub:labeled_bs]
+    lab_a, lab_b = label[:sub], label[sub:labeled_bs]
+    img_mask, loss_mask, box = generate_mask_acdc(img_a, rng)
+    net_input = mask_mix(img_a, img_b, img_mask)
+    out = model(net_input)
+    loss_dice, loss_ce = mix_loss_acdc(out, lab_a, lab_b, loss_mask, u_weight=1.0, unlab=True)
+    loss = (loss_dice + loss_ce) / 2
+    optimizer.zero_grad()
+    loss.backward()
+    optimizer.step()
+    return dict(loss=loss.detach(), loss_dice=loss_dice.detach(), loss_ce=loss_ce.detach(), box=box, out=out.detach())
+
+
+def pan_pre_train_step(net, optimizer, img_a, lab_a, img_b, lab_b, patch_size=64, rng=np.random):
+    """pancreas/train_pancreas.py:82-99: image AND label mixed through the box, unmasked CE + Dice."""
+    img_mask, _, box = generate_mask_pan(img_a, patch_size, rng)
+    img = mask_mix(img_a, img_b, img_mask)
+    lab = mask_mix(lab_a, lab_b, img_mask)
+    out = net(img)[0]
+    loss_ce = F.cross_entropy(out, lab)
+    loss_dice = mask_dice_loss(out, lab)
+    loss = (loss_ce + loss_dice) / 2
+    optimizer.zero_grad()
+    loss.backward()
+    optimizer.step()
+    return dict(loss=loss.detach(), loss_ce=loss_ce.detach(), loss_dice=loss_dice.detach(), box=box, out=out.detach())
+
+
 def pan_self_train_step(net, ema_net, optimizer, img_a, lab_a, img_b, lab_b, unimg_a, unimg_b,
                         patch_size=64, alpha=0.99, connect_mode=2, rng=np.random):
     """pancreas/train_pancreas.py:144-174."""

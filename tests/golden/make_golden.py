@@ -344,6 +344,63 @@ def gen_acdc_step():
     save("acdc_step", **out)
 
 
+def gen_acdc_pre_step():
+    """ACDC_BCP_train.py:237-255 with the reference's own modules and script-local helpers."""
+    model = R.net_factory.BCP_net(1, 4)
+    O.fill_state_dict_(model, 151)
+    model.train()
+    inject_dropout(model, seed=152)
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=0.0001)
+    H, W, labeled_bs = 64, 64, 4
+    np.random.seed(4242)
+    volume_batch = O.synthetic_volume((labeled_bs, 1, H, W), 153, "rand")
+    label_batch = O.synthetic_labels((labeled_bs, H, W), 154, n_classes=4).to(torch.uint8)
+    sub = labeled_bs // 2
+    img_a, img_b = volume_batch[:sub], volume_batch[sub:labeled_bs]
+    lab_a, lab_b = label_batch[:sub], label_batch[sub:labeled_bs]
+    img_mask, loss_mask = ACDC_ns.generate_mask(img_a)
+    net_input = img_a * img_mask + img_b * (1 - img_mask)
+    out_mixl = model(net_input)
+    loss_dice, loss_ce = ACDC_ns.mix_loss(out_mixl, lab_a, lab_b, loss_mask, u_weight=1.0, unlab=True)
+    loss = (loss_dice + loss_ce) / 2
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    save("acdc_pre_step", shape=np.array([H, W]), labeled_bs=labeled_bs, seed=4242, loss=loss.detach(), loss_dice=loss_dice.detach(),
+         loss_ce=loss_ce.detach(), out=out_mixl.detach(), net_input=net_input,
+         grad_digest=digest_named({n: p.grad for n, p in model.named_parameters() if p.grad is not None}),
+         model_digest=digest_named(model.state_dict()))
+    print("acdc pre step", float(loss))
+
+
+def gen_pan_pre_step():
+    """pancreas/train_pancreas.py:82-99."""
+    net = R.pan_Vnet.VNet()
+    O.fill_state_dict_(net, 161)
+    net.train()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    DICE = R.pan_losses.DiceLoss(nclass=2)
+    np.random.seed(777)
+    S = (96, 96, 96)
+    v = O.synthetic_volume((2, 1) + S, 162)
+    l = O.synthetic_labels((2,) + S, 163)
+    img_a, img_b, lab_a, lab_b = v[0:1], v[1:2], l[0:1], l[1:2]
+    img_mask, loss_mask = PANU.generate_mask(img_a, 64)
+    img = img_a * img_mask + img_b * (1 - img_mask)
+    lab = lab_a * img_mask + lab_b * (1 - img_mask)
+    out = net(img)[0]
+    ce = F.cross_entropy(out, lab)
+    dice = DICE(out, lab)
+    loss = (ce + dice) / 2
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    save("pan_pre_step", seed=777, loss=loss.detach(), loss_ce=ce.detach(), loss_dice=dice.detach(), out=out.detach()[..., ::4, ::4, ::4],
+         grad_digest=digest_named({n: p.grad for n, p in net.named_parameters() if p.grad is not None}),
+         model_digest=digest_named(net.state_dict()))
+    print("pan pre step", float(loss))
+
+
 def gen_pan_step():
     t0 = time.time()
     net, ema = R.pan_Vnet.VNet(), R.pan_Vnet.VNet()
@@ -387,7 +444,11 @@ def gen_pan_step():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["functions", "networks", "la_small", "la_pre", "acdc", "la_full", "pan"]
+    which = sys.argv[1:] or ["functions", "networks", "la_small", "la_pre", "acdc", "la_full", "pan", "acdc_pre", "pan_pre"]
+    if "acdc_pre" in which:
+        gen_acdc_pre_step()
+    if "pan_pre" in which:
+        gen_pan_pre_step()
     if "functions" in which:
         gen_functions()
     if "networks" in which:

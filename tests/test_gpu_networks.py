@@ -1,6 +1,7 @@
 """GPU parity of whole networks and whole BCP steps against the golden vectors minted from the reference
 (tests/golden/*.npz) and the fp32 oracle.  Activations are bf16 on the B200 path, the reference is fp32, so logits
 carry bf16 rounding noise; the tolerances below are the stated bf16 budget (DESIGN.md section "Parity")."""
+import os
 import numpy as np
 import pytest
 import torch
@@ -303,3 +304,52 @@ def test_pan_step(dev):
     e = rel_rms(r["out"][:2][..., ::4, ::4, ::4].cpu(), T(g["s0_out_1"]))
     record("pan_out_rel_rms", e)
     assert e <= 2 * TRAIN_SMALL_TOL
+
+
+# The two pre-training steps below were added after round 1's GPU budget was spent: their oracle side is pinned on the
+# CPU (tests/test_oracle_golden.py::test_acdc_pre_step / test_pan_pre_step); the device side first runs in round 2.
+_PENDING = pytest.mark.skipif(os.environ.get("BCP_RUN_PENDING_GPU_TESTS", "0") != "1",
+                              reason="first GPU run pending (set BCP_RUN_PENDING_GPU_TESTS=1)")
+
+
+@_PENDING
+def test_acdc_pre_step(dev):
+    from bcp_b200.networks.net_factory import BCP_net
+    from bcp_b200.optim import FusedSGD_EMA
+    from bcp_b200.step import acdc_pre_train_step
+    g = load_golden("acdc_pre_step")
+    model = BCP_net(1, 4)
+    O.fill_state_dict_(model, 151)
+    model.train()
+    inject_dropout(model, seed=152)
+    opt = FusedSGD_EMA(model, None, lr=0.01, momentum=0.9, weight_decay=1e-4)
+    np.random.seed(int(g["seed"]))
+    vol = O.synthetic_volume((4, 1, 64, 64), 153, "rand").to(dev)
+    lab = O.synthetic_labels((4, 64, 64), 154, n_classes=4).to(torch.uint8).to(dev)
+    r = acdc_pre_train_step(model, opt, vol, lab, labeled_bs=4)
+    for k in ("loss", "loss_dice", "loss_ce"):
+        rel = abs(float(r[k]) - float(g[k])) / abs(float(g[k]))
+        record(f"acdc_pre_{k}_rel_err", rel)
+        assert rel <= 2e-2, (k, rel)
+    assert rel_rms(r["out"].cpu(), T(g["out"])) <= 2 * TRAIN_SMALL_TOL
+
+
+@_PENDING
+def test_pan_pre_step(dev):
+    from bcp_b200.pancreas.Vnet import VNet
+    from bcp_b200.optim import FusedAdam_EMA
+    from bcp_b200.step import pan_pre_train_step
+    g = load_golden("pan_pre_step")
+    net = VNet().to(dev)
+    O.fill_state_dict_(net, 161)
+    net.train()
+    opt = FusedAdam_EMA(net, None, lr=1e-3)
+    np.random.seed(int(g["seed"]))
+    S = (96, 96, 96)
+    v = O.synthetic_volume((2, 1) + S, 162).to(dev)
+    l = O.synthetic_labels((2,) + S, 163).to(torch.uint8).to(dev)
+    r = pan_pre_train_step(net, opt, v[0:1], l[0:1], v[1:2], l[1:2])
+    rel = abs(float(r["loss"]) - float(g["loss"])) / abs(float(g["loss"]))
+    record("pan_pre_loss_rel_err", rel)
+    assert rel <= LOSS_TOL
+    assert rel_rms(r["out"].cpu()[..., ::4, ::4, ::4], T(g["out"])) <= 2 * TRAIN_SMALL_TOL

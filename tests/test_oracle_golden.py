@@ -265,3 +265,40 @@ def test_pan_step():
     close(r["out_1"][..., ::4, ::4, ::4], g["s0_out_1"], rtol=1e-3, atol=1e-3)
     digests_close(digest_named(net.state_dict()), g["s0_model_digest"])
     digests_close(digest_named(ema.state_dict()), g["s0_ema_digest"])
+
+
+def test_acdc_pre_step():
+    """ACDC pre-training step (ACDC_BCP_train.py:237-255) of the oracle against the reference-generated fixture."""
+    g = load("acdc_pre_step")
+    model = O.BCP_net(1, 4)
+    O.fill_state_dict_(model, 151)
+    model.train()
+    inject_dropout(model, seed=152)
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=0.0001)
+    vol = O.synthetic_volume((4, 1, 64, 64), 153, "rand")
+    lab = O.synthetic_labels((4, 64, 64), 154, n_classes=4).to(torch.uint8)
+    r = O.acdc_pre_train_step(model, opt, vol, lab, labeled_bs=4, rng=np.random.RandomState(int(g["seed"])))
+    close(r["loss"], g["loss"], rtol=2e-5)
+    close(r["loss_dice"], g["loss_dice"], rtol=2e-5)
+    close(r["loss_ce"], g["loss_ce"], rtol=2e-5)
+    close(r["out"], g["out"], rtol=1e-3, atol=1e-3)
+    digests_close(digest_named(model.state_dict()), g["model_digest"])
+
+
+@pytest.mark.slow
+def test_pan_pre_step():
+    """Pancreas pre-training step (pancreas/train_pancreas.py:82-99)."""
+    g = load("pan_pre_step")
+    net = O.OraclePanVNet()
+    O.fill_state_dict_(net, 161)
+    net.train()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    S = (96, 96, 96)
+    v = O.synthetic_volume((2, 1) + S, 162)
+    l = O.synthetic_labels((2,) + S, 163)
+    r = O.pan_pre_train_step(net, opt, v[0:1], l[0:1], v[1:2], l[1:2], 64, rng=np.random.RandomState(int(g["seed"])))
+    close(r["loss"], g["loss"], rtol=2e-5)
+    close(r["loss_ce"], g["loss_ce"], rtol=2e-5)
+    close(r["loss_dice"], g["loss_dice"], rtol=2e-5)
+    close(r["out"][..., ::4, ::4, ::4], g["out"], rtol=1e-3, atol=1e-3)
+    digests_close(digest_named(net.state_dict()), g["model_digest"], rtol=2e-3)
