@@ -88,6 +88,25 @@ def test_flat_arena_and_packs():
     assert g.numel() == rt.n_train
     assert net.decoder.out_conv.weight.grad.data_ptr() >= g.data_ptr()
     assert rt.njobs == 64       # 20 'same' convs x (fwd, dgrad) + 8 stride-2 convs x 3 packs; block_one/out_conv read fp32
+    # the EMA teacher never runs a 3x3x3 data gradient: no kind-1 (flipped / transposed) packs, everything else unchanged
+    from bcp_b200.networks.runtime import _JOB
+    ema = VNet(1, 2, 16, "batchnorm", True)
+    for p in ema.parameters():
+        p.detach_()
+    ema.runtime.flatten_()
+    assert ema.runtime.njobs == 64 - 20
+    kinds = np.frombuffer(ema.runtime.jobs.cpu().numpy().tobytes(), dtype=_JOB)["kind"]
+    assert 1 not in set(kinds.tolist()) and {0, 2, 3} <= set(kinds.tolist())
+
+
+def test_launch_count_rules():
+    """gpu_launches in bench.py is counted from C-ABI calls: the per-call kernel counts follow the dispatch in norm.cu"""
+    from bcp_b200._native import KERNELS_PER_CALL, _norm_bwd_kernels
+    base = [0] * 8 + [1, 1] + [0, 0, 0]
+    assert _norm_bwd_kernels(base + [4, 256, 245, 2, 0.0, 1, 0, 0]) == 1          # tiny layer: reduce+apply in one launch
+    assert _norm_bwd_kernels(base + [4, 16, 1003520, 2, 0.0, 1, 0, 0]) == 2        # reduce pass + apply pass
+    assert _norm_bwd_kernels([0] * 8 + [None, None] + [0, 0, 0] + [4, 16, 1003520, 2, 0.0, 0, 0, 0]) == 1   # no statistics gradient
+    assert KERNELS_PER_CALL["bcp_largest_cc"] == 5 and KERNELS_PER_CALL["bcp_conv_tc_wgrad"] == 2
 
 
 def test_box_draw_order_matches_reference():
