@@ -483,6 +483,181 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 }
 
 // =========================================================================================================
+// EXPERIMENTAL (round-2 plan; not on the default path, enabled by BCP_TC_FOLD=1 in ops.py and not
+// yet run on a GPU): the same convolution with the three dz taps of a (dx,dy) pair folded into the MMA N dimension.
+//   B tile of a group g=(dx,dy): [W(g,dz=0) | W(g,dz=1) | W(g,dz=2)]  -> N = 3*Ns, D'[row][dz*Ns + co]
+//   A tile: 8-row core-matrix groups start every SIX rows (descriptor SBO = 96 B): tile row i is frame row
+//           96*mt + 6*(i/8) + (i%8), so an 8-lane group of the epilogue holds rows r..r+7 and produces outputs r..r+5 as
+//           out[r] = D'[r][0] + D'[r+1][1] + D'[r+2][2] with two intra-group shuffles (tools/model_dzfold.py checks the
+//           index algebra).  9 MMAs of N = 3*Ns per 96 output rows instead of 27 of N = Ns per 128.
+// Same roles / barriers as conv_tc_kernel; one weight stage = all taps of a 16-channel chunk laid out [g][plane][dz][Ns].
+// =========================================================================================================
+struct FoldParams {
+  int N, X, Y, Z, Cin, Cout, kx;
+  int BX, BY, BZ, HX, HY, HZ;
+  int nbx, nby, nbz, nbricks;
+  int rows_h, MT, nchunks, ngrp;   // MT = tiles of 96 output rows per brick, ngrp = (dx,dy) groups (9 or 3)
+  int SA, SB, NS, Ns, AS, tmem_cols;
+  unsigned slotA_bytes, stageB_bytes, offA, offB, offBar;
+  int mergedA;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_w,
+                    const float* __restrict__ bias, uint4* __restrict__ out, const FoldParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t a_base = sbase + p.offA, b_base = sbase + p.offB, bar_base = sbase + p.offBar;
+  const uint32_t full_a = bar_base, empty_a = full_a + 8 * p.SA, full_b = empty_a + 8 * p.SA, empty_b = full_b + 8 * p.SB;
+  const uint32_t tmem_full = empty_b + 8 * p.SB, tmem_empty = tmem_full + 8 * p.AS;
+  volatile uint32_t* tmem_slot = (volatile uint32_t*)(smem + p.offBar + 8 * (2 * p.SA + 2 * p.SB + 2 * p.AS));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p.SA; ++i) { mbar_init(full_a + 8 * i, 1); mbar_init(empty_a + 8 * i, 1); }
+    for (int i = 0; i < p.SB; ++i) { mbar_init(full_b + 8 * i, 1); mbar_init(empty_b + 8 * i, 1); }
+    for (int i = 0; i < p.AS; ++i) { mbar_init(tmem_full + 8 * i, 1); mbar_init(tmem_empty + 8 * i, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int Cib = p.Cin >> 3, Cob = p.Cout >> 3;
+  const int bricks_per_n = p.nbx * p.nby * p.nbz;
+  const int nitems = p.nbricks * p.NS;
+  const int N3 = 3 * p.Ns;
+
+  if (warp == 0) {
+    Ring ra, rb;
+    const uint32_t a_bytes = (uint32_t)p.rows_h * 32u;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const int brick = item / p.NS, n0 = (item - brick * p.NS) * p.Ns;
+      const int n = brick / bricks_per_n;
+      int r = brick - n * bricks_per_n;
+      const int bz = r % p.nbz; r /= p.nbz;
+      const int by = r % p.nby;
+      const int bx = r / p.nby;
+      const int x0 = bx * p.BX - (p.kx >> 1), y0 = by * p.BY - 1, z0 = bz * p.BZ - 1;
+      for (int c = 0; c < p.nchunks; ++c) {
+        mbar_wait(empty_a + 8 * ra.s, ra.ph ^ 1);
+        mbar_wait(empty_b + 8 * rb.s, rb.ph ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(full_a + 8 * ra.s, a_bytes);
+          tma_load_cb8(a_base + ra.s * p.slotA_bytes, &tmap, full_a + 8 * ra.s, p.mergedA, z0, y0, x0, n * Cib + 2 * c);
+          // weight box {Ns*2 (8-byte units), dz 3, plane 2, group ngrp} -> shared memory [g][plane][dz][Ns rows]
+          mbar_expect_tx(full_b + 8 * rb.s, p.stageB_bytes);
+          tma_load_4d(b_base + rb.s * p.stageB_bytes, &tmap_w, full_b + 8 * rb.s, 2 * n0, 0, 2 * c, 0);
+        }
+        __syncwarp();
+        ra.advance(p.SA);
+        rb.advance(p.SB);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N3 >> 3) << 17) | ((128u >> 4) << 24);
+      const uint64_t adesc0 = make_desc(0, (uint32_t)p.rows_h * 16u, 96u);        // SBO = 96 B: row groups overlap by two rows
+      const uint64_t bdesc0 = make_desc(0, (uint32_t)N3 * 16u, 128u);
+      const uint32_t a_hi = (uint32_t)(adesc0 >> 32), b_hi = (uint32_t)(bdesc0 >> 32);
+      const uint32_t a_lo0 = (uint32_t)adesc0, b_lo0 = (uint32_t)bdesc0;
+      const uint32_t HZ = (uint32_t)p.HZ, plane = (uint32_t)(p.HY * p.HZ);
+      const uint32_t bgroup = 2u * (uint32_t)N3;                                    // 16-byte units per (dx,dy) group: 2 planes x 3*Ns rows
+      Ring ra, rb, rt;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x, rt.advance(p.AS)) {
+        mbar_wait(tmem_empty + 8 * rt.s, rt.ph ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + rt.s * (uint32_t)(p.MT * N3);
+        for (int c = 0; c < p.nchunks; ++c) {
+          mbar_wait(full_a + 8 * ra.s, ra.ph);
+          mbar_wait(full_b + 8 * rb.s, rb.ph);
+          tc_fence_after();
+          const uint32_t a_slot = a_lo0 + ((a_base + ra.s * p.slotA_bytes) >> 4);
+          const uint32_t b_slot = b_lo0 + ((b_base + rb.s * p.stageB_bytes) >> 4);
+          uint32_t d = d0, a_m = a_slot;
+          for (int mt = 0; mt < p.MT; ++mt) {
+#pragma unroll
+            for (int g = 0; g < 9; ++g) {
+              if (g < p.ngrp) {
+                const uint32_t goff = (p.kx == 3) ? (uint32_t)(g / 3) * plane + (uint32_t)(g % 3) * HZ : (uint32_t)g * HZ;
+                umma_bf16(d, ((uint64_t)a_hi << 32) | (a_m + goff), ((uint64_t)b_hi << 32) | (b_slot + (uint32_t)g * bgroup), idesc,
+                          g ? 1u : (uint32_t)c);
+              }
+            }
+            d += (uint32_t)N3;
+            a_m += 96u;                                                               // next tile: 96 frame rows further
+          }
+          umma_commit(empty_a + 8 * ra.s);
+          umma_commit(empty_b + 8 * rb.s);
+          ra.advance(p.SA);
+          rb.advance(p.SB);
+        }
+        umma_commit(tmem_full + 8 * rt.s);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    Ring rt;
+    const long long S = (long long)p.X * p.Y * p.Z;
+    const int grp = q * 4 + (lane >> 3), k8 = lane & 7;                               // tile row i = 32q + lane = 8*grp + k8
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, rt.advance(p.AS)) {
+      const int brick = item / p.NS, n0 = (item - brick * p.NS) * p.Ns;
+      const int n = brick / bricks_per_n;
+      int r = brick - n * bricks_per_n;
+      const int bz = r % p.nbz; r /= p.nbz;
+      const int by = r % p.nby;
+      const int bx = r / p.nby;
+      mbar_wait(tmem_full + 8 * rt.s, rt.ph);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + rt.s * (uint32_t)(p.MT * N3) + ((uint32_t)(q * 32) << 16);
+      for (int mt = 0; mt < p.MT; ++mt) {
+        const int L = mt * 96 + grp * 6 + k8;                                         // frame row of this lane
+        const int iz = L % p.HZ;
+        const int ry = L / p.HZ;
+        const int iy = ry % p.HY, ix = ry / p.HY;
+        const int x = bx * p.BX + ix, y = by * p.BY + iy, z = bz * p.BZ + iz;
+        const bool valid = (k8 < 6) && (ix < p.BX) && (iy < p.BY) && (iz < p.BZ) && (x < p.X) && (y < p.Y) && (z < p.Z);
+        const long long sp = ((long long)x * p.Y + y) * p.Z + z;
+        for (int c16 = 0; c16 < p.Ns; c16 += 16) {
+          uint32_t v0[16], v1[16], v2[16];
+          tmem_ld16(d0 + (uint32_t)(mt * N3 + c16), v0);
+          tmem_ld16(d0 + (uint32_t)(mt * N3 + p.Ns + c16), v1);
+          tmem_ld16(d0 + (uint32_t)(mt * N3 + 2 * p.Ns + c16), v2);
+          tmem_ld_wait();
+          float f[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const float a1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[k]), 1, 8);   // D'[r+1][dz=1]
+            const float a2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[k]), 2, 8);   // D'[r+2][dz=2]
+            f[k] = (__uint_as_float(v0[k]) + a1) + a2 + (bias ? __ldg(bias + n0 + c16 + k) : 0.f);
+          }
+          if (valid) {
+            uint4* dst = out + ((long long)n * Cob + ((n0 + c16) >> 3)) * S + sp;
+            dst[0] = pack8(f);
+            dst[S] = pack8(f + 8);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + 8 * rt.s);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// =========================================================================================================
 // stride-2 family on tensor cores ("tap GEMM"): 2x2x2 stride-2 conv (gather) and transposed conv (scatter).
 //   rows = voxels of the HALF-resolution grid, compact per brick (no halo, no dropped rows except tile padding)
 //   gather : out_half[o][co]        = sum_t sum_ci in_full[2o+t][ci] * W[t][ci][co]
@@ -1331,6 +1506,130 @@ int bcp_conv_tc_fwd_stats(const void* in, const void* wpack, const float* bias, 
   sa.running_mean = running_mean; sa.running_var = running_var; sa.nbt = num_batches_tracked;
   sa.stat = stat; sa.coef = coef; sa.spg = spg; sa.G = n / spg; sa.eps = eps; sa.momentum = momentum;
   return conv_tc_launch(in, wpack, bias, out, n, cin, cout, dims, kernel, &sa, stream);
+}
+
+// ---- EXPERIMENTAL dz-folded forward (conv_tc_fold_kernel): brick plan + launch.  Not used unless ops.py is told to.
+static bool fold_shape_ok(int cin, int cout, const int* dims, const int* kernel) {
+  if (!shape_ok(cin, cout, dims, kernel)) return false;
+  return cout == 16 || cout == 32;                 // N = 3*Cout <= 96; wider layers are already near the tensor rate
+}
+
+static bool fold_plan(FoldParams& p, int nsm) {
+  const int T = p.kx * 9;
+  p.ngrp = T / 3;
+  p.nchunks = p.Cin / 16;
+  p.NS = 1; p.Ns = p.Cout;
+  const int N3 = 3 * p.Ns;
+  const unsigned stageB = (unsigned)p.ngrp * 2u * (unsigned)N3 * 16u;
+  const double per_mma = (N3 / 2.0 > 32.0 + N3 / 4.0) ? N3 / 2.0 : 32.0 + N3 / 4.0;
+  double best = 1e300;
+  bool found = false;
+  FoldParams bp = p;
+  int bz_opts[4];
+  int nz = 0;
+  for (int d = 1; d <= 8 && nz < 4; d *= 2) {
+    const int bz = (p.Z + d - 1) / d;
+    if (bz + 2 <= 256 && (nz == 0 || bz_opts[nz - 1] != bz)) bz_opts[nz++] = bz;
+  }
+  for (int zi = 0; zi < nz; ++zi) {
+    const int BZ = bz_opts[zi], HZ = BZ + 2;
+    for (int BY = 1; BY <= p.Y && BY + 2 <= 256; ++BY) {
+      const int HY = BY + 2;
+      const int bxmax = (p.kx == 1) ? 1 : p.X;
+      for (int BX = 1; BX <= bxmax; ++BX) {
+        const int HX = BX + p.kx - 1;
+        const long long rows_h = (long long)HX * HY * HZ;
+        if (rows_h >= 16384) break;
+        const long long lmax = ((long long)(BX - 1) * HY + (BY - 1)) * HZ + BZ;
+        const int MT = (int)((lmax + 95) / 96);
+        int AS = 2;
+        if (2 * MT * N3 > 512) AS = 1;
+        if (MT * N3 > 512) break;
+        // rows the MMAs may touch: last tile start + 98 rows + the largest (dx,dy) shift
+        const long long rows_alloc = 96ll * (MT - 1) + 98 + ((long long)(p.kx - 1) * HY + 2) * HZ;
+        const long long slotA = ((rows_h + (rows_alloc > rows_h ? rows_alloc : rows_h)) * 16 + 127) / 128 * 128;
+        int SB = 2;
+        int SA = (int)(((long long)SMEM_BUDGET - 1024 - (long long)SB * stageB) / slotA);
+        if (SA < 2) break;
+        if (SA > 3) SA = 3;
+        SB = (int)(((long long)SMEM_BUDGET - 1024 - (long long)SA * slotA) / stageB);
+        if (SB > 4) SB = 4;
+        const int nbx = (p.X + BX - 1) / BX, nby = (p.Y + BY - 1) / BY, nbz = (p.Z + BZ - 1) / BZ;
+        const long long nb = (long long)p.N * nbx * nby * nbz;
+        const long long waves = (nb + nsm - 1) / nsm;
+        const double mma_cyc = (double)MT * p.ngrp * p.nchunks * per_mma;
+        const double epi_cyc = (double)MT * (p.Ns / 16) * 900.0;            // three TMEM loads + 32 shuffles per 16 channels
+        const double item_bytes = (double)rows_h * p.Cin * 2.0 + (double)stageB * p.nchunks;
+        const double load_cyc = item_bytes / 40.0;
+        double per_item = mma_cyc > load_cyc ? mma_cyc : load_cyc;
+        per_item = (AS == 2) ? (per_item > epi_cyc ? per_item : epi_cyc) : per_item + epi_cyc;
+        const double l2_bound = (double)nb * item_bytes / 2500.0;
+        const double t_sm = (double)waves * (per_item + 1500.0);
+        const double cost = t_sm > l2_bound ? t_sm : l2_bound;
+        if (cost < best) {
+          best = cost; found = true; bp = p;
+          bp.BX = BX; bp.BY = BY; bp.BZ = BZ; bp.HX = HX; bp.HY = HY; bp.HZ = HZ;
+          bp.nbx = nbx; bp.nby = nby; bp.nbz = nbz; bp.nbricks = (int)nb;
+          bp.rows_h = (int)rows_h; bp.MT = MT; bp.SA = SA; bp.SB = SB; bp.AS = AS;
+          bp.slotA_bytes = (unsigned)slotA; bp.stageB_bytes = stageB;
+        }
+      }
+    }
+  }
+  if (!found) return false;
+  p = bp;
+  int cols = 32;
+  while (cols < p.AS * p.MT * N3) cols *= 2;
+  p.tmem_cols = cols;
+  p.offA = 0;
+  p.offB = p.SA * p.slotA_bytes;
+  p.offBar = p.offB + p.SB * p.stageB_bytes;
+  return true;
+}
+
+int bcp_conv_tc_fold_supported(int cin, int cout, const int* dims, const int* kernel) {
+  if (!dims || !kernel || !fold_shape_ok(cin, cout, dims, kernel)) return 0;
+  return get_encode() != nullptr ? 1 : 0;
+}
+
+int bcp_conv_tc_fold_fwd(const void* in, const void* wpack, const float* bias, void* out, int n, int cin, int cout,
+                         const int* dims, const int* kernel, cudaStream_t stream) {
+  BCP_REQUIRE(in && wpack && out && dims && kernel, "conv_tc_fold_fwd: null pointer");
+  if (!fold_shape_ok(cin, cout, dims, kernel)) { set_last_error("conv_tc_fold_fwd: unsupported shape"); return BCP_ERR_UNSUPPORTED; }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_last_error("conv_tc_fold_fwd: cuTensorMapEncodeTiled unavailable"); return BCP_ERR_CUDA; }
+  FoldParams p{};
+  p.N = n; p.X = dims[0]; p.Y = dims[1]; p.Z = dims[2]; p.Cin = cin; p.Cout = cout; p.kx = kernel[0];
+  const int nsm = sm_count();
+  if (!fold_plan(p, nsm)) { set_last_error("conv_tc_fold_fwd: no brick shape fits"); return BCP_ERR_UNSUPPORTED; }
+  CUtensorMap tmap, tmap_w;
+  CUresult cr = encode_cb8(enc, &tmap, in, p.Z, p.Y, p.X, (long long)n * (cin / 8), p.HZ, p.HY, p.HX, 2, &p.mergedA);
+  if (cr != CUDA_SUCCESS) { set_last_error("conv_tc_fold_fwd: tensor map failed (%d)", (int)cr); return BCP_ERR_CUDA; }
+  {
+    // pack [T][Cin/8][Cout][8] bf16 with t = g*3 + dz, seen as 8-byte elements: dims (inner -> outer) cout*2, dz, plane, g
+    // (the dz stride is larger than the plane stride; if the driver rejects non-monotonic strides, add a repack kind
+    // that stores [g][Cin/8][dz][Cout][8] instead)
+    const cuuint64_t tap_bytes = (cuuint64_t)(cin / 8) * cout * 16;
+    const cuuint64_t wdim[4] = {(cuuint64_t)cout * 2, 3, (cuuint64_t)(cin / 8), (cuuint64_t)p.ngrp};
+    const cuuint64_t wstr[3] = {tap_bytes, (cuuint64_t)cout * 16, 3 * tap_bytes};
+    const cuuint32_t wbox[4] = {(cuuint32_t)p.Ns * 2, 3, 2, (cuuint32_t)p.ngrp};
+    const cuuint32_t wes[4] = {1, 1, 1, 1};
+    cr = enc(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(wpack), wdim, wstr, wbox, wes, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { set_last_error("conv_tc_fold_fwd: weight tensor map failed (%d)", (int)cr); return BCP_ERR_CUDA; }
+  }
+  const size_t smem = (size_t)p.offBar + 8 * (2 * p.SA + 2 * p.SB + 2 * p.AS) + 16 + 128;
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(conv_tc_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (attr_err != cudaSuccess) cudaGetLastError();
+  });
+  if (attr_err != cudaSuccess) { set_last_error("conv_tc_fold_fwd: cudaFuncSetAttribute failed"); return BCP_ERR_CUDA; }
+  BCP_REQUIRE(smem <= 226 * 1024, "conv_tc_fold_fwd: shared memory plan overflow");
+  const int grid = p.nbricks < nsm ? p.nbricks : nsm;
+  conv_tc_fold_kernel<<<grid, TC_THREADS, smem, stream>>>(tmap, tmap_w, bias, (uint4*)out, p);
+  return check_launch("conv_tc_fold_fwd");
 }
 
 int bcp_conv_tc_wgrad_supported(int cin, int cout, const int* dims, const int* kernel) {

@@ -21,6 +21,8 @@ _TC_WGRAD = _TC_FWD and os.environ.get("BCP_DISABLE_TC_WGRAD", "0") != "1"
 # conv epilogue produces the following norm's statistics (bcp_conv_tc_fwd_stats).  Opt-in: parity-tested, but on the LA step
 # the fused epilogue + last-CTA finalize cost about what the (now 4-loads-in-flight) standalone statistics pass costs.
 _FUSE_STATS = os.environ.get("BCP_FUSED_STATS", "0") == "1"
+# experimental dz-folded forward kernel for 16/32-channel layers; first GPU run pending
+_TC_FOLD = os.environ.get("BCP_TC_FOLD", "0") == "1"
 
 
 def _require_cuda(t: torch.Tensor, what: str):
@@ -129,7 +131,9 @@ def _conv_same(a, wpack, bias, cout, kernel, allow_tc=True):
     n, cin, x, y, z = act_dims(a)
     out = torch.empty(cb8_shape(n, cout, x, y, z), dtype=BF16, device=a.device)
     dims, k = i3(x, y, z), i3(*kernel)
-    if allow_tc and _TC_FWD and LIB.query("bcp_conv_tc_supported", cin, cout, dims, k):
+    if allow_tc and _TC_FWD and _TC_FOLD and LIB.query("bcp_conv_tc_fold_supported", cin, cout, dims, k):
+        LIB.call("bcp_conv_tc_fold_fwd", ptr(a), ptr(wpack), ptr(bias), ptr(out), n, cin, cout, dims, k, stream())
+    elif allow_tc and _TC_FWD and LIB.query("bcp_conv_tc_supported", cin, cout, dims, k):
         LIB.call("bcp_conv_tc_fwd", ptr(a), ptr(wpack), ptr(bias), ptr(out), n, cin, cout, dims, k, stream())
     else:
         LIB.call("bcp_conv_direct_fwd", ptr(a), ptr(wpack), ptr(bias), ptr(out), n, cin, cout, dims, k,

@@ -167,6 +167,11 @@ int bcp_conv_tc_fwd_stats(const void* in, const void* wpack, const float* bias, 
                           const int* dims, const int* kernel, const float* gamma, const float* beta, float* running_mean,
                           float* running_var, long long* num_batches_tracked, float* stat, float* coef, void* workspace,
                           int* counter, int spg, float eps, float momentum, cudaStream_t stream);
+/* EXPERIMENTAL (not on the default path, first GPU run pending): the same convolution for Cout in {16, 32} with the three
+ * dz taps folded into the MMA N dimension.  Same arguments and packs as bcp_conv_tc_fwd. */
+int bcp_conv_tc_fold_supported(int cin, int cout, const int* dims, const int* kernel);
+int bcp_conv_tc_fold_fwd(const void* in, const void* wpack, const float* bias, void* out, int n, int cin, int cout,
+                         const int* dims, const int* kernel, cudaStream_t stream);
 /* debug only: when `buffer` (device, 16 x uint64 per CTA, >= 148 CTAs) is non-null, bcp_conv_tc_fwd launches the
  * instrumented kernel variant that records per-role wait cycles; pass NULL to return to the product kernel. */
 int bcp_conv_tc_debug_profile(void* buffer);
