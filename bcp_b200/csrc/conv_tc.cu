@@ -502,7 +502,10 @@ struct FoldParams {
   int mergedA;
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+constexpr int FOLD_EPI_WARPS = 8;                    // epilogue warps (multiple of 4: TMEM lane quarter = warp % 4); 2 tile subsets
+constexpr int FOLD_THREADS = 64 + 32 * FOLD_EPI_WARPS;
+
+__global__ void __launch_bounds__(FOLD_THREADS, 1)
 conv_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_w,
                     const float* __restrict__ bias, uint4* __restrict__ out, const FoldParams p) {
   extern __shared__ unsigned char smem_raw[];
@@ -516,7 +519,7 @@ conv_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.SA; ++i) { mbar_init(full_a + 8 * i, 1); mbar_init(empty_a + 8 * i, 1); }
     for (int i = 0; i < p.SB; ++i) { mbar_init(full_b + 8 * i, 1); mbar_init(empty_b + 8 * i, 1); }
-    for (int i = 0; i < p.AS; ++i) { mbar_init(tmem_full + 8 * i, 1); mbar_init(tmem_empty + 8 * i, 4); }
+    for (int i = 0; i < p.AS; ++i) { mbar_init(tmem_full + 8 * i, 1); mbar_init(tmem_empty + 8 * i, FOLD_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
@@ -603,10 +606,14 @@ conv_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     }
     __syncwarp();
   } else {
-    const int q = warp & 3;
+    // FOLD_EPI_WARPS epilogue warps: warp w reads TMEM lane quarter w % 4 and takes the tiles mt = sub, sub + nsub, ...
+    // The frame row of a lane advances by 96*nsub per step; (ix,iy,iz) follow incrementally (no per-row divisions).
+    const int q = warp & 3, sub = (warp - 2) >> 2, nsub = FOLD_EPI_WARPS / 4;
     Ring rt;
     const long long S = (long long)p.X * p.Y * p.Z;
     const int grp = q * 4 + (lane >> 3), k8 = lane & 7;                               // tile row i = 32q + lane = 8*grp + k8
+    const int step = 96 * nsub;
+    const int sz = step % p.HZ, sy = (step / p.HZ) % p.HY, sx = (step / p.HZ) / p.HY;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x, rt.advance(p.AS)) {
       const int brick = item / p.NS, n0 = (item - brick * p.NS) * p.Ns;
       const int n = brick / bricks_per_n;
@@ -617,11 +624,9 @@ conv_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
       mbar_wait(tmem_full + 8 * rt.s, rt.ph);
       tc_fence_after();
       const uint32_t d0 = tmem_base + rt.s * (uint32_t)(p.MT * N3) + ((uint32_t)(q * 32) << 16);
-      for (int mt = 0; mt < p.MT; ++mt) {
-        const int L = mt * 96 + grp * 6 + k8;                                         // frame row of this lane
-        const int iz = L % p.HZ;
-        const int ry = L / p.HZ;
-        const int iy = ry % p.HY, ix = ry / p.HY;
+      const int L0 = sub * 96 + grp * 6 + k8;                                          // frame row of this lane in its first tile
+      int iz = L0 % p.HZ, iy = (L0 / p.HZ) % p.HY, ix = (L0 / p.HZ) / p.HY;
+      for (int mt = sub; mt < p.MT; mt += nsub) {
         const int x = bx * p.BX + ix, y = by * p.BY + iy, z = bz * p.BZ + iz;
         const bool valid = (k8 < 6) && (ix < p.BX) && (iy < p.BY) && (iz < p.BZ) && (x < p.X) && (y < p.Y) && (z < p.Z);
         const long long sp = ((long long)x * p.Y + y) * p.Z + z;
@@ -644,6 +649,11 @@ conv_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
             dst[S] = pack8(f + 8);
           }
         }
+        iz += sz;
+        if (iz >= p.HZ) { iz -= p.HZ; ++iy; }
+        iy += sy;
+        if (iy >= p.HY) { iy -= p.HY; ++ix; }
+        ix += sx;
       }
       tc_fence_before();
       __syncwarp();
@@ -1628,7 +1638,7 @@ int bcp_conv_tc_fold_fwd(const void* in, const void* wpack, const float* bias, v
   if (attr_err != cudaSuccess) { set_last_error("conv_tc_fold_fwd: cudaFuncSetAttribute failed"); return BCP_ERR_CUDA; }
   BCP_REQUIRE(smem <= 226 * 1024, "conv_tc_fold_fwd: shared memory plan overflow");
   const int grid = p.nbricks < nsm ? p.nbricks : nsm;
-  conv_tc_fold_kernel<<<grid, TC_THREADS, smem, stream>>>(tmap, tmap_w, bias, (uint4*)out, p);
+  conv_tc_fold_kernel<<<grid, FOLD_THREADS, smem, stream>>>(tmap, tmap_w, bias, (uint4*)out, p);
   return check_launch("conv_tc_fold_fwd");
 }
 
