@@ -183,6 +183,33 @@ if __name__ == "__main__":
                     (2, 128, 256, (3, 4, 2)), (4, 16, 32, (56, 56, 40)), (4, 128, 256, (7, 7, 5))]:
             ws = max(ws, run_s2(*cfg))
         print("WORST s2 tc_vs_torch", ws, flush=True)
+    if "--fold" in sys.argv:
+        # experimental dz-folded kernel (BCP_TC_FOLD path) against the standard tcgen05 kernel: error vs torch and time
+        for cfg in [(1, 16, 16, (4, 6, 8)), (2, 16, 16, (8, 12, 20)), (2, 32, 32, (6, 10, 12)), (4, 16, 16, (112, 112, 80)),
+                    (4, 32, 32, (56, 56, 40))]:
+            n, cin, cout, dims = cfg
+            kernel = (3, 3, 3)
+            torch.manual_seed(0)
+            x = torch.randn(n, cin, *dims, device=dev).to(torch.bfloat16).float()
+            w = (torch.randn(cout, cin, *kernel, device=dev) / np.sqrt(cin * 27)).to(torch.bfloat16).float()
+            b = 0.1 * torch.randn(cout, device=dev)
+            pack = _packs(ops, dev, w, (0, 1))
+            a = cb8_from_planar(x)
+            ref = F.conv3d(x, w, b, padding=1)
+            res = {}
+            for name, flag in (("std", False), ("fold", True)):
+                ops._TC_FOLD = flag
+                y = ops._conv_same(a, pack.k[0], b, cout, kernel)
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+                ev[0].record()
+                for _ in range(10):
+                    ops._conv_same(a, pack.k[0], b, cout, kernel)
+                ev[1].record()
+                torch.cuda.synchronize()
+                res[name] = (rel_rms(planar_from_cb8(y, cout), ref), ev[0].elapsed_time(ev[1]) * 100.0)
+            ops._TC_FOLD = False
+            print(f"[fold] n={n} c={cin}->{cout} dims={dims} std err {res['std'][0]:.2e} {res['std'][1]:.1f} us | "
+                  f"fold err {res['fold'][0]:.2e} {res['fold'][1]:.1f} us", flush=True)
     if "--prof" in sys.argv:
         for cfg in [(4, 16, (112, 112, 80)), (4, 32, (56, 56, 40)), (4, 64, (28, 28, 20)), (4, 128, (14, 14, 10)), (4, 256, (7, 7, 5))]:
             run_prof(*cfg)
