@@ -18,6 +18,8 @@ Every function cites the reference file:line it follows (paths relative to
 """
 from __future__ import annotations
 
+import math
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -544,6 +546,46 @@ def pan_self_train_step(net, ema_net, optimizer, img_a, lab_a, img_b, lab_b, uni
     update_ema_variables(net, ema_net, alpha)
     return dict(loss=loss.detach(), loss_1=loss_1.detach(), loss_2=loss_2.detach(), box=box,
                 plab_a=plab_a, plab_b=plab_b, out_1=out_1.detach(), out_2=out_2.detach())
+
+
+# --------------------------------------------------------------------------------------
+# sliding-window validation (utils/test_3d_patch.py:82-141)
+# --------------------------------------------------------------------------------------
+def sliding_window_predict(model, image: np.ndarray, stride_xy: int, stride_z: int, patch_size, num_classes: int = 1):
+    """test_single_case: zero-pad the volume up to the patch size (split evenly, extra voxel on the high side), visit
+    windows on a stride grid whose last window is clamped to the border, add the class-1 softmax probability of every
+    window into a score map (broadcast over `num_classes` planes) and a visit count, threshold the mean at 0.5.
+    Returns (label_map int64 [w,h,d], score_map float32 [num_classes,w,h,d]) cropped back to the input size."""
+    w, h, d = image.shape
+    pads = [max(patch_size[i] - image.shape[i], 0) for i in range(3)]
+    lo = [p // 2 for p in pads]
+    if any(pads):
+        image = np.pad(image, [(lo[i], pads[i] - lo[i]) for i in range(3)], mode="constant", constant_values=0)
+    ww, hh, dd = image.shape
+    nx = math.ceil((ww - patch_size[0]) / stride_xy) + 1
+    ny = math.ceil((hh - patch_size[1]) / stride_xy) + 1
+    nz = math.ceil((dd - patch_size[2]) / stride_z) + 1
+    score = np.zeros((num_classes,) + image.shape, np.float32)
+    cnt = np.zeros(image.shape, np.float32)
+    for ixw in range(nx):
+        xs = min(stride_xy * ixw, ww - patch_size[0])
+        for iyw in range(ny):
+            ys = min(stride_xy * iyw, hh - patch_size[1])
+            for izw in range(nz):
+                zs = min(stride_z * izw, dd - patch_size[2])
+                patch = image[xs:xs + patch_size[0], ys:ys + patch_size[1], zs:zs + patch_size[2]].astype(np.float32)
+                with torch.no_grad():
+                    logits, _ = model(torch.from_numpy(patch[None, None]))
+                    prob = F.softmax(logits, dim=1)[0, 1].numpy()
+                sl = (slice(None), slice(xs, xs + patch_size[0]), slice(ys, ys + patch_size[1]), slice(zs, zs + patch_size[2]))
+                score[sl] = score[sl] + prob
+                cnt[sl[1:]] = cnt[sl[1:]] + 1
+    score = score / cnt[None]
+    label = (score[0] > 0.5).astype(np.int64)
+    if any(pads):
+        label = label[lo[0]:lo[0] + w, lo[1]:lo[1] + h, lo[2]:lo[2] + d]
+        score = score[:, lo[0]:lo[0] + w, lo[1]:lo[1] + h, lo[2]:lo[2] + d]
+    return label, score
 
 
 # --------------------------------------------------------------------------------------

@@ -401,6 +401,33 @@ def gen_pan_pre_step():
     print("pan pre step", float(loss))
 
 
+def gen_sliding_window():
+    """utils/test_3d_patch.py:82-141 (test_single_case), function source taken verbatim from the reference file; the two
+    cases exercise the clamped last window and the pad-then-crop branch."""
+    import math
+    ns, glb = ref_shims.extract_defs(os.path.join(ref_shims.REF_CODE, "utils", "test_3d_patch.py"), ["test_single_case"])
+    glb["math"] = math
+    had = hasattr(np, "int")
+    if not had:
+        np.int = int                       # the reference predates numpy 1.24 (uses np.int); restored below
+    try:
+        model = R.net_factory.net_factory("VNet", 1, 2, "test")
+        O.fill_state_dict_(model, 171)
+        model.eval()
+        out = {}
+        for tag, shape in (("a", (60, 56, 52)), ("b", (40, 50, 48))):
+            img = O.synthetic_volume(shape, 172 if tag == "a" else 173).numpy()
+            label, score = ns.test_single_case(model, img, 18, 4, (48, 48, 48), num_classes=2)
+            out[tag + "_label"] = label.astype(np.uint8)
+            out[tag + "_score"] = score.astype(np.float32)[0, ::2, ::2, ::2]
+            out[tag + "_shape"] = np.array(shape)
+            print("sliding window", tag, shape, "positive fraction", float(label.mean()))
+    finally:
+        if not had:
+            del np.int
+    save("sliding_window", **out)
+
+
 def gen_pan_step():
     t0 = time.time()
     net, ema = R.pan_Vnet.VNet(), R.pan_Vnet.VNet()
@@ -444,7 +471,9 @@ def gen_pan_step():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["functions", "networks", "la_small", "la_pre", "acdc", "la_full", "pan", "acdc_pre", "pan_pre"]
+    which = sys.argv[1:] or ["functions", "networks", "la_small", "la_pre", "acdc", "la_full", "pan", "acdc_pre", "pan_pre", "sliding"]
+    if "sliding" in which:
+        gen_sliding_window()
     if "acdc_pre" in which:
         gen_acdc_pre_step()
     if "pan_pre" in which:

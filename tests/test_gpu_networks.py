@@ -353,3 +353,24 @@ def test_pan_pre_step(dev):
     record("pan_pre_loss_rel_err", rel)
     assert rel <= LOSS_TOL
     assert rel_rms(r["out"].cpu()[..., ::4, ::4, ::4], T(g["out"])) <= 2 * TRAIN_SMALL_TOL
+
+
+@_PENDING
+def test_sliding_window_validation(dev):
+    """device-side test_single_case against the reference-minted fixture."""
+    from bcp_b200.networks.net_factory import net_factory
+    from bcp_b200.utils.test_3d_patch import test_single_case as native_single_case
+    g = load_golden("sliding_window")
+    model = net_factory("VNet", 1, 2, "test")
+    O.fill_state_dict_(model, 171)
+    model.eval()
+    for tag, seed in (("a", 172), ("b", 173)):
+        shape = tuple(int(v) for v in g[tag + "_shape"])
+        img = O.synthetic_volume(shape, seed).numpy()
+        label, score = native_single_case(model, img, 18, 4, (48, 48, 48), num_classes=2)
+        assert label.shape == shape and score.shape == (2,) + shape
+        err = np.abs(score[0, ::2, ::2, ::2] - g[tag + "_score"])
+        record(f"sliding_window_{tag}_score_abs_err_max", float(err.max()))
+        assert err.max() <= 3e-2                      # bf16 activations in eval mode: logits carry ~6e-3 relative noise
+        sure = np.abs(score[0] - 0.5) > 5e-2
+        assert np.array_equal(label[sure], g[tag + "_label"][sure].astype(np.int64))

@@ -302,3 +302,21 @@ def test_pan_pre_step():
     close(r["loss_dice"], g["loss_dice"], rtol=2e-5)
     close(r["out"][..., ::4, ::4, ::4], g["out"], rtol=1e-3, atol=1e-3)
     digests_close(digest_named(net.state_dict()), g["model_digest"], rtol=2e-3)
+
+
+def test_sliding_window_validation():
+    """utils/test_3d_patch.py:82-141 (test_single_case) -- clamped last window and pad/crop."""
+    g = load("sliding_window")
+    model = O.net_factory("VNet", 1, 2, "test")
+    O.fill_state_dict_(model, 171)
+    model.eval()
+    for tag, seed in (("a", 172), ("b", 173)):
+        shape = tuple(int(v) for v in g[tag + "_shape"])
+        img = O.synthetic_volume(shape, seed).numpy()
+        label, score = O.sliding_window_predict(model, img, 18, 4, (48, 48, 48), num_classes=2)
+        assert label.shape == shape and score.shape == (2,) + shape
+        close(score[0, ::2, ::2, ::2], g[tag + "_score"], rtol=1e-4, atol=1e-5)
+        # voxels whose mean probability sits within float noise of the 0.5 threshold may flip; everything else is exact
+        sure = np.abs(score[0] - 0.5) > 1e-4
+        assert np.array_equal(label[sure], g[tag + "_label"][sure].astype(np.int64))
+        assert (~sure).mean() < 1e-3
