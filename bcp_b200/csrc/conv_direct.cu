@@ -365,17 +365,19 @@ __global__ void __launch_bounds__(128) conv_first_wgrad_partial_kernel(const flo
   }
 }
 
+// one WARP per output element: lanes stride the chunk list (independent loads in flight), fixed butterfly => deterministic
 __global__ void conv_first_wgrad_finalize_kernel(const float* __restrict__ partial, float* __restrict__ dw, int chunks,
                                                  int Cout, int kx, int ky, int kz, int accumulate) {
   const int Cob = (Cout + 7) / 8, T = kx * ky * kz;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (i >= Cout * T) return;
   const int co = i / T, t = i % T;
   const int tz = t % kz, ty = (t / kz) % ky, tx = t / (kz * ky);
   const int cob = co >> 3, j = co & 7;
   float s = 0.f;
-  for (int c = 0; c < chunks; ++c) s += partial[(((long long)c * Cob + cob) * kx + tx) * 72 + (ty * 3 + tz) * 8 + j];
-  dw[i] = accumulate ? dw[i] + s : s;
+  for (int c = lane; c < chunks; c += 32) s += partial[(((long long)c * Cob + cob) * kx + tx) * 72 + (ty * 3 + tz) * 8 + j];
+  s = warp_sum(s);
+  if (lane == 0) dw[i] = accumulate ? dw[i] + s : s;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -498,22 +500,25 @@ __global__ void __launch_bounds__(128) head_wgrad_partial_kernel(const uint4* __
   }
 }
 
+// one WARP per output element (see conv_first_wgrad_finalize_kernel)
 template <int NC>
 __global__ void head_wgrad_finalize_kernel(const float* __restrict__ partial, float* __restrict__ dw, float* __restrict__ db,
                                            int chunks, int T, int Cin, int accumulate) {
   const int Cib = (Cin + 7) / 8;
   constexpr int K = NC * 8 + NC;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (i < NC * Cin * T) {
     const int t = i % T, ci = (i / T) % Cin, k = i / (T * Cin);
     float s = 0.f;
-    for (int c = 0; c < chunks; ++c) s += partial[(((long long)c * T + t) * Cib + (ci >> 3)) * K + k * 8 + (ci & 7)];
-    dw[i] = accumulate ? dw[i] + s : s;
+    for (int c = lane; c < chunks; c += 32) s += partial[(((long long)c * T + t) * Cib + (ci >> 3)) * K + k * 8 + (ci & 7)];
+    s = warp_sum(s);
+    if (lane == 0) dw[i] = accumulate ? dw[i] + s : s;
   } else if (i < NC * Cin * T + NC && db) {
     const int k = i - NC * Cin * T;
     float s = 0.f;
-    for (int c = 0; c < chunks; ++c) s += partial[(((long long)c * T + 0) * Cib + 0) * K + NC * 8 + k];
-    db[k] = accumulate ? db[k] + s : s;
+    for (int c = lane; c < chunks; c += 32) s += partial[(((long long)c * T + 0) * Cib + 0) * K + NC * 8 + k];
+    s = warp_sum(s);
+    if (lane == 0) db[k] = accumulate ? db[k] + s : s;
   }
 }
 
@@ -641,7 +646,7 @@ int bcp_conv_first_wgrad(const float* in, const void* outgrad, float* dw, float*
   dim3 grid(per_n, n, Cob * g.kx);
   conv_first_wgrad_partial_kernel<<<grid, 128, 0, stream>>>(in, (const uint4*)outgrad, workspace, g, cout);
   const int T = g.kx * g.ky * g.kz;
-  conv_first_wgrad_finalize_kernel<<<(cout * T + 127) / 128, 128, 0, stream>>>(workspace, dw, chunks, cout, g.kx, g.ky, g.kz, accumulate);
+  conv_first_wgrad_finalize_kernel<<<(cout * T * 32 + 127) / 128, 128, 0, stream>>>(workspace, dw, chunks, cout, g.kx, g.ky, g.kz, accumulate);
   return check_launch("conv_first_wgrad");
 }
 
@@ -702,7 +707,7 @@ int bcp_head_wgrad(const void* in, const float* dlogits, float* dw, float* db, f
   dim3 grid(chunks, Cib, T);
   HEAD_DISPATCH(ncls, (head_wgrad_partial_kernel<NC><<<grid, 128, 0, stream>>>((const uint4*)in, dlogits, workspace, g, cin)));
   const int nout = ncls * cin * T + ncls;
-  HEAD_DISPATCH(ncls, (head_wgrad_finalize_kernel<NC><<<(nout + 127) / 128, 128, 0, stream>>>(workspace, dw, db, chunks, T, cin, accumulate)));
+  HEAD_DISPATCH(ncls, (head_wgrad_finalize_kernel<NC><<<(nout * 32 + 127) / 128, 128, 0, stream>>>(workspace, dw, db, chunks, T, cin, accumulate)));
   return check_launch("head_wgrad");
 }
 

@@ -505,9 +505,14 @@ struct FoldParams {
 constexpr int FOLD_EPI_WARPS = 8;                    // epilogue warps (multiple of 4: TMEM lane quarter = warp % 4); 2 tile subsets
 constexpr int FOLD_THREADS = 64 + 32 * FOLD_EPI_WARPS;
 
+template <bool PROF>
 __global__ void __launch_bounds__(FOLD_THREADS, 1)
 conv_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_w,
-                    const float* __restrict__ bias, uint4* __restrict__ out, const FoldParams p) {
+                    const float* __restrict__ bias, uint4* __restrict__ out, const FoldParams p,
+                    unsigned long long* __restrict__ prof) {
+  // PROF: per-CTA cycle counters (same slots as conv_tc_kernel<true, .>), tools/debug_conv_tc.py --prof-fold only
+  long long t_start = 0, w0 = 0, w1 = 0, w2 = 0;
+  if (PROF) t_start = clock64();
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
   const uint32_t sbase = smem_u32(smem);
@@ -549,8 +554,8 @@ conv_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
       const int bx = r / p.nby;
       const int x0 = bx * p.BX - (p.kx >> 1), y0 = by * p.BY - 1, z0 = bz * p.BZ - 1;
       for (int c = 0; c < p.nchunks; ++c) {
-        mbar_wait(empty_a + 8 * ra.s, ra.ph ^ 1);
-        mbar_wait(empty_b + 8 * rb.s, rb.ph ^ 1);
+        { long long t0 = PROF ? clock64() : 0; mbar_wait(empty_a + 8 * ra.s, ra.ph ^ 1); if (PROF) w0 += clock64() - t0; }
+        { long long t0 = PROF ? clock64() : 0; mbar_wait(empty_b + 8 * rb.s, rb.ph ^ 1); if (PROF) w1 += clock64() - t0; }
         if (elect_one()) {
           mbar_expect_tx(full_a + 8 * ra.s, a_bytes);
           tma_load_cb8(a_base + ra.s * p.slotA_bytes, &tmap, full_a + 8 * ra.s, p.mergedA, z0, y0, x0, n * Cib + 2 * c);
@@ -563,6 +568,7 @@ conv_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
         rb.advance(p.SB);
       }
     }
+    if (PROF && lane == 0) { prof[blockIdx.x * 16 + 1] = w0; prof[blockIdx.x * 16 + 2] = w1; }
   } else if (warp == 1) {
     if (elect_one()) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N3 >> 3) << 17) | ((128u >> 4) << 24);
@@ -573,13 +579,14 @@ conv_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
       const uint32_t HZ = (uint32_t)p.HZ, plane = (uint32_t)(p.HY * p.HZ);
       const uint32_t bgroup = 2u * (uint32_t)N3;                                    // 16-byte units per (dx,dy) group: 2 planes x 3*Ns rows
       Ring ra, rb, rt;
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x, rt.advance(p.AS)) {
-        mbar_wait(tmem_empty + 8 * rt.s, rt.ph ^ 1);
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x, rt.advance(p.AS), ++it) {
+        { long long t0 = PROF ? clock64() : 0; mbar_wait(tmem_empty + 8 * rt.s, rt.ph ^ 1); if (PROF) w2 += clock64() - t0; }
         tc_fence_after();
         const uint32_t d0 = tmem_base + rt.s * (uint32_t)(p.MT * N3);
         for (int c = 0; c < p.nchunks; ++c) {
-          mbar_wait(full_a + 8 * ra.s, ra.ph);
-          mbar_wait(full_b + 8 * rb.s, rb.ph);
+          { long long t0 = PROF ? clock64() : 0; mbar_wait(full_a + 8 * ra.s, ra.ph); if (PROF) w0 += clock64() - t0; }
+          { long long t0 = PROF ? clock64() : 0; mbar_wait(full_b + 8 * rb.s, rb.ph); if (PROF) w1 += clock64() - t0; }
           tc_fence_after();
           const uint32_t a_slot = a_lo0 + ((a_base + ra.s * p.slotA_bytes) >> 4);
           const uint32_t b_slot = b_lo0 + ((b_base + rb.s * p.stageB_bytes) >> 4);
@@ -603,6 +610,7 @@ conv_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
         }
         umma_commit(tmem_full + 8 * rt.s);
       }
+      if (PROF) { prof[blockIdx.x * 16 + 3] = w0; prof[blockIdx.x * 16 + 4] = w1; prof[blockIdx.x * 16 + 5] = w2; prof[blockIdx.x * 16 + 8] = clock64() - t_start; prof[blockIdx.x * 16 + 9] = it; }
     }
     __syncwarp();
   } else {
@@ -621,7 +629,8 @@ conv_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
       const int bz = r % p.nbz; r /= p.nbz;
       const int by = r % p.nby;
       const int bx = r / p.nby;
-      mbar_wait(tmem_full + 8 * rt.s, rt.ph);
+      long long t_e0 = 0;
+      { long long t0 = PROF ? clock64() : 0; mbar_wait(tmem_full + 8 * rt.s, rt.ph); if (PROF) { t_e0 = clock64(); w0 += t_e0 - t0; } }
       tc_fence_after();
       const uint32_t d0 = tmem_base + rt.s * (uint32_t)(p.MT * N3) + ((uint32_t)(q * 32) << 16);
       const int L0 = sub * 96 + grp * 6 + k8;                                          // frame row of this lane in its first tile
@@ -658,10 +667,13 @@ conv_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty + 8 * rt.s);
+      if (PROF) w1 += clock64() - t_e0;
     }
+    if (PROF && warp == 2 && lane == 0) { prof[blockIdx.x * 16 + 6] = w0; prof[blockIdx.x * 16 + 7] = w1; }
   }
   tc_fence_before();
   __syncthreads();
+  if (PROF && threadIdx.x == 0) prof[blockIdx.x * 16 + 0] = clock64() - t_start;
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
@@ -881,11 +893,12 @@ struct WgParams {
   // D[(dz,co)][ci]; a 16-channel layer then issues 9 MMAs per K-step with 48 useful rows instead of 27 with 16.
   int fz;                         // 1 or 3
   int KG, ngrp;                   // folded: (dx,dy) groups per pass / in total
+  int KS, accumulate;             // in-kernel finalize: lanes sharing one output quad (power of two <= 32); dw += or =
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_dy,
-                     float* __restrict__ partial, const WgParams p) {
+                     float* __restrict__ partial, float* __restrict__ dw, int* __restrict__ counter, const WgParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
   const uint32_t sbase = smem_u32(smem);
@@ -1068,13 +1081,70 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     }
   }
   tc_fence_before();
+  __threadfence();                       // this CTA's partial is visible device-wide before it arrives at the barrier
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
+  // ---- in-kernel finalize (replaces a separate finalize launch and its ~25 us of launch gap + cold reads): the grid is
+  // launched cooperatively (<= one CTA per SM, all co-resident), every CTA arrives at a device-wide barrier, then ALL
+  // CTAs sum the partials -- dw[co][ci][t] = sum_split partial[split][t][co][ci] -- each output quad by a fixed set of KS
+  // lanes in a fixed order (deterministic, no float atomics).  counter[0] = arrivals, counter[1] = departures; the last
+  // CTA to leave resets both, so the pair is reusable by the next launch on the stream.
+  const unsigned nct = gridDim.x * gridDim.y;
+  if (threadIdx.x == 0) {
+    atomicAdd(counter, 1);
+    unsigned seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+      if (seen < nct) __nanosleep(64);
+    } while (seen < nct);
+  }
+  __syncthreads();
+  {
+    const long long per = (long long)p.T * p.Cout * p.Cin;
+    const long long items = per >> 2;                                 // float4 outputs (Cin % 16 == 0)
+    const float4* part4 = reinterpret_cast<const float4*>(partial);
+    const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x;
+    const unsigned KS = (unsigned)p.KS, opw = 32u / KS;               // outputs per warp pass
+    const unsigned ks = lane & (KS - 1), ol = lane / KS;
+    const long long wstride = (long long)nct * (TC_THREADS / 32) * opw;
+    for (long long base = ((long long)cta * (TC_THREADS / 32) + warp) * opw; base < items; base += wstride) {
+      const long long o = base + ol;
+      const bool valid = o < items;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) {
+#pragma unroll 4
+        for (int k = (int)ks; k < p.splits; k += (int)KS) {
+          const float4 v = __ldcg(part4 + (long long)k * items + o);
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+      }
+      for (unsigned m = 1; m < KS; m <<= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, m);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, m);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, m);
+        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, m);
+      }
+      if (valid && ks == 0) {
+        const long long i = o << 2;
+        const int ci = (int)(i % p.Cin);
+        const int co = (int)((i / p.Cin) % p.Cout);
+        const int t = (int)(i / ((long long)p.Cin * p.Cout));
+        float* dst = dw + ((long long)co * p.Cin + ci) * p.T + t;
+        if (p.accumulate) { dst[0] += acc.x; dst[p.T] += acc.y; dst[2 * p.T] += acc.z; dst[3 * p.T] += acc.w; }
+        else { dst[0] = acc.x; dst[p.T] = acc.y; dst[2 * p.T] = acc.z; dst[3 * p.T] = acc.w; }
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = (unsigned)atomicAdd(counter + 1, 1);
+    if (prev == nct - 1) { counter[0] = 0; counter[1] = 0; __threadfence(); }
+  }
 }
 
-// dw[co][ci][t] = sum_split partial[split][t][co][ci]   (fixed order)
+// stand-alone finalize kept for reference / debugging: dw[co][ci][t] = sum_split partial[split][t][co][ci]   (fixed order)
 __global__ void conv_tc_wgrad_finalize_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int T,
                                               int Cout, int Cin, int accumulate) {
   const long long per = (long long)T * Cout * Cin;
@@ -1115,7 +1185,7 @@ static EncodeTiledFn get_encode() {
 // Out-of-bounds z (the conv padding) still zero-fills because z*2 stays the coordinate of its own dimension.
 static CUresult encode_cb8(EncodeTiledFn enc, CUtensorMap* map, const void* base, long long Z, long long Y, long long X,
                            long long planes, int bz, int by, int bx, int bp, int* merged) {
-  const int want = (bz <= 128 && !getenv("BCP_TMA_NO_MERGE")) ? 1 : 0;
+  const int want = (bz <= 128) ? 1 : 0;
   *merged = want;
   if (want) {
     const cuuint64_t gdim[4] = {(cuuint64_t)(2 * Z), (cuuint64_t)Y, (cuuint64_t)X, (cuuint64_t)planes};
@@ -1296,15 +1366,9 @@ static bool s2_plan(S2Params& p) {
 }
 
 // M = 64 accumulate mode for the weight-gradient kernels (output channels <= 64): halves the A-operand shared-memory
-// traffic.  BCP_WG_M64 = -1 disables it, 0/1/2 pick the TMEM row->lane map (validated on the GPU by the parity tests).
-static int wg_m64_mode() {
-  static int mode = -2;
-  if (mode == -2) {
-    const char* e = getenv("BCP_WG_M64");
-    mode = e ? atoi(e) : 0;       // map 0 validated against torch on B200 (tools/debug_conv_tc.py, profiles/)
-  }
-  return mode;
-}
+// traffic.  TMEM row->lane map 0 (row r at lane (r & 15) + 32 * (r >> 4)) was validated against torch on the B200
+// (tests/test_gpu_primitives.py::test_conv_production_shapes); the kernel keeps the other two conventions for reference.
+static constexpr int wg_m64_mode() { return 0; }
 
 static bool wg_shape_ok(int cin, int cout, const int* dims, const int* kernel) {
   if (!shape_ok(cin, cout, dims, kernel)) return false;
@@ -1325,8 +1389,7 @@ static bool wg_plan(WgParams& p, int nsm) {
   p.HZ = p.Z + 2;
   p.ZP = (p.Z + 15) / 16 * 16;
   p.fz = 1; p.KG = 0; p.ngrp = 0;
-  static const bool no_fold = getenv("BCP_WG_NO_FOLD") != nullptr;
-  if (!no_fold && 3 * p.Cout <= 128 && (p.Z + 2 + 15) / 16 * 16 <= 256 && p.Cin <= 512 / 3 && (wg_m64_mode() >= 0 || 3 * p.Cout > 64)) {
+  if (3 * p.Cout <= 128 && (p.Z + 2 + 15) / 16 * 16 <= 256 && p.Cin <= 512 / 3 && (wg_m64_mode() >= 0 || 3 * p.Cout > 64)) {
     // dz-folded: K runs over the halo'd z-line (Z+2 rows, rounded up to 16); both bricks use that z extent
     p.fz = 3;
     p.ZP = (p.Z + 2 + 15) / 16 * 16;
@@ -1410,9 +1473,6 @@ int bcp_conv_tc_plan(int n, int cin, int cout, const int* dims, const int* kerne
   return BCP_OK;
 }
 
-static unsigned long long* g_tc_prof = nullptr;
-// debug only (tools/debug_conv_tc.py --prof): 16 counters per CTA, see conv_tc_kernel<true>
-int bcp_conv_tc_debug_profile(void* buffer) { g_tc_prof = (unsigned long long*)buffer; return BCP_OK; }
 
 // fused-statistics eligibility: big layers only (on the deep ones the standalone statistics launch is a few microseconds
 // and the per-CTA partial reduce would cost as much), table of 4 x G x Cout x 2 doubles <= 16 KB
@@ -1425,7 +1485,7 @@ static unsigned stats_table_bytes(int n, int cout, const int* dims, int spg) {
 }
 
 static int conv_tc_launch(const void* in, const void* wpack, const float* bias, void* out, int n, int cin, int cout,
-                          const int* dims, const int* kernel, const StatsArgs* sa, cudaStream_t stream) {
+                          const int* dims, const int* kernel, const StatsArgs* sa, unsigned long long* prof, cudaStream_t stream) {
   BCP_REQUIRE(in && wpack && out && dims && kernel, "conv_tc_fwd: null pointer");
   if (!shape_ok(cin, cout, dims, kernel)) { set_last_error("conv_tc_fwd: unsupported shape cin=%d cout=%d", cin, cout); return BCP_ERR_UNSUPPORTED; }
   EncodeTiledFn enc = get_encode();
@@ -1443,7 +1503,7 @@ static int conv_tc_launch(const void* in, const void* wpack, const float* bias, 
   CUtensorMap tmap_w;
   {
     // pack [T][Cin/8][Cout][8]: the Ns-channel run of a (tap, plane) is contiguous, so fold (cout, 8) into 8-byte elements
-    p.mergedB = (p.Ns <= 128 && !getenv("BCP_TMA_NO_MERGE")) ? 1 : 0;
+    p.mergedB = (p.Ns <= 128) ? 1 : 0;
     CUresult cw;
     if (p.mergedB) {
       const cuuint64_t wdim[3] = {(cuuint64_t)cout * 2, (cuuint64_t)(cin / 8), (cuuint64_t)p.T};
@@ -1484,14 +1544,14 @@ static int conv_tc_launch(const void* in, const void* wpack, const float* bias, 
   const int nitems = p.nbricks * p.NS;
   const int grid = nitems < nsm ? nitems : nsm;
   if (sa) conv_tc_kernel<false, true><<<grid, TC_THREADS, smem, stream>>>(tmap, tmap_w, bias, (uint4*)out, p, nullptr, *sa);
-  else if (g_tc_prof) conv_tc_kernel<true, false><<<grid, TC_THREADS, smem, stream>>>(tmap, tmap_w, bias, (uint4*)out, p, g_tc_prof, StatsArgs{});
+  else if (prof) conv_tc_kernel<true, false><<<grid, TC_THREADS, smem, stream>>>(tmap, tmap_w, bias, (uint4*)out, p, prof, StatsArgs{});
   else conv_tc_kernel<false, false><<<grid, TC_THREADS, smem, stream>>>(tmap, tmap_w, bias, (uint4*)out, p, nullptr, StatsArgs{});
   return check_launch("conv_tc_fwd");
 }
 
 int bcp_conv_tc_fwd(const void* in, const void* wpack, const float* bias, void* out, int n, int cin, int cout,
                     const int* dims, const int* kernel, cudaStream_t stream) {
-  return conv_tc_launch(in, wpack, bias, out, n, cin, cout, dims, kernel, nullptr, stream);
+  return conv_tc_launch(in, wpack, bias, out, n, cin, cout, dims, kernel, nullptr, nullptr, stream);
 }
 
 long long bcp_conv_tc_stats_workspace_bytes(int n, int cin, int cout, const int* dims, const int* kernel, int spg) {
@@ -1515,7 +1575,7 @@ int bcp_conv_tc_fwd_stats(const void* in, const void* wpack, const float* bias, 
   sa.partial = (double*)workspace; sa.counter = counter; sa.gamma = gamma; sa.beta = beta;
   sa.running_mean = running_mean; sa.running_var = running_var; sa.nbt = num_batches_tracked;
   sa.stat = stat; sa.coef = coef; sa.spg = spg; sa.G = n / spg; sa.eps = eps; sa.momentum = momentum;
-  return conv_tc_launch(in, wpack, bias, out, n, cin, cout, dims, kernel, &sa, stream);
+  return conv_tc_launch(in, wpack, bias, out, n, cin, cout, dims, kernel, &sa, nullptr, stream);
 }
 
 // ---- EXPERIMENTAL dz-folded forward (conv_tc_fold_kernel): brick plan + launch.  Not used unless ops.py is told to.
@@ -1602,8 +1662,20 @@ int bcp_conv_tc_fold_supported(int cin, int cout, const int* dims, const int* ke
   return get_encode() != nullptr ? 1 : 0;
 }
 
-int bcp_conv_tc_fold_fwd(const void* in, const void* wpack, const float* bias, void* out, int n, int cin, int cout,
-                         const int* dims, const int* kernel, cudaStream_t stream) {
+// chosen tiling for inspection: {BX,BY,BZ,MT,SA,SB,AS,nbricks,tmem_cols,smem_bytes}
+int bcp_conv_tc_fold_plan(int n, int cin, int cout, const int* dims, const int* kernel, int* plan10) {
+  BCP_REQUIRE(dims && kernel && plan10, "conv_tc_fold_plan: null pointer");
+  if (!fold_shape_ok(cin, cout, dims, kernel)) { set_last_error("conv_tc_fold_plan: unsupported shape"); return BCP_ERR_UNSUPPORTED; }
+  FoldParams p{};
+  p.N = n; p.X = dims[0]; p.Y = dims[1]; p.Z = dims[2]; p.Cin = cin; p.Cout = cout; p.kx = kernel[0];
+  if (!fold_plan(p, sm_count())) { set_last_error("conv_tc_fold_plan: no brick shape fits"); return BCP_ERR_UNSUPPORTED; }
+  const int v[10] = {p.BX, p.BY, p.BZ, p.MT, p.SA, p.SB, p.AS, p.nbricks, p.tmem_cols, (int)(p.offBar + 8 * (2 * p.SA + 2 * p.SB + 2 * p.AS) + 16 + 128)};
+  for (int i = 0; i < 10; ++i) plan10[i] = v[i];
+  return BCP_OK;
+}
+
+static int conv_tc_fold_launch(const void* in, const void* wpack, const float* bias, void* out, int n, int cin, int cout,
+                               const int* dims, const int* kernel, unsigned long long* prof, cudaStream_t stream) {
   BCP_REQUIRE(in && wpack && out && dims && kernel, "conv_tc_fold_fwd: null pointer");
   if (!fold_shape_ok(cin, cout, dims, kernel)) { set_last_error("conv_tc_fold_fwd: unsupported shape"); return BCP_ERR_UNSUPPORTED; }
   EncodeTiledFn enc = get_encode();
@@ -1632,14 +1704,66 @@ int bcp_conv_tc_fold_fwd(const void* in, const void* wpack, const float* bias, v
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(conv_tc_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    attr_err = cudaFuncSetAttribute(conv_tc_fold_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(conv_tc_fold_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (attr_err != cudaSuccess) cudaGetLastError();
   });
   if (attr_err != cudaSuccess) { set_last_error("conv_tc_fold_fwd: cudaFuncSetAttribute failed"); return BCP_ERR_CUDA; }
   BCP_REQUIRE(smem <= 226 * 1024, "conv_tc_fold_fwd: shared memory plan overflow");
   const int grid = p.nbricks < nsm ? p.nbricks : nsm;
-  conv_tc_fold_kernel<<<grid, FOLD_THREADS, smem, stream>>>(tmap, tmap_w, bias, (uint4*)out, p);
+  if (prof) conv_tc_fold_kernel<true><<<grid, FOLD_THREADS, smem, stream>>>(tmap, tmap_w, bias, (uint4*)out, p, prof);
+  else conv_tc_fold_kernel<false><<<grid, FOLD_THREADS, smem, stream>>>(tmap, tmap_w, bias, (uint4*)out, p, nullptr);
   return check_launch("conv_tc_fold_fwd");
+}
+
+int bcp_conv_tc_fold_fwd(const void* in, const void* wpack, const float* bias, void* out, int n, int cin, int cout,
+                         const int* dims, const int* kernel, cudaStream_t stream) {
+  return conv_tc_fold_launch(in, wpack, bias, out, n, cin, cout, dims, kernel, nullptr, stream);
+}
+
+// Instrumented variants for tools/debug_conv_tc.py: `prof` = device buffer of 16 x uint64 per CTA (>= #SMs CTAs) that
+// receives per-role wait cycles.  fold = 1 selects the dz-folded kernel.  The caller passes the buffer explicitly: the
+// library keeps no profiling state.
+int bcp_conv_tc_fwd_profiled(const void* in, const void* wpack, const float* bias, void* out, int n, int cin, int cout,
+                             const int* dims, const int* kernel, int fold, void* prof, cudaStream_t stream) {
+  BCP_REQUIRE(prof, "conv_tc_fwd_profiled: null profile buffer");
+  if (fold) return conv_tc_fold_launch(in, wpack, bias, out, n, cin, cout, dims, kernel, (unsigned long long*)prof, stream);
+  return conv_tc_launch(in, wpack, bias, out, n, cin, cout, dims, kernel, nullptr, (unsigned long long*)prof, stream);
+}
+
+
+// Cooperative launch of the weight-gradient kernel (its in-kernel finalize needs every CTA of the grid co-resident: the grid
+// is splits x passes <= #SMs with one CTA per SM, and the cooperative attribute makes the driver guarantee it).
+static int wg_launch(const CUtensorMap& map_a, const CUtensorMap& map_dy, float* workspace, float* dw, int* counter, WgParams& p,
+                     cudaStream_t stream, const char* what) {
+  const size_t smem = (size_t)p.offBar + 8 * (2 * p.S + 1) + 16 + 128 + 128;
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err != cudaSuccess) cudaGetLastError();
+  });
+  if (attr_err != cudaSuccess) { set_last_error("%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(attr_err)); return BCP_ERR_CUDA; }
+  const int nct = p.splits * p.npass_t * p.MH;
+  if (nct > sm_count()) { set_last_error("%s: grid of %d CTAs cannot be co-resident", what, nct); return BCP_ERR_UNSUPPORTED; }
+  // lanes per output quad: spread the `splits` partials of an output over KS lanes when there are more threads than quads
+  const long long items = (long long)p.T * p.Cout * p.Cin / 4, threads = (long long)nct * TC_THREADS;
+  int ks = 1;
+  while (ks < 32 && ks * 2 <= p.splits && items * ks * 2 <= threads) ks *= 2;
+  p.KS = ks;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(p.splits, p.npass_t * p.MH);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_wgrad_kernel, map_a, map_dy, workspace, dw, counter, (const WgParams)p);
+  if (e != cudaSuccess) { cudaGetLastError(); set_last_error("%s: launch failed: %s", what, cudaGetErrorString(e)); return BCP_ERR_CUDA; }
+  return check_launch(what);
 }
 
 int bcp_conv_tc_wgrad_supported(int cin, int cout, const int* dims, const int* kernel) {
@@ -1662,9 +1786,9 @@ long long bcp_conv_tc_wgrad_workspace_floats(int n, int cin, int cout, const int
 }
 
 // dw[cout][cin][T] fp32; `a` = layer input (cin channels), `dy` = output gradient (cout channels), both CB8 at `dims`
-int bcp_conv_tc_wgrad(const void* a, const void* dy, float* dw, float* workspace, int n, int cin, int cout,
+int bcp_conv_tc_wgrad(const void* a, const void* dy, float* dw, float* workspace, int* counter, int n, int cin, int cout,
                       const int* dims, const int* kernel, int accumulate, cudaStream_t stream) {
-  BCP_REQUIRE(a && dy && dw && workspace && dims && kernel, "conv_tc_wgrad: null pointer");
+  BCP_REQUIRE(a && dy && dw && workspace && counter && dims && kernel, "conv_tc_wgrad: null pointer");
   if (!wg_shape_ok(cin, cout, dims, kernel)) { set_last_error("conv_tc_wgrad: unsupported shape"); return BCP_ERR_UNSUPPORTED; }
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_last_error("conv_tc_wgrad: cuTensorMapEncodeTiled unavailable"); return BCP_ERR_CUDA; }
@@ -1679,14 +1803,8 @@ int bcp_conv_tc_wgrad(const void* a, const void* dy, float* dw, float* workspace
     const CUresult cr = encode_cb8(enc, &map_dy, dy, p.Z, p.Y, p.X, (long long)n * (cout / 8), p.ZP, p.BY, p.BX, p.PL, &p.mergedD);
     if (cr != CUDA_SUCCESS) { set_last_error("conv_tc_wgrad: tensor map (dy) failed (%d)", (int)cr); return BCP_ERR_CUDA; }
   }
-  const size_t smem = (size_t)p.offBar + 8 * (2 * p.S + 1) + 16 + 128 + 128;
-  static std::once_flag attr_once;
-  std::call_once(attr_once, [] { cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
-  dim3 grid(p.splits, p.npass_t * p.MH);
-  conv_tc_wgrad_kernel<<<grid, TC_THREADS, smem, stream>>>(map_a, map_dy, workspace, p);
-  const long long per = (long long)p.T * cout * cin;
-  conv_tc_wgrad_finalize_kernel<<<(unsigned)((per + 255) / 256), 256, 0, stream>>>(workspace, dw, p.splits, p.T, cout, cin, accumulate);
-  return check_launch("conv_tc_wgrad");
+  p.accumulate = accumulate;
+  return wg_launch(map_a, map_dy, workspace, dw, counter, p, stream, "conv_tc_wgrad");
 }
 
 // ---- stride-2 family.  half_dims = dims of the half-resolution grid (full = 2x).  mode 1 (gather): `in` is full-res with
@@ -1808,9 +1926,9 @@ long long bcp_conv_tc_s2_wgrad_workspace_floats(int n, int c_half, int c_full, c
   return (long long)p.splits * 8 * c_half * c_full;
 }
 
-int bcp_conv_tc_s2_wgrad(const void* full, const void* half, float* dw, float* workspace, int n, int c_half, int c_full,
-                         const int* half_dims, int accumulate, cudaStream_t stream) {
-  BCP_REQUIRE(full && half && dw && workspace && half_dims, "conv_tc_s2_wgrad: null pointer");
+int bcp_conv_tc_s2_wgrad(const void* full, const void* half, float* dw, float* workspace, int* counter, int n, int c_half,
+                         int c_full, const int* half_dims, int accumulate, cudaStream_t stream) {
+  BCP_REQUIRE(full && half && dw && workspace && counter && half_dims, "conv_tc_s2_wgrad: null pointer");
   if (!s2_shape_ok(c_full, c_half, half_dims)) { set_last_error("conv_tc_s2_wgrad: unsupported shape"); return BCP_ERR_UNSUPPORTED; }
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_last_error("conv_tc_s2_wgrad: cuTensorMapEncodeTiled unavailable"); return BCP_ERR_CUDA; }
@@ -1832,14 +1950,8 @@ int bcp_conv_tc_s2_wgrad(const void* full, const void* half, float* dw, float* w
     const CUresult cr = encode_cb8(enc, &map_dy, half, p.Z, p.Y, p.X, (long long)n * (c_half / 8), p.ZP, p.BY, p.BX, p.PL, &p.mergedD);
     if (cr != CUDA_SUCCESS) { set_last_error("conv_tc_s2_wgrad: tensor map (half) failed (%d)", (int)cr); return BCP_ERR_CUDA; }
   }
-  const size_t smem = (size_t)p.offBar + 8 * (2 * p.S + 1) + 16 + 128 + 128;
-  static std::once_flag attr_once;
-  std::call_once(attr_once, [] { cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
-  dim3 grid(p.splits, p.npass_t * p.MH);
-  conv_tc_wgrad_kernel<<<grid, TC_THREADS, smem, stream>>>(map_a, map_dy, workspace, p);
-  const long long per = 8ll * c_half * c_full;
-  conv_tc_wgrad_finalize_kernel<<<(unsigned)((per + 255) / 256), 256, 0, stream>>>(workspace, dw, p.splits, 8, c_half, c_full, accumulate);
-  return check_launch("conv_tc_s2_wgrad");
+  p.accumulate = accumulate;
+  return wg_launch(map_a, map_dy, workspace, dw, counter, p, stream, "conv_tc_s2_wgrad");
 }
 
 }  // extern "C"

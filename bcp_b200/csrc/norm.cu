@@ -12,8 +12,45 @@ namespace bcp {
 
 constexpr int NT = 256;
 
-// Per-channel finalize, executed by ONE block (the last one to finish its partial): fixed-order double-precision
-// reduce of the partials => deterministic no matter which block happens to be last.
+// ---- finalize stage shared by the forward statistics and the backward reduction -------------------------------------
+// The partial buffer holds one 16-float record per (sample, channel octet, chunk): {8 x sum_a, 8 x sum_b}.  The LAST block to
+// arrive reduces them to per-(group, channel) double-precision totals in shared memory: one warp per (group, octet) task,
+// one record per lane per iteration (four independent 16-byte loads in flight per lane, so the L2 round trips of a task
+// overlap instead of forming the dependent chain the first version had: 64 sequential loads ~ 20 us on a 64-channel layer),
+// then a fixed butterfly => bit-identical run to run no matter which block happens to be last.
+constexpr int FIN_PAIRS = 1024;          // (group, channel) pairs per shared-memory tile
+
+__device__ __forceinline__ void fin_reduce_tile(const float* __restrict__ partial, double* __restrict__ sm_a,
+                                                double* __restrict__ sm_b, int G, int Cb, int cb0, int ncb, int chunks, int spg) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int per_group = spg * chunks;
+  for (int task = warp; task < G * ncb; task += nwarps) {
+    const int g = task / ncb, cbl = task - g * ncb, cb = cb0 + cbl;
+    double acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+    for (int e = lane; e < per_group; e += 32) {
+      const int ns = e / chunks, ch = e - ns * chunks;
+      const float4* p = reinterpret_cast<const float4*>(partial + ((((long long)(g * spg + ns)) * Cb + cb) * chunks + ch) * 16);
+      const float4 v0 = __ldcg(p), v1 = __ldcg(p + 1), v2 = __ldcg(p + 2), v3 = __ldcg(p + 3);
+      acc[0] += (double)v0.x; acc[1] += (double)v0.y; acc[2] += (double)v0.z; acc[3] += (double)v0.w;
+      acc[4] += (double)v1.x; acc[5] += (double)v1.y; acc[6] += (double)v1.z; acc[7] += (double)v1.w;
+      acc[8] += (double)v2.x; acc[9] += (double)v2.y; acc[10] += (double)v2.z; acc[11] += (double)v2.w;
+      acc[12] += (double)v3.x; acc[13] += (double)v3.y; acc[14] += (double)v3.z; acc[15] += (double)v3.w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { sm_a[(g * ncb + cbl) * 8 + k] = acc[k]; sm_b[(g * ncb + cbl) * 8 + k] = acc[8 + k]; }
+    }
+  }
+}
+
+// Per-channel finalize, executed by ONE block (the last one to finish its partial).
 // stat[g][C][2] = {mean, invstd}; coef[g][C][2] = {scale, shift}.
 __device__ void bn_finalize_block(const float* __restrict__ partial, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, float* __restrict__ running_mean,
@@ -24,61 +61,39 @@ __device__ void bn_finalize_block(const float* __restrict__ partial, const float
   const int G = N / spg;
   if (threadIdx.x == 0 && nbt != nullptr) nbt[0] += G;
   const double M = (double)spg * (double)S;
-  // Layers with many partials per (group, channel) first reduce them cooperatively: one warp per pair, lanes split the
-  // (sample, chunk) list in a fixed pattern and a fixed butterfly combines them.  The double-precision mean / variance /
-  // running-statistics chain then runs one channel per THREAD (a dependent chain of FP64 div/sqrt per warp is slow).
-  __shared__ double sm_s[256], sm_q[256];
-  const int per_group = spg * chunks;
-  const bool coop = per_group > 32 && G * C <= 256;
-  if (coop) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    for (int pair = warp; pair < G * C; pair += nwarps) {
-      const int g = pair / C, c = pair - g * C, cb = c >> 3, k = c & 7;
-      double s = 0.0, q = 0.0;
-      for (int e = lane; e < per_group; e += 32) {
-        const int n = g * spg + e / chunks, ch = e - (e / chunks) * chunks;
-        const float* p = partial + (((long long)n * Cb + cb) * chunks + ch) * 16;
-        s += (double)p[k];
-        q += (double)p[8 + k];
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        s += __shfl_xor_sync(0xffffffffu, s, o);
-        q += __shfl_xor_sync(0xffffffffu, q, o);
-      }
-      if (lane == 0) { sm_s[pair] = s; sm_q[pair] = q; }
-    }
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int cb = c >> 3, k = c & 7;
-    float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 0.f;
-    for (int g = 0; g < G; ++g) {
-      double s = 0.0, q = 0.0;
-      if (coop) { s = sm_s[g * C + c]; q = sm_q[g * C + c]; }
-      else {
-        for (int n = g * spg; n < (g + 1) * spg; ++n) {
-          const float* p = partial + ((long long)n * Cb + cb) * chunks * 16;
-          for (int ch = 0; ch < chunks; ++ch) { s += (double)p[ch * 16 + k]; q += (double)p[ch * 16 + 8 + k]; }
+  __shared__ double sm_s[FIN_PAIRS], sm_q[FIN_PAIRS];
+  int tile_cb = FIN_PAIRS / (8 * G);
+  if (tile_cb < 1) tile_cb = 1;                       // G > 128 groups: the host wrapper rejects such shapes
+  for (int cb0 = 0; cb0 < Cb; cb0 += tile_cb) {
+    const int ncb = min(tile_cb, Cb - cb0);
+    __syncthreads();
+    fin_reduce_tile(partial, sm_s, sm_q, G, Cb, cb0, ncb, chunks, spg);
+    __syncthreads();
+    // the double-precision mean / variance / running-statistics chain runs one channel per THREAD
+    for (int t = threadIdx.x; t < ncb * 8; t += blockDim.x) {
+      const int c = cb0 * 8 + t;
+      if (c >= C) continue;
+      float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 0.f;
+      for (int g = 0; g < G; ++g) {
+        const double s = sm_s[g * ncb * 8 + t], q = sm_q[g * ncb * 8 + t];
+        const double mean = s / M;
+        double var = q / M - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+        const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+        const float scale = ga * invstd;
+        stat[((long long)g * C + c) * 2 + 0] = (float)mean;
+        stat[((long long)g * C + c) * 2 + 1] = invstd;
+        coef[((long long)g * C + c) * 2 + 0] = scale;
+        coef[((long long)g * C + c) * 2 + 1] = be - (float)mean * scale;
+        if (running_mean) {   // sequential per-call update, like calling the module once per group
+          const double unbiased = (M > 1.0) ? var * M / (M - 1.0) : var;
+          rm = (1.f - momentum) * rm + momentum * (float)mean;
+          rv = (1.f - momentum) * rv + momentum * (float)unbiased;
         }
       }
-      const double mean = s / M;
-      double var = q / M - mean * mean;
-      if (var < 0.0) var = 0.0;
-      const float invstd = (float)(1.0 / sqrt(var + (double)eps));
-      const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
-      const float scale = ga * invstd;
-      stat[((long long)g * C + c) * 2 + 0] = (float)mean;
-      stat[((long long)g * C + c) * 2 + 1] = invstd;
-      coef[((long long)g * C + c) * 2 + 0] = scale;
-      coef[((long long)g * C + c) * 2 + 1] = be - (float)mean * scale;
-      if (running_mean) {   // sequential per-call update, like calling the module once per group
-        const double unbiased = (M > 1.0) ? var * M / (M - 1.0) : var;
-        rm = (1.f - momentum) * rm + momentum * (float)mean;
-        rv = (1.f - momentum) * rv + momentum * (float)unbiased;
-      }
+      if (running_mean) { running_mean[c] = rm; running_var[c] = rv; }
     }
-    if (running_mean) { running_mean[c] = rm; running_var[c] = rv; }
   }
 }
 
@@ -324,47 +339,27 @@ __device__ void bn_bwd_finalize_block(const float* __restrict__ partial, float* 
                                       int N, int C, long long S, int chunks, int spg, int accumulate) {
   const int Cb = (C + 7) / 8, G = N / spg;
   const double M = (double)spg * (double)S;
-  __shared__ double sm_a[256], sm_b[256];            // cooperative pre-reduction, see bn_finalize_block
-  const int per_group = spg * chunks;
-  const bool coop = per_group > 32 && G * C <= 256;
-  if (coop) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    for (int pair = warp; pair < G * C; pair += nwarps) {
-      const int g = pair / C, c = pair - g * C, cb = c >> 3, k = c & 7;
-      double a = 0.0, b = 0.0;
-      for (int e = lane; e < per_group; e += 32) {
-        const int n = g * spg + e / chunks, ch = e - (e / chunks) * chunks;
-        const float* p = partial + (((long long)n * Cb + cb) * chunks + ch) * 16;
-        a += (double)p[k];
-        b += (double)p[8 + k];
+  __shared__ double sm_a[FIN_PAIRS], sm_b[FIN_PAIRS];
+  int tile_cb = FIN_PAIRS / (8 * G);
+  if (tile_cb < 1) tile_cb = 1;
+  for (int cb0 = 0; cb0 < Cb; cb0 += tile_cb) {
+    const int ncb = min(tile_cb, Cb - cb0);
+    __syncthreads();
+    fin_reduce_tile(partial, sm_a, sm_b, G, Cb, cb0, ncb, chunks, spg);
+    __syncthreads();
+    for (int t = threadIdx.x; t < ncb * 8; t += blockDim.x) {
+      const int c = cb0 * 8 + t;
+      if (c >= C) continue;
+      double tg = 0.0, tb = 0.0;
+      for (int g = 0; g < G; ++g) {
+        const double a = sm_a[g * ncb * 8 + t], b = sm_b[g * ncb * 8 + t];
+        sums[((long long)g * C + c) * 2 + 0] = (float)(a / M);
+        sums[((long long)g * C + c) * 2 + 1] = (float)(b / M);
+        tb += a; tg += b;
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        a += __shfl_xor_sync(0xffffffffu, a, o);
-        b += __shfl_xor_sync(0xffffffffu, b, o);
-      }
-      if (lane == 0) { sm_a[pair] = a; sm_b[pair] = b; }
+      if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)tg : (float)tg;
+      if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)tb : (float)tb;
     }
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int cb = c >> 3, k = c & 7;
-    double tg = 0.0, tb = 0.0;
-    for (int g = 0; g < G; ++g) {
-      double a = 0.0, b = 0.0;
-      if (coop) { a = sm_a[g * C + c]; b = sm_b[g * C + c]; }
-      else {
-        for (int n = g * spg; n < (g + 1) * spg; ++n) {
-          const float* p = partial + ((long long)n * Cb + cb) * chunks * 16;
-          for (int ch = 0; ch < chunks; ++ch) { a += (double)p[ch * 16 + k]; b += (double)p[ch * 16 + 8 + k]; }
-        }
-      }
-      sums[((long long)g * C + c) * 2 + 0] = (float)(a / M);
-      sums[((long long)g * C + c) * 2 + 1] = (float)(b / M);
-      tb += a; tg += b;
-    }
-    if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)tg : (float)tg;
-    if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)tb : (float)tb;
   }
 }
 
@@ -524,6 +519,7 @@ int bcp_norm_stats(const void* y, const float* gamma, const float* beta, float* 
                    int n, int c, long long s, int spg, float eps, float momentum, cudaStream_t stream) {
   BCP_REQUIRE(y && stat && coef && workspace && counter, "norm_stats: null pointer");
   BCP_REQUIRE(n > 0 && c > 0 && s > 0 && spg > 0 && n % spg == 0, "norm_stats: bad shape n=%d spg=%d", n, spg);
+  BCP_REQUIRE(n / spg <= 128, "norm_stats: more than 128 normalisation groups in one call (%d)", n / spg);
   const int Cb = (c + 7) / 8, chunks = pick_chunks(s, n * Cb);
   if ((long long)n * s <= SMALL_LIMIT) {
     bn_stats_small_kernel<<<Cb, NT, 0, stream>>>((const uint4*)y, s, gamma, beta, running_mean, running_var, num_batches_tracked,
@@ -563,6 +559,7 @@ int bcp_norm_bwd(const void* dact, const void* y, void* dy, const float* stat, c
                  int accumulate, cudaStream_t stream) {
   BCP_REQUIRE(dact && y && dy && stat && coef && sums && workspace && counter, "norm_bwd: null pointer");
   BCP_REQUIRE(n > 0 && c > 0 && s > 0 && spg > 0 && n % spg == 0, "norm_bwd: bad shape");
+  BCP_REQUIRE(n / spg <= 128, "norm_bwd: more than 128 normalisation groups in one call (%d)", n / spg);
   const int Cb = (c + 7) / 8, chunks = pick_chunks(s, n * Cb);
   if ((long long)n * s <= SMALL_LIMIT) {
     const int reduce = (stats_grad || dgamma || dbeta) ? 1 : 0;

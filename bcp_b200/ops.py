@@ -21,8 +21,9 @@ _TC_WGRAD = _TC_FWD and os.environ.get("BCP_DISABLE_TC_WGRAD", "0") != "1"
 # conv epilogue produces the following norm's statistics (bcp_conv_tc_fwd_stats).  Opt-in: parity-tested, but on the LA step
 # the fused epilogue + last-CTA finalize cost about what the (now 4-loads-in-flight) standalone statistics pass costs.
 _FUSE_STATS = os.environ.get("BCP_FUSED_STATS", "0") == "1"
-# experimental dz-folded forward kernel for 16/32-channel layers; first GPU run pending
-_TC_FOLD = os.environ.get("BCP_TC_FOLD", "0") == "1"
+# dz-folded forward kernel for 16/32-channel layers (three dz taps ride in the MMA N dimension).
+# Module switch for the parity tests / tools that compare it against the unfolded kernel.
+_TC_FOLD = True
 
 
 def _require_cuda(t: torch.Tensor, what: str):
@@ -172,7 +173,8 @@ def _wgrad(inp, outgrad, cin, cout, in_dims, kernel, stride, pad, wshape, allow_
     if allow_tc and _TC_WGRAD and same and LIB.query("bcp_conv_tc_wgrad_supported", cin, cout, i3(*in_dims), i3(*kernel)):
         ws = _f32(LIB.query("bcp_conv_tc_wgrad_workspace_floats", n, cin, cout, i3(*in_dims), i3(*kernel)), inp.device)
         dw = into if into is not None else torch.empty(wshape, dtype=torch.float32, device=inp.device)
-        LIB.call("bcp_conv_tc_wgrad", ptr(inp), ptr(outgrad), ptr(dw), ptr(ws), n, cin, cout, i3(*in_dims), i3(*kernel), acc, stream())
+        LIB.call("bcp_conv_tc_wgrad", ptr(inp), ptr(outgrad), ptr(dw), ptr(ws), _counter(inp.device).data_ptr() + 16, n, cin, cout,
+                 i3(*in_dims), i3(*kernel), acc, stream())
         return None if into is not None else dw
     od = [(in_dims[i] + 2 * pad[i] - kernel[i]) // stride[i] + 1 for i in range(3)]
     ws = _f32(LIB.query("bcp_conv_wgrad_workspace_floats", n, cin, cout, i3(*od), i3(*kernel)), inp.device)
@@ -264,8 +266,8 @@ def _s2_wgrad(full, half, c_full, c_half, half_dims, wshape, into=None):
     if _TC_WGRAD and LIB.query("bcp_conv_tc_s2_wgrad_supported", c_half, c_full, i3(*half_dims)):
         ws = _f32(LIB.query("bcp_conv_tc_s2_wgrad_workspace_floats", n, c_half, c_full, i3(*half_dims)), full.device)
         dw = into if into is not None else torch.empty(wshape, dtype=torch.float32, device=full.device)
-        LIB.call("bcp_conv_tc_s2_wgrad", ptr(full), ptr(half), ptr(dw), ptr(ws), n, c_half, c_full, i3(*half_dims),
-                 1 if into is not None else 0, stream())
+        LIB.call("bcp_conv_tc_s2_wgrad", ptr(full), ptr(half), ptr(dw), ptr(ws), _counter(full.device).data_ptr() + 16, n, c_half,
+                 c_full, i3(*half_dims), 1 if into is not None else 0, stream())
         return None if into is not None else dw
     return _wgrad(full, half, c_full, c_half, (2 * hx, 2 * hy, 2 * hz), (2, 2, 2), (2, 2, 2), (0, 0, 0), wshape, allow_tc=False,
                   into=into)

@@ -11,7 +11,9 @@
  *   - return 0 on success, <0 on error (-1 invalid argument, -2 unsupported shape, -3 CUDA error);
  *     bcp_last_error() returns a thread-local message.  Never throws, never aborts, never synchronises.
  *   - the CALLER owns all memory, including workspaces (query bcp_*_workspace_* first); no hidden allocation
- *     and no global mutable state, so calls are re-entrant (autograd's backward thread, one process per GPU)
+ *     and no mutable library state beyond immutable per-shape tiling plans memoised behind a mutex and the
+ *     thread-local error string, so calls are re-entrant (autograd's backward thread, one process per GPU); kernel
+ *     selection never reads the environment
  *   - activations: channel-blocked bf16 "CB8"  [N][ceil(C/8)][X][Y][Z][8]  (2-D nets use X = 1)
  *     network input / logits: planar fp32 [N][C][X][Y][Z] (PyTorch NCDHW); labels: uint8 [N][X][Y][Z]
  *     statistics, master weights, gradients of weights: fp32
@@ -178,16 +180,21 @@ int bcp_window_finalize(float* score, const float* count, unsigned char* label, 
 /* EXPERIMENTAL (not on the default path, first GPU run pending): the same convolution for Cout in {16, 32} with the three
  * dz taps folded into the MMA N dimension.  Same arguments and packs as bcp_conv_tc_fwd. */
 int bcp_conv_tc_fold_supported(int cin, int cout, const int* dims, const int* kernel);
+int bcp_conv_tc_fold_plan(int n, int cin, int cout, const int* dims, const int* kernel, int* plan10);
 int bcp_conv_tc_fold_fwd(const void* in, const void* wpack, const float* bias, void* out, int n, int cin, int cout,
                          const int* dims, const int* kernel, cudaStream_t stream);
-/* debug only: when `buffer` (device, 16 x uint64 per CTA, >= 148 CTAs) is non-null, bcp_conv_tc_fwd launches the
- * instrumented kernel variant that records per-role wait cycles; pass NULL to return to the product kernel. */
-int bcp_conv_tc_debug_profile(void* buffer);
+/* debug only (tools/debug_conv_tc.py): the instrumented template instance of bcp_conv_tc_fwd (fold = 0) or
+ * bcp_conv_tc_fold_fwd (fold = 1); `prof` (device, 16 x uint64 per CTA, >= #SMs CTAs) receives per-role wait cycles. */
+int bcp_conv_tc_fwd_profiled(const void* in, const void* wpack, const float* bias, void* out, int n, int cin, int cout,
+                             const int* dims, const int* kernel, int fold, void* prof, cudaStream_t stream);
 
-/* tcgen05 weight gradient for the same family: dw[cout][cin][taps] fp32 (PyTorch layout), deterministic. */
+/* tcgen05 weight gradient for the same family: dw[cout][cin][taps] fp32 (PyTorch layout), deterministic.  ONE cooperative
+ * launch: every CTA accumulates its share of the voxels in TMEM, writes a partial to `workspace`, meets the others at a
+ * device-wide barrier and then all CTAs reduce the partials in fixed order into dw.  `counter`: TWO device ints, zero
+ * before the first call (the kernel resets them), private to the stream. */
 int bcp_conv_tc_wgrad_supported(int cin, int cout, const int* dims, const int* kernel);
 long long bcp_conv_tc_wgrad_workspace_floats(int n, int cin, int cout, const int* dims, const int* kernel);
-int bcp_conv_tc_wgrad(const void* a, const void* dy, float* dw, float* workspace, int n, int cin, int cout,
+int bcp_conv_tc_wgrad(const void* a, const void* dy, float* dw, float* workspace, int* counter, int n, int cin, int cout,
                       const int* dims, const int* kernel, int accumulate, cudaStream_t stream);
 
 /* tcgen05 stride-2 family (nn.Conv3d(k=2,s=2) networks/VNet.py:74, nn.ConvTranspose3d(k=2,s=2) networks/VNet.py:101).
@@ -199,8 +206,8 @@ int bcp_conv_tc_s2_fwd(const void* in, const void* wpack, const float* bias, voi
                        const int* half_dims, int mode, cudaStream_t stream);
 int bcp_conv_tc_s2_wgrad_supported(int c_half, int c_full, const int* half_dims);
 long long bcp_conv_tc_s2_wgrad_workspace_floats(int n, int c_half, int c_full, const int* half_dims);
-int bcp_conv_tc_s2_wgrad(const void* full, const void* half, float* dw, float* workspace, int n, int c_half, int c_full,
-                         const int* half_dims, int accumulate, cudaStream_t stream);
+int bcp_conv_tc_s2_wgrad(const void* full, const void* half, float* dw, float* workspace, int* counter, int n, int c_half,
+                         int c_full, const int* half_dims, int accumulate, cudaStream_t stream);
 
 /* ---- resampling (networks/unet.py:37 MaxPool2d(2); :50 Upsample(bilinear, align_corners=True);
  * networks/VNet.py:249 MaxPool3d(3, stride=2)).  planes = n * ceil(c/8) * X. */

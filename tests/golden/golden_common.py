@@ -72,3 +72,58 @@ def find_box_seed_la(shape, start=0):
         if w + px <= X and h + py <= Y and z + pz <= Z:
             return s
     raise RuntimeError("no seed")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# fixtures built on the reference's SHIPPED checkpoints (models/LA/LA_10.pth, models/ACDC/ACDC_10.pth)
+# ---------------------------------------------------------------------------------------------------------
+def bf16_round_np(x: np.ndarray) -> np.ndarray:
+    """fp32 -> bf16 bit patterns (uint16), round to nearest even (same rule as torch's .to(bfloat16))."""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    r = ((u >> 16) & 1) + np.uint32(0x7FFF)
+    return ((u + r) >> 16).astype(np.uint16)
+
+
+def pack_weights_bf16(sd) -> dict:
+    """state_dict -> {key: uint16 bf16 bits (float tensors) | int64 (counters)}.  The checkpoint's values rounded to
+    bf16 ARE the fixture's weights: the reference (fp32 arithmetic) and the native path both load exactly these numbers,
+    so the weight rounding of the bf16 operand packs is not part of the measured difference."""
+    out = {}
+    for k, v in sd.items():
+        a = v.detach().cpu().numpy()
+        out[k] = a.astype(np.int64) if a.dtype.kind in "iu" else bf16_round_np(a)
+    return out
+
+
+def unpack_weights_bf16(npz) -> dict:
+    sd = {}
+    for k in npz.files:
+        a = npz[k]
+        if a.dtype == np.uint16:
+            sd[k] = torch.from_numpy((a.astype(np.uint32) << 16).view(np.float32).copy())
+        else:
+            sd[k] = torch.from_numpy(a.copy())
+    return sd
+
+
+def synthetic_scene(n, shape, seed, n_classes=2, kind="randn"):
+    """Images that carry their labels (blob + noise) so a trained network has something to segment:
+    volume [n,1,*shape] fp32, label [n,*shape] int64.  numpy streams only (regenerable on the GPU box)."""
+    from oracle import bcp_oracle as O
+    lab = O.synthetic_labels((n,) + tuple(shape), seed + 1, n_classes=n_classes)
+    noise = O.synthetic_volume((n, 1) + tuple(shape), seed, kind)
+    if kind == "randn":
+        vol = 0.6 * noise + 1.8 * (lab > 0).float().unsqueeze(1) - 0.3
+    else:
+        vol = (0.35 * noise + 0.2 * lab.float().unsqueeze(1)).clamp_(0.0, 1.0)
+    return vol.contiguous(), lab
+
+
+def packbits(t) -> np.ndarray:
+    a = t.detach().cpu().numpy() if torch.is_tensor(t) else np.asarray(t)
+    return np.packbits(a.astype(bool).reshape(-1))
+
+
+def unpackbits(a, shape) -> np.ndarray:
+    n = int(np.prod(shape))
+    return np.unpackbits(np.asarray(a))[:n].reshape(shape)

@@ -28,7 +28,7 @@ sys.path.insert(0, os.path.abspath(os.path.join(HERE, "..", "..")))
 from oracle import ref_shims  # noqa: E402
 from oracle import bcp_oracle as O  # noqa: E402
 from tests.golden.golden_common import (InjectedDropout, inject_dropout, tensor_digest, digest_named,  # noqa: E402
-                                        find_box_seed_la)
+                                        find_box_seed_la, pack_weights_bf16, unpack_weights_bf16, synthetic_scene, packbits)
 
 torch.set_num_threads(os.cpu_count() or 8)
 R = ref_shims.load()
@@ -428,6 +428,124 @@ def gen_sliding_window():
     save("sliding_window", **out)
 
 
+# ------------------------------------------------------------------ fixtures on the SHIPPED checkpoints
+CKPT = {"la10": os.path.join(ref_shims.REF_ROOT, "models", "LA", "LA_10.pth"),
+        "acdc10": os.path.join(ref_shims.REF_ROOT, "models", "ACDC", "ACDC_10.pth")}
+SURE_MARGIN = 0.25        # |logit margin| above which a pseudo label is called "sure" (bf16 noise cannot flip it)
+
+
+def gen_ckpt_weights():
+    """models/LA/LA_10.pth and models/ACDC/ACDC_10.pth rounded to bf16 (tests/golden/weights_*_bf16.npz): the trained
+    weights the step fixtures below -- and bench.py -- run on (non-degenerate pseudo labels)."""
+    for tag, path in CKPT.items():
+        sd = torch.load(path, map_location="cpu")
+        np.savez_compressed(os.path.join(HERE, "weights_%s_bf16.npz" % tag), **pack_weights_bf16(sd))
+        print("wrote weights", tag, os.path.getsize(os.path.join(HERE, "weights_%s_bf16.npz" % tag)) // 1024, "KiB")
+
+
+def _ckpt_sd(tag):
+    return unpack_weights_bf16(np.load(os.path.join(HERE, "weights_%s_bf16.npz" % tag)))
+
+
+def gen_la_ckpt_step(nsteps=2):
+    """LA_BCP_train.py:234-270 at BASELINE configs[1] (8 volumes 112x112x80) from the shipped LA_10 weights: the teacher
+    is a trained network, so its pseudo labels are decided (no plab_override in the parity test)."""
+    t0 = time.time()
+    shape = (112, 112, 80)
+    model = R.net_factory.net_factory("VNet", 1, 2, "train")
+    ema = R.net_factory.net_factory("VNet", 1, 2, "train")
+    for p in ema.parameters():
+        p.detach_()
+    sd = _ckpt_sd("la10")
+    model.load_state_dict(sd)
+    ema.load_state_dict(sd)
+    model.train()
+    ema.train()
+    inject_dropout(model, seed=252)
+    inject_dropout(ema, seed=253)
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=0.0001)
+    out = dict(shape=np.array(shape), box_seed=1337, nsteps=nsteps, sub=4, sure_margin=SURE_MARGIN)
+    np.random.seed(1337)
+    for it in range(nsteps):
+        vol, lab = synthetic_scene(8, shape, 260 + 10 * it)
+        # teacher logits of this step (before the step changes the EMA net): same dropout-stream position as the step's own
+        # calls, so run the step and capture the teacher outputs through a forward hook
+        cap = []
+        h = ema.register_forward_hook(lambda m, i, o: cap.append(o[0].detach().clone()))
+        r = la_step_reference(model, ema, opt, vol, lab)
+        h.remove()
+        t_logits = torch.cat(cap[:2])
+        margin = t_logits[:, 1] - t_logits[:, 0]
+        for k in ("loss", "loss_l", "loss_u"):
+            out[f"s{it}_{k}"] = r[k]
+        out[f"s{it}_plab"] = packbits(torch.cat([r["plab_a"], r["plab_b"]]))
+        out[f"s{it}_plab_raw"] = packbits(margin >= 0)           # softmax >= 0.5 before largest-CC (informative; the
+        out[f"s{it}_sure"] = packbits(margin.abs() >= SURE_MARGIN)  # bit-exact kernel check lives in test_gpu_primitives)
+        out[f"s{it}_teacher_logits"] = t_logits[..., ::4, ::4, ::4]
+        out[f"s{it}_out_l"] = r["out_l"][..., ::4, ::4, ::4]
+        out[f"s{it}_out_u"] = r["out_u"][..., ::4, ::4, ::4]
+        out[f"s{it}_mixl_digest"] = tensor_digest(r["mixl"])
+        out[f"s{it}_mixu_digest"] = tensor_digest(r["mixu"])
+        out[f"s{it}_grad_digest"] = digest_named({n: p.grad for n, p in model.named_parameters() if p.grad is not None})
+        out[f"s{it}_model_digest"] = digest_named(model.state_dict())
+        out[f"s{it}_ema_digest"] = digest_named(ema.state_dict())
+        print("la_ckpt step", it, "loss", float(r["loss"]), "plab fg", float(torch.cat([r["plab_a"], r["plab_b"]]).float().mean()),
+              "sure", float((margin.abs() >= SURE_MARGIN).float().mean()), "t=%.1fs" % (time.time() - t0))
+    save("la_ckpt_step", **out)
+
+
+def gen_acdc_ckpt_step(nsteps=2):
+    """ACDC_BCP_train.py:354-390 at BASELINE configs[2] (batch 24 / labeled 12 of 256x256) from the shipped ACDC_10."""
+    model = R.net_factory.BCP_net(1, 4)
+    ema = R.net_factory.BCP_net(1, 4, ema=True)
+    sd = _ckpt_sd("acdc10")
+    model.load_state_dict(sd)
+    ema.load_state_dict(sd)
+    model.train()
+    ema.train()
+    inject_dropout(model, seed=292)
+    inject_dropout(ema, seed=293)
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=0.0001)
+    H, W, B, labeled_bs = 256, 256, 24, 12
+    out = dict(shape=np.array([H, W]), B=B, labeled_bs=labeled_bs, sure_margin=SURE_MARGIN, nsteps=nsteps)
+    np.random.seed(1337)
+    for it in range(nsteps):
+        volume_batch, label_batch = synthetic_scene(B, (H, W), 300 + 10 * it, n_classes=4, kind="rand")
+        label_batch = label_batch.to(torch.uint8)
+        ls, us = labeled_bs // 2, (B - labeled_bs) // 2
+        img_a, img_b = volume_batch[:ls], volume_batch[ls:labeled_bs]
+        uimg_a, uimg_b = volume_batch[labeled_bs:labeled_bs + us], volume_batch[labeled_bs + us:]
+        lab_a, lab_b = label_batch[:ls], label_batch[ls:labeled_bs]
+        with torch.no_grad():
+            pre_a, pre_b = ema(uimg_a), ema(uimg_b)
+            plab_a = ACDC_ns.get_ACDC_masks(pre_a, nms=1)
+            plab_b = ACDC_ns.get_ACDC_masks(pre_b, nms=1)
+            img_mask, loss_mask = ACDC_ns.generate_mask(img_a)
+        net_input_unl = uimg_a * img_mask + img_a * (1 - img_mask)
+        net_input_l = img_b * img_mask + uimg_b * (1 - img_mask)
+        out_unl, out_l = model(net_input_unl), model(net_input_l)
+        unl_dice, unl_ce = ACDC_ns.mix_loss(out_unl, plab_a, lab_a, loss_mask, u_weight=0.5, unlab=True)
+        l_dice, l_ce = ACDC_ns.mix_loss(out_l, lab_b, plab_b, loss_mask, u_weight=0.5)
+        loss_ce, loss_dice = unl_ce + l_ce, unl_dice + l_dice
+        loss = (loss_dice + loss_ce) / 2
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        ACDC_ns.update_model_ema(model, ema, 0.99)
+        pre = torch.cat([pre_a, pre_b])
+        top2 = pre.topk(2, dim=1).values
+        out.update({f"s{it}_loss": loss.detach(), f"s{it}_loss_dice": loss_dice.detach(), f"s{it}_loss_ce": loss_ce.detach(),
+                    f"s{it}_plab": torch.cat([plab_a, plab_b]).to(torch.uint8), f"s{it}_plab_raw": pre.argmax(1).to(torch.uint8),
+                    f"s{it}_sure": packbits((top2[:, 0] - top2[:, 1]) >= SURE_MARGIN),
+                    f"s{it}_teacher_logits": pre[..., ::4, ::4], f"s{it}_out_unl": out_unl.detach()[..., ::4, ::4],
+                    f"s{it}_out_l": out_l.detach()[..., ::4, ::4],
+                    f"s{it}_grad_digest": digest_named({n: p.grad for n, p in model.named_parameters() if p.grad is not None}),
+                    f"s{it}_model_digest": digest_named(model.state_dict()), f"s{it}_ema_digest": digest_named(ema.state_dict())})
+        print("acdc_ckpt step", it, float(loss), "plab classes", np.bincount(torch.cat([plab_a, plab_b]).long().flatten().numpy(), minlength=4),
+              "sure", float(((top2[:, 0] - top2[:, 1]) >= SURE_MARGIN).float().mean()))
+    save("acdc_ckpt_step", **out)
+
+
 def gen_pan_step():
     t0 = time.time()
     net, ema = R.pan_Vnet.VNet(), R.pan_Vnet.VNet()
@@ -471,7 +589,14 @@ def gen_pan_step():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["functions", "networks", "la_small", "la_pre", "acdc", "la_full", "pan", "acdc_pre", "pan_pre", "sliding"]
+    which = sys.argv[1:] or ["functions", "networks", "la_small", "la_pre", "acdc", "la_full", "pan", "acdc_pre", "pan_pre", "sliding",
+                             "ckpt_weights", "la_ckpt", "acdc_ckpt"]
+    if "ckpt_weights" in which:
+        gen_ckpt_weights()
+    if "la_ckpt" in which:
+        gen_la_ckpt_step()
+    if "acdc_ckpt" in which:
+        gen_acdc_ckpt_step()
     if "sliding" in which:
         gen_sliding_window()
     if "acdc_pre" in which:

@@ -59,15 +59,19 @@ def run(n, cin, cout, dims, kernel, mode="rand", verbose=True):
     return e_t
 
 
-def run_prof(n, c, dims, kernel=(3, 3, 3)):
-    """Per-role wait cycles of the instrumented forward kernel (bcp_conv_tc_debug_profile)."""
+def run_prof(n, c, dims, kernel=(3, 3, 3), fold=False):
+    """Per-role wait cycles of the instrumented forward kernels (bcp_conv_tc_fwd_profiled; fold=True: dz-folded kernel)."""
+    from bcp_b200._native import ptr, stream
     torch.manual_seed(0)
     x = torch.randn(n, c, *dims, device=dev).to(torch.bfloat16).float()
     w = (torch.randn(c, c, *kernel, device=dev) / np.sqrt(c * 27)).to(torch.bfloat16).float()
     b = torch.zeros(c, device=dev)
     pack = _packs(ops, dev, w, (0, 1))
     a = cb8_from_planar(x)
-    rc, pl = plan(n, c, c, dims, kernel)
+    out = (ctypes.c_int * 10)()
+    LIB.query("bcp_conv_tc_fold_plan" if fold else "bcp_conv_tc_plan", n, c, c, i3(*dims), i3(*kernel), out)
+    pl = list(out)
+    ops._TC_FOLD = fold
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     for _ in range(3):
         ops._conv_same(a, pack.k[0], b, c, kernel, allow_tc=True)
@@ -79,15 +83,15 @@ def run_prof(n, c, dims, kernel=(3, 3, 3)):
     us = ev[0].elapsed_time(ev[1]) * 100.0
     flops = 2.0 * n * np.prod(dims) * c * c * 27
     buf = torch.zeros(160 * 16, dtype=torch.int64, device=dev)
-    LIB.call("bcp_conv_tc_debug_profile", buf.data_ptr())
-    ops._conv_same(a, pack.k[0], b, c, kernel, allow_tc=True)
+    y = torch.empty(ops.cb8_shape(n, c, *dims), dtype=torch.bfloat16, device=dev)
+    LIB.call("bcp_conv_tc_fwd_profiled", ptr(a), ptr(pack.k[0]), ptr(b), ptr(y), n, c, c, i3(*dims), i3(*kernel), 1 if fold else 0,
+             buf.data_ptr(), stream())
     torch.cuda.synchronize()
-    LIB.call("bcp_conv_tc_debug_profile", None)
     p = buf.cpu().numpy().reshape(160, 16)
     p = p[p[:, 0] > 0]
     names = ["total", "prod_wait_emptyA", "prod_wait_emptyB", "mma_wait_fullA", "mma_wait_fullB", "mma_wait_tmem_empty",
              "epi_wait_tmem_full", "epi_work", "mma_loop_end", "items"]
-    print(f"[prof] n={n} c={c} dims={dims} plan(BX,BY,BZ,MT,SA,NS*100+TG,AS,nb,cols,smem)={pl} {us:.1f} us "
+    print(f"[prof{'-fold' if fold else ''}] n={n} c={c} dims={dims} plan(BX,BY,BZ,MT,SA,SB|NS*100+TG,AS,nb,cols,smem)={pl} {us:.1f} us "
           f"{flops / us * 1e-6:.1f} TF/s ctas={len(p)}", flush=True)
     print("       " + "  ".join(f"{nm}={p[:, i].mean():.0f}(max {p[:, i].max()})" for i, nm in enumerate(names)), flush=True)
 
@@ -211,8 +215,13 @@ if __name__ == "__main__":
             print(f"[fold] n={n} c={cin}->{cout} dims={dims} std err {res['std'][0]:.2e} {res['std'][1]:.1f} us | "
                   f"fold err {res['fold'][0]:.2e} {res['fold'][1]:.1f} us", flush=True)
     if "--prof" in sys.argv:
+        ops._TC_FOLD = False
         for cfg in [(4, 16, (112, 112, 80)), (4, 32, (56, 56, 40)), (4, 64, (28, 28, 20)), (4, 128, (14, 14, 10)), (4, 256, (7, 7, 5))]:
             run_prof(*cfg)
+    if "--prof-fold" in sys.argv:
+        for cfg in [(4, 16, (112, 112, 80)), (4, 32, (56, 56, 40))]:
+            run_prof(*cfg, fold=True)
+        ops._TC_FOLD = False
     if "--wgrad" in sys.argv:
         ww = 0.0
         for cfg in [(1, 16, 16, (4, 6, 8), (3, 3, 3)), (2, 16, 16, (8, 12, 20), (3, 3, 3)), (2, 32, 32, (6, 10, 12), (3, 3, 3)),
