@@ -34,7 +34,7 @@ def _norm_bwd_kernels(args):
 
 KERNELS_PER_CALL = {
     "bcp_norm_stats": 1, "bcp_norm_bwd": _norm_bwd_kernels, "bcp_mix_loss_fwd": 2, "bcp_conv_direct_wgrad": 2,
-    "bcp_chan_sum": 2, "bcp_conv_first_wgrad": 2, "bcp_head_wgrad": 2, "bcp_largest_cc": 5,
+    "bcp_chan_sum": 2, "bcp_dice_prob_fwd": 2, "bcp_conv_first_wgrad": 2, "bcp_head_wgrad": 2, "bcp_largest_cc": 5,
 }
 
 

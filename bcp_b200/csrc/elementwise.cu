@@ -45,6 +45,69 @@ __global__ void label_mix_kernel(const unsigned char* __restrict__ a, const unsi
   }
 }
 
+// 128-bit versions (Z % 4 == 0 / Z % 16 == 0, 16-byte aligned bases, < 2^31 elements): one thread moves a run of 4 floats
+// (16 labels) that lies inside ONE z-line, so the (x, y) part of the box test and the 32-bit index decomposition happen once
+// per run; only the z compare is per element.  Same literal arithmetic per element as the scalar kernel (bit-exact).
+__global__ void __launch_bounds__(256) mask_mix_vec4_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
+                                                            float4* __restrict__ out, unsigned total4, unsigned X, unsigned Y,
+                                                            unsigned Z4, int Z, const int* __restrict__ box) {
+  const int bx0 = __ldg(box), by0 = __ldg(box + 1), bz0 = __ldg(box + 2);
+  const int bx1 = min(bx0 + __ldg(box + 3), (int)X), by1 = min(by0 + __ldg(box + 4), (int)Y), bz1 = min(bz0 + __ldg(box + 5), Z);
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
+    unsigned r = i;
+    const int z = (int)(r % Z4) * 4; r /= Z4;
+    const int y = (int)(r % Y); r /= Y;
+    const int x = (int)(r % X);
+    const bool row = (x >= bx0) & (x < bx1) & (y >= by0) & (y < by1);
+    const float4 va = __ldg(a + i), vb = __ldg(b + i);
+    const float m0 = (row & (z >= bz0) & (z < bz1)) ? 0.f : 1.f;
+    const float m1 = (row & (z + 1 >= bz0) & (z + 1 < bz1)) ? 0.f : 1.f;
+    const float m2 = (row & (z + 2 >= bz0) & (z + 2 < bz1)) ? 0.f : 1.f;
+    const float m3 = (row & (z + 3 >= bz0) & (z + 3 < bz1)) ? 0.f : 1.f;
+    float4 o;
+    o.x = __fadd_rn(__fmul_rn(va.x, m0), __fmul_rn(vb.x, 1.f - m0));
+    o.y = __fadd_rn(__fmul_rn(va.y, m1), __fmul_rn(vb.y, 1.f - m1));
+    o.z = __fadd_rn(__fmul_rn(va.z, m2), __fmul_rn(vb.z, 1.f - m2));
+    o.w = __fadd_rn(__fmul_rn(va.w, m3), __fmul_rn(vb.w, 1.f - m3));
+    out[i] = o;
+  }
+}
+
+__global__ void __launch_bounds__(256) label_mix_vec16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
+                                                              uint4* __restrict__ out, unsigned total16, unsigned X, unsigned Y,
+                                                              unsigned Z16, int Z, const int* __restrict__ box) {
+  const int bx0 = __ldg(box), by0 = __ldg(box + 1), bz0 = __ldg(box + 2);
+  const int bx1 = min(bx0 + __ldg(box + 3), (int)X), by1 = min(by0 + __ldg(box + 4), (int)Y), bz1 = min(bz0 + __ldg(box + 5), Z);
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total16; i += stride) {
+    unsigned r = i;
+    const int z = (int)(r % Z16) * 16; r /= Z16;
+    const int y = (int)(r % Y); r /= Y;
+    const int x = (int)(r % X);
+    const bool row = (x >= bx0) & (x < bx1) & (y >= by0) & (y < by1);
+    const uint4 va = __ldg(a + i), vb = __ldg(b + i);
+    // byte-select mask: 0xFF where the voxel lies inside the box (take b)
+    unsigned sel[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      unsigned mword = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int zz = z + w * 4 + k;
+        if (row & (zz >= bz0) & (zz < bz1)) mword |= 0xFFu << (8 * k);
+      }
+      sel[w] = mword;
+    }
+    uint4 o;
+    o.x = (va.x & ~sel[0]) | (vb.x & sel[0]);
+    o.y = (va.y & ~sel[1]) | (vb.y & sel[1]);
+    o.z = (va.z & ~sel[2]) | (vb.z & sel[2]);
+    o.w = (va.w & ~sel[3]) | (vb.w & sel[3]);
+    out[i] = o;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // pseudo labels.  thresh: (softmax(x,1) >= thr)[:,1]   (LA_BCP_train.py:57-60, pancreas_utils.py:275-278)
 //                 argmax: torch.max(softmax(x,1),1)[1] (ACDC_BCP_train.py:112-114)
@@ -88,6 +151,47 @@ __global__ void pseudo_label_kernel(const float* __restrict__ logits, unsigned c
   }
 }
 
+// 128-bit version (V % 4 == 0): four voxels per thread, one float4 per class plane, one 32-bit store of four labels.
+template <int C>
+__global__ void __launch_bounds__(256) pseudo_label_vec4_kernel(const float4* __restrict__ logits, uchar4* __restrict__ out,
+                                                                unsigned N, unsigned V4, int mode, float thr) {
+  const unsigned total4 = N * V4, stride = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
+    const unsigned n = i / V4, v = i - n * V4;
+    const float4* p = logits + (size_t)n * C * V4 + v;
+    float x[C][4];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float4 t = __ldg(p + (size_t)c * V4);
+      x[c][0] = t.x; x[c][1] = t.y; x[c][2] = t.z; x[c][3] = t.w;
+    }
+    unsigned char lab[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float m = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < C; ++c) m = fmaxf(m, x[c][k]);
+      float e[C];
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) { e[c] = exp_near_one(x[c][k] - m); s += e[c]; }
+      if (mode == 0) {
+        lab[k] = (__fdiv_rn(e[1], s) >= thr) ? 1 : 0;
+      } else {
+        float best = __fdiv_rn(e[0], s);
+        int bi = 0;
+#pragma unroll
+        for (int c = 1; c < C; ++c) {
+          const float pc = __fdiv_rn(e[c], s);
+          if (pc > best) { best = pc; bi = c; }
+        }
+        lab[k] = (unsigned char)bi;
+      }
+    }
+    out[i] = make_uchar4(lab[0], lab[1], lab[2], lab[3]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // fused SGD(momentum, weight decay) + EMA over a flat fp32 arena (optim.SGD semantics,
 // LA_BCP_train.py:218 + utils/BCP_utils.py:78-81).  hyper = {lr, momentum, wd, ema_alpha, grad_scale, 1-ema_alpha}
@@ -95,42 +199,101 @@ __global__ void pseudo_label_kernel(const float* __restrict__ logits, unsigned c
 //   g = grad*grad_scale + wd*p ; buf = mom*buf + g ; p -= lr*buf ; e = e*alpha + (1-alpha)*p
 // elements [n_train, n_total) are EMA-only (never-trained MLP heads / BN buffers for ACDC).
 // ------------------------------------------------------------------------------------------
-__global__ void sgd_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
-                               float* __restrict__ e, const float* __restrict__ hyper, long long n_train, long long n_total) {
+// One thread owns four consecutive floats: 128-bit loads/stores of p, g, buf, e (the arenas are allocator-aligned); the
+// n_train boundary (EMA-only tail) is a per-element predicate inside the vector.
+__global__ void __launch_bounds__(256) sgd_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
+                                                      float* __restrict__ e, const float* __restrict__ hyper, long long n_train,
+                                                      long long n_total) {
   const float lr = hyper[0], mom = hyper[1], wd = hyper[2], alpha = hyper[3], gs = hyper[4];
   const float one_m_alpha = hyper[5];   // float(1 - alpha) evaluated in double on the host, like the Python expression
+  const long long n4 = (n_total + 3) >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_total; i += stride) {
-    float pv = p[i];
-    if (i < n_train) {
-      const float gv = g[i] * gs + wd * pv;
-      const float bv = mom * buf[i] + gv;
-      buf[i] = bv;
-      pv = pv - lr * bv;
-      p[i] = pv;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
+    const long long i0 = q << 2;
+    if (i0 + 4 <= n_total) {
+      float4 pv = *reinterpret_cast<const float4*>(p + i0);
+      float* pf = reinterpret_cast<float*>(&pv);
+      if (i0 < n_train) {
+        if (i0 + 4 <= n_train) {
+          const float4 gv = *reinterpret_cast<const float4*>(g + i0);
+          float4 bv = *reinterpret_cast<const float4*>(buf + i0);
+          const float* gf = reinterpret_cast<const float*>(&gv);
+          float* bf = reinterpret_cast<float*>(&bv);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float gk = gf[k] * gs + wd * pf[k];
+            bf[k] = mom * bf[k] + gk;
+            pf[k] = pf[k] - lr * bf[k];
+          }
+          *reinterpret_cast<float4*>(buf + i0) = bv;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (i0 + k < n_train) {
+              const float gk = g[i0 + k] * gs + wd * pf[k];
+              const float bk = mom * buf[i0 + k] + gk;
+              buf[i0 + k] = bk;
+              pf[k] = pf[k] - lr * bk;
+            }
+        }
+        *reinterpret_cast<float4*>(p + i0) = pv;
+      }
+      if (e != nullptr) {
+        float4 ev = *reinterpret_cast<const float4*>(e + i0);
+        float* ef = reinterpret_cast<float*>(&ev);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ef[k] = __fadd_rn(__fmul_rn(ef[k], alpha), __fmul_rn(one_m_alpha, pf[k]));
+        *reinterpret_cast<float4*>(e + i0) = ev;
+      }
+    } else {
+      for (long long i = i0; i < n_total; ++i) {
+        float pv = p[i];
+        if (i < n_train) {
+          const float gv = g[i] * gs + wd * pv;
+          const float bv = mom * buf[i] + gv;
+          buf[i] = bv;
+          pv = pv - lr * bv;
+          p[i] = pv;
+        }
+        if (e != nullptr) e[i] = __fadd_rn(__fmul_rn(e[i], alpha), __fmul_rn(one_m_alpha, pv));
+      }
     }
-    if (e != nullptr) e[i] = __fadd_rn(__fmul_rn(e[i], alpha), __fmul_rn(one_m_alpha, pv));
   }
 }
 
-// Adam (optim.Adam defaults, pancreas/dataloaders.py:182) + EMA.  hyper = {lr, beta1, beta2, eps, ema_alpha,
-// grad_scale, bias_corr1, bias_corr2_sqrt, 1-ema_alpha}; the two bias corrections are refreshed by the host each step.
-__global__ void adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                float* __restrict__ v, float* __restrict__ e, const float* __restrict__ hyper,
-                                long long n_train, long long n_total) {
-  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], alpha = hyper[4], gs = hyper[5];
-  const float bc1 = hyper[6], bc2s = hyper[7];
+// Adam (optim.Adam defaults, pancreas/dataloaders.py:182) + EMA.  hyper = {lr, beta1, beta2, eps, ema_alpha, grad_scale,
+// bias_corr1, bias_corr2_sqrt, 1-ema_alpha, step_size = lr / bias_corr1}.  Slots 6, 7, 9 are produced ON THE DEVICE by
+// adam_tick_kernel from a device-resident step counter (so a captured CUDA graph advances the bias corrections on every
+// replay), in double precision like the Python expressions of torch.optim.Adam.
+__global__ void adam_tick_kernel(float* __restrict__ hyper, long long* __restrict__ step) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const long long t = step[0] + 1;
+    step[0] = t;
+    const double b1 = (double)hyper[1], b2 = (double)hyper[2];
+    const double bc1 = 1.0 - pow(b1, (double)t), bc2 = 1.0 - pow(b2, (double)t);
+    hyper[6] = (float)bc1;
+    hyper[7] = (float)sqrt(bc2);
+    hyper[9] = (float)((double)hyper[0] / bc1);
+  }
+}
+
+__global__ void __launch_bounds__(256) adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                       float* __restrict__ v, float* __restrict__ e, const float* __restrict__ hyper,
+                                                       long long n_train, long long n_total) {
+  const float b1 = hyper[1], b2 = hyper[2], eps = hyper[3], alpha = hyper[4], gs = hyper[5];
+  const float bc2s = hyper[7], step_size = hyper[9];
   const float one_m_alpha = hyper[8];
+  const float w1 = 1.f - b1, w2 = 1.f - b2;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_total; i += stride) {
     float pv = p[i];
     if (i < n_train) {
       const float gv = g[i] * gs;
-      const float mv = b1 * m[i] + (1.f - b1) * gv;
-      const float vv = b2 * v[i] + (1.f - b2) * gv * gv;
+      const float mv = fmaf(w1, gv - m[i], m[i]);              // exp_avg.lerp_(grad, 1 - beta1)
+      const float vv = fmaf(w2 * gv, gv, v[i] * b2);            // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
       m[i] = mv; v[i] = vv;
       const float denom = sqrtf(vv) / bc2s + eps;
-      pv = pv - (lr / bc1) * (mv / denom);
+      pv = pv - step_size * (mv / denom);
       p[i] = pv;
     }
     if (e != nullptr) e[i] = __fadd_rn(__fmul_rn(e[i], alpha), __fmul_rn(one_m_alpha, pv));
@@ -264,7 +427,12 @@ int bcp_mask_mix(const float* a, const float* b, float* out, int n, int c, int X
   BCP_REQUIRE(a && b && out && box6_dev, "mask_mix: null pointer");
   BCP_REQUIRE(n > 0 && c > 0 && X > 0 && Y > 0 && Z > 0, "mask_mix: bad shape");
   const long long total = (long long)n * c * X * Y * Z;
-  mask_mix_kernel<<<grid_for(total, 256), 256, 0, stream>>>(a, b, out, total, X, Y, Z, box6_dev);
+  const bool aligned = ((((uintptr_t)a) | ((uintptr_t)b) | ((uintptr_t)out)) & 15) == 0;
+  if (Z % 4 == 0 && aligned && total < (1ll << 31))
+    mask_mix_vec4_kernel<<<grid_for(total / 4, 256), 256, 0, stream>>>((const float4*)a, (const float4*)b, (float4*)out,
+                                                                         (unsigned)(total / 4), X, Y, Z / 4, Z, box6_dev);
+  else
+    mask_mix_kernel<<<grid_for(total, 256), 256, 0, stream>>>(a, b, out, total, X, Y, Z, box6_dev);
   return check_launch("mask_mix");
 }
 
@@ -272,7 +440,12 @@ int bcp_label_mix(const unsigned char* a, const unsigned char* b, unsigned char*
                   const int* box6_dev, cudaStream_t stream) {
   BCP_REQUIRE(a && b && out && box6_dev && n > 0 && X > 0 && Y > 0 && Z > 0, "label_mix: bad args");
   const long long total = (long long)n * X * Y * Z;
-  label_mix_kernel<<<grid_for(total, 256), 256, 0, stream>>>(a, b, out, total, X, Y, Z, box6_dev);
+  const bool aligned = ((((uintptr_t)a) | ((uintptr_t)b) | ((uintptr_t)out)) & 15) == 0;
+  if (Z % 16 == 0 && aligned && total < (1ll << 31))
+    label_mix_vec16_kernel<<<grid_for(total / 16, 256), 256, 0, stream>>>((const uint4*)a, (const uint4*)b, (uint4*)out,
+                                                                            (unsigned)(total / 16), X, Y, Z / 16, Z, box6_dev);
+  else
+    label_mix_kernel<<<grid_for(total, 256), 256, 0, stream>>>(a, b, out, total, X, Y, Z, box6_dev);
   return check_launch("label_mix");
 }
 
@@ -283,7 +456,12 @@ int bcp_pseudo_label(const float* logits, unsigned char* out, int n, int c, long
   BCP_REQUIRE(mode == 0 || mode == 1, "pseudo_label: mode");
   BCP_REQUIRE(!(mode == 0 && c != 2), "pseudo_label: threshold mode takes channel 1 of 2");
   const long long total = (long long)n * v;
-  if (c == 2)
+  const bool aligned = ((((uintptr_t)logits) & 15) | (((uintptr_t)out) & 3)) == 0;
+  if (v % 4 == 0 && aligned && total * c < (1ll << 31)) {
+    const int grid = grid_for(total / 4, 256);
+    if (c == 2) pseudo_label_vec4_kernel<2><<<grid, 256, 0, stream>>>((const float4*)logits, (uchar4*)out, n, (unsigned)(v / 4), mode, thr);
+    else pseudo_label_vec4_kernel<4><<<grid, 256, 0, stream>>>((const float4*)logits, (uchar4*)out, n, (unsigned)(v / 4), mode, thr);
+  } else if (c == 2)
     pseudo_label_kernel<2><<<grid_for(total, 256), 256, 0, stream>>>(logits, out, n, v, mode, thr);
   else
     pseudo_label_kernel<4><<<grid_for(total, 256), 256, 0, stream>>>(logits, out, n, v, mode, thr);
@@ -295,7 +473,9 @@ int bcp_sgd_ema_step(float* params, const float* grads, float* momentum, float* 
   BCP_REQUIRE(params && grads && momentum && hyper, "sgd_ema_step: null pointer");
   BCP_REQUIRE(n_train >= 0 && n_total >= n_train, "sgd_ema_step: bad sizes");
   if (n_total == 0) return BCP_OK;
-  sgd_ema_kernel<<<grid_for(n_total, 256), 256, 0, stream>>>(params, grads, momentum, ema, hyper, n_train, n_total);
+  BCP_REQUIRE(((((uintptr_t)params) | ((uintptr_t)grads) | ((uintptr_t)momentum) | ((uintptr_t)ema)) & 15) == 0,
+              "sgd_ema_step: arenas must be 16-byte aligned");
+  sgd_ema_kernel<<<grid_for((n_total + 3) / 4, 256), 256, 0, stream>>>(params, grads, momentum, ema, hyper, n_train, n_total);
   return check_launch("sgd_ema_step");
 }
 
@@ -306,6 +486,12 @@ int bcp_adam_ema_step(float* params, const float* grads, float* exp_avg, float* 
   if (n_total == 0) return BCP_OK;
   adam_ema_kernel<<<grid_for(n_total, 256), 256, 0, stream>>>(params, grads, exp_avg, exp_avg_sq, ema, hyper, n_train, n_total);
   return check_launch("adam_ema_step");
+}
+
+int bcp_adam_tick(float* hyper, long long* step, cudaStream_t stream) {
+  BCP_REQUIRE(hyper && step, "adam_tick: null pointer");
+  adam_tick_kernel<<<1, 32, 0, stream>>>(hyper, step);
+  return check_launch("adam_tick");
 }
 
 int bcp_ema_i64(long long* ema, const long long* model, int n, float alpha, float one_minus_alpha, cudaStream_t stream) {

@@ -234,6 +234,79 @@ __global__ void __launch_bounds__(LT) mix_loss_bwd_kernel(const float* __restric
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// DiceLoss on PROBABILITIES (utils/losses.py:113-134 as called from ACDC_BCP_train.py:170,175 with softmax=False):
+// batch-global per-class  1 - (2*sum(s*t*m) + 1e-10) / (sum(s*s*m) + sum(t*t*m) + 1e-10), mean over classes.
+// The drop-in utils.losses.DiceLoss uses this pair so the reference's own mix_loss body (which calls F.softmax itself)
+// runs unchanged.  partial[(blk*C + c)*3 + {I,Y,Z}]; ctx = {loss, -, cA[C], cC[C]}: dL/ds_c(v) = m*(cA_c*[t==c] + cC_c*s).
+// ------------------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(LT) dice_prob_fwd_kernel(const float* __restrict__ probs, const unsigned char* __restrict__ target,
+                                                            const unsigned char* __restrict__ mask, float* __restrict__ partial,
+                                                            int N, long long V) {
+  float acc[3 * C];
+#pragma unroll
+  for (int k = 0; k < 3 * C; ++k) acc[k] = 0.f;
+  const long long total = (long long)N * V, stride = (long long)gridDim.x * LT;
+  for (long long i = (long long)blockIdx.x * LT + threadIdx.x; i < total; i += stride) {
+    const long long n = i / V, v = i - n * V;
+    const float m = mask ? (mask[i] ? 1.f : 0.f) : 1.f;
+    const int t = target[i];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float sc = probs[(n * C + c) * V + v];
+      const float oh = (t == c) ? 1.f : 0.f;
+      acc[c * 3 + 0] += sc * oh * m;
+      acc[c * 3 + 1] += oh * m;
+      acc[c * 3 + 2] += sc * sc * m;
+    }
+  }
+  __shared__ float red[3 * C * (LT / 32)];
+  block_sum<3 * C, LT>(acc, red);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < 3 * C; ++k) partial[(long long)blockIdx.x * 3 * C + k] = acc[k];
+  }
+}
+
+template <int C>
+__global__ void dice_prob_finalize_kernel(const float* __restrict__ partial, float* __restrict__ ctx, int blocks) {
+  double a[3 * C];
+  sum_partials<3 * C>(partial, 0, blocks, a);
+  if (threadIdx.x != 0) return;
+  const double eps = 1e-10;
+  double loss = 0.0;
+  for (int c = 0; c < C; ++c) {
+    const double I = a[c * 3], Y = a[c * 3 + 1], Z = a[c * 3 + 2];
+    const double den = Z + Y + eps;
+    loss += 1.0 - (2.0 * I + eps) / den;
+    ctx[2 + c] = (float)(-2.0 / den / C);
+    ctx[2 + C + c] = (float)(2.0 * (2.0 * I + eps) / (den * den) / C);
+  }
+  ctx[0] = (float)(loss / C);
+  ctx[1] = 0.f;
+}
+
+template <int C>
+__global__ void __launch_bounds__(LT) dice_prob_bwd_kernel(const float* __restrict__ probs, const unsigned char* __restrict__ target,
+                                                            const unsigned char* __restrict__ mask, const float* __restrict__ ctx,
+                                                            const float* __restrict__ gout, float* __restrict__ dprobs, int N, long long V) {
+  const float g = gout[0];
+  const long long total = (long long)N * V, stride = (long long)gridDim.x * LT;
+  for (long long i = (long long)blockIdx.x * LT + threadIdx.x; i < total; i += stride) {
+    const long long n = i / V, v = i - n * V;
+    const float m = mask ? (mask[i] ? 1.f : 0.f) : 1.f;
+    const int t = target[i];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const long long j = (n * C + c) * V + v;
+      const float oh = (t == c) ? 1.f : 0.f;
+      dprobs[j] = g * m * (ctx[2 + c] * oh + ctx[2 + C + c] * probs[j]);
+    }
+  }
+}
+
 static inline int loss_blocks(long long V) {
   long long b = (V + 8191) / 8192;
   if (b < 1) b = 1;
@@ -286,6 +359,32 @@ int bcp_mix_loss_bwd(const float* logits, const unsigned char* lab_img, const un
   else
     mix_loss_bwd_kernel<4><<<(int)blocks, LT, 0, stream>>>(logits, lab_img, lab_patch, mask, ctx, grad3, dlogits, n, V, X, Y, Z, box6);
   return check_launch("mix_loss_bwd");
+}
+
+long long bcp_dice_prob_ctx_floats(int c) { return 2 + 2 * (long long)c; }
+long long bcp_dice_prob_workspace_floats(int n, int c, long long v) { return (long long)loss_blocks((long long)n * v) * 3 * c; }
+
+int bcp_dice_prob_fwd(const float* probs, const unsigned char* target, const unsigned char* mask, float* ctx, float* workspace,
+                      int n, int c, long long v, cudaStream_t stream) {
+  BCP_REQUIRE(probs && target && ctx && workspace, "dice_prob_fwd: null pointer");
+  BCP_REQUIRE(c == 2 || c == 4, "dice_prob_fwd: %d classes unsupported (2 or 4)", c);
+  BCP_REQUIRE(n > 0 && v > 0, "dice_prob_fwd: bad shape");
+  const int blocks = loss_blocks((long long)n * v);
+  if (c == 2) { dice_prob_fwd_kernel<2><<<blocks, LT, 0, stream>>>(probs, target, mask, workspace, n, v); dice_prob_finalize_kernel<2><<<1, 32, 0, stream>>>(workspace, ctx, blocks); }
+  else { dice_prob_fwd_kernel<4><<<blocks, LT, 0, stream>>>(probs, target, mask, workspace, n, v); dice_prob_finalize_kernel<4><<<1, 32, 0, stream>>>(workspace, ctx, blocks); }
+  return check_launch("dice_prob_fwd");
+}
+
+int bcp_dice_prob_bwd(const float* probs, const unsigned char* target, const unsigned char* mask, const float* ctx,
+                      const float* grad_out, float* dprobs, int n, int c, long long v, cudaStream_t stream) {
+  BCP_REQUIRE(probs && target && ctx && grad_out && dprobs, "dice_prob_bwd: null pointer");
+  BCP_REQUIRE(c == 2 || c == 4, "dice_prob_bwd: %d classes unsupported", c);
+  long long blocks = ((long long)n * v + LT - 1) / LT;
+  const long long cap = (long long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (c == 2) dice_prob_bwd_kernel<2><<<(int)blocks, LT, 0, stream>>>(probs, target, mask, ctx, grad_out, dprobs, n, v);
+  else dice_prob_bwd_kernel<4><<<(int)blocks, LT, 0, stream>>>(probs, target, mask, ctx, grad_out, dprobs, n, v);
+  return check_launch("dice_prob_bwd");
 }
 
 }  // extern "C"

@@ -153,7 +153,9 @@ class Encoder(nn.Module):
         x1 = self.block_one(input)
         x2 = self.block_two(self.block_one_dw(x1))
         x3 = self.block_three(self.block_two_dw(x2))
-        x4 = self.block_four(self.block_three_dw(x3))
+        # data-parallel bucket boundary: when backward reaches this point the deep encoder layers (73 % of the parameters)
+        # have final gradients and their all-reduce overlaps the backward of the three full-resolution blocks
+        x4 = self.block_four(self.block_three_dw(self.block_three._rt.boundary(x3, "encoder.block_three_dw.conv.0.weight")))
         x4_dw = self.block_four_dw(x4)
         scale = None
         if self.has_dropout and self.dropout.training:
@@ -233,6 +235,7 @@ class VNet(nn.Module):
         rt.spg = n // groups
         try:
             feats = self.encoder(input)
+            feats[4] = rt.boundary(feats[4], "decoder.block_five_up.conv.0.weight")      # bucket boundary: decoder done
             out_seg, _ = self.decoder(feats)
             x5 = feats[4]
             features = None

@@ -36,6 +36,15 @@ class NetRuntime:
         self._versions = None
         self.dirty = True
         self.grad_arena = None
+        self.grad_ready_cb = None         # set by the fused optimiser when data parallel: callable(lo_offset)
+
+    def boundary(self, a, first_param_name):
+        """Mark a point of the forward pass after which (in backward: before which) all parameters from
+        ``first_param_name`` on have final gradients (ops.GradBoundary).  No-op unless a data-parallel optimiser listens."""
+        if self.grad_ready_cb is None or not a.requires_grad:
+            return a
+        from ..ops import GradBoundary
+        return GradBoundary.apply(a, self, self.offsets[first_param_name])
 
     # ---- registration -----------------------------------------------------------------------
     def register_conv(self, conv: nn.Module, kinds):

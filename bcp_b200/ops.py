@@ -417,6 +417,24 @@ class Head(Function):
         return da, dw, db, None
 
 
+class GradBoundary(Function):
+    """Identity in forward.  In backward it tells the optimiser that every parameter gradient stored at arena offset >=
+    ``lo`` is final (parameters are laid out in forward order and autograd runs later-created nodes first), so the
+    data-parallel all-reduce of that slice can start on the side stream while backward continues."""
+
+    @staticmethod
+    def forward(ctx, a, rt, lo):
+        ctx.rt, ctx.lo = rt, lo
+        return a.view_as(a)
+
+    @staticmethod
+    def backward(ctx, g):
+        cb = getattr(ctx.rt, "grad_ready_cb", None)
+        if cb is not None:
+            cb(ctx.lo)
+        return g, None, None
+
+
 # ----------------------------------------------------------------------------------------------
 # normalisation + activation (+ dropout) (+ residual)
 # ----------------------------------------------------------------------------------------------
@@ -646,6 +664,37 @@ class MixLoss(Function):
         LIB.call("bcp_mix_loss_bwd", ptr(logits), ptr(li), ptr(lp), ptr(mask_u8), ptr(cbuf), ptr(g3), ptr(dlog), n, c, X, Y, Z,
                  ptr(box6), stream())
         return dlog, None, None, None, None, None, None, None
+
+
+class DiceProb(Function):
+    """DiceLoss on probabilities (utils/losses.py:113-134 with softmax=False, as ACDC_BCP_train.py:170,175 calls it)."""
+
+    @staticmethod
+    def forward(ctx, probs, target_u8, mask_u8):
+        _require_cuda(probs, "dice_prob")
+        probs = probs.contiguous().float()
+        n, c = probs.shape[:2]
+        v = probs[0, 0].numel()
+        t = target_u8.contiguous()
+        assert t.dtype == torch.uint8 and t.numel() == n * v
+        if mask_u8 is not None:
+            mask_u8 = mask_u8.contiguous()
+            assert mask_u8.dtype == torch.uint8 and mask_u8.numel() == n * v
+        cbuf = _f32(LIB.query("bcp_dice_prob_ctx_floats", c), probs.device)
+        ws = _f32(LIB.query("bcp_dice_prob_workspace_floats", n, c, v), probs.device)
+        LIB.call("bcp_dice_prob_fwd", ptr(probs), ptr(t), ptr(mask_u8), ptr(cbuf), ptr(ws), n, c, v, stream())
+        ctx.save_for_backward(probs, t, mask_u8, cbuf)
+        ctx.meta = (n, c, v)
+        return cbuf[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        probs, t, mask_u8, cbuf = ctx.saved_tensors
+        n, c, v = ctx.meta
+        g = g.contiguous().float().reshape(1)
+        d = torch.empty_like(probs)
+        LIB.call("bcp_dice_prob_bwd", ptr(probs), ptr(t), ptr(mask_u8), ptr(cbuf), ptr(g), ptr(d), n, c, v, stream())
+        return d, None, None
 
 
 def to_u8_labels(t: torch.Tensor) -> torch.Tensor:

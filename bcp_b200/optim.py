@@ -5,12 +5,20 @@ FusedSGD_EMA  == torch.optim.SGD(momentum, weight_decay) (LA_BCP_train.py:218, A
                  (ACDC_BCP_train.py:123-129, mode 'state_dict': parameters + BN buffers + int64 counters).
 FusedAdam_EMA == torch.optim.Adam(lr) (pancreas/dataloaders.py:182) + pancreas/pancreas_utils.py:299-302.
 
-Data parallel: when torch.distributed is initialised the flat gradient arena is all-reduced (sum) with ONE NCCL
-call before the update and the 1/world_size average is folded into the kernel (grad_scale).
+Data parallel: when torch.distributed is initialised the flat gradient arena is all-reduced (sum) before the update and
+the 1/world_size average is folded into the kernel (grad_scale).  The reduction is bucketed: ``notify_grad_ready(lo, hi)``
+(called by the step body as backward finishes a block of layers) starts the all-reduce of that slice on a side stream so
+it overlaps the rest of backward; ``step()`` reduces whatever is left and joins the side stream.  Replicas are made
+identical at construction (rank 0's parameters / buffers / optimiser state are broadcast).
+
+Hyper-parameters live in a small device vector so a captured CUDA graph sees changes: ``refresh_hyper()`` uploads it
+(host side, outside any capture) and is what ``GraphedStep.__call__`` runs before each replay; Adam's bias corrections
+are advanced on the device by ``bcp_adam_tick``.
 """
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -22,6 +30,10 @@ def _world():
     if dist.is_available() and dist.is_initialized():
         return dist, dist.get_world_size()
     return None, 1
+
+
+def _capturing():
+    return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
 
 
 class _FusedBase:
@@ -36,15 +48,62 @@ class _FusedBase:
         self.dev = self.rt.arena.device
         self.param_groups = [{"lr": None}]
         self.step_count = 0
+        self._reduced_upto = None          # gradient-arena elements [_reduced_upto, n_train) are already being reduced
+        self._comm_stream = None
+        self._hyper_host = None
+        # Bucketed overlap is opt-in (BCP_DP_OVERLAP=1): the conv kernels are persistent one-CTA-per-SM grids with static
+        # work assignment, so a communication kernel that takes SMs away mid-backward stretches them; measured before use.
+        if _world()[1] > 1 and os.environ.get("BCP_DP_OVERLAP", "0") == "1":
+            self.rt.grad_ready_cb = self.notify_grad_ready
+
+    # ---- data-parallel plumbing ---------------------------------------------------------------
+    def broadcast_state(self, state_tensors=()):
+        """Make every rank start from rank 0's parameters, buffers and optimiser state (replicas then stay bit-identical
+        because they apply identical reduced gradients)."""
+        dist, world = _world()
+        if world <= 1:
+            return
+        for r in (self.rt, self.ert):
+            if r is not None:
+                dist.broadcast(r.arena, 0)
+                for b in r.int_buffers:
+                    dist.broadcast(b, 0)
+                r.dirty = True
+        for t in state_tensors:
+            dist.broadcast(t, 0)
 
     def zero_grad(self, set_to_none: bool = False):
         g = self.rt.ensure_grad_arena()
         g.zero_()
+        self._reduced_upto = None
+
+    def notify_grad_ready(self, lo: int):
+        """Backward has finished every gradient whose arena offset is >= ``lo`` (parameters are laid out in forward order,
+        so backward completes the arena from the top down): start reducing [lo, previous lo) on the side stream."""
+        dist, world = _world()
+        if world <= 1:
+            return
+        hi = self.rt.n_train if self._reduced_upto is None else self._reduced_upto
+        lo = max(0, min(int(lo), hi))
+        if lo >= hi:
+            return
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=self.dev)
+        cur = torch.cuda.current_stream(self.dev)
+        self._comm_stream.wait_stream(cur)
+        with torch.cuda.stream(self._comm_stream):
+            dist.all_reduce(self.rt.grad_arena[lo:hi])
+        self._reduced_upto = lo
 
     def _allreduce(self):
         dist, world = _world()
         if world > 1:
-            dist.all_reduce(self.rt.grad_arena)
+            if self._reduced_upto is None:                             # nothing in flight: one all-reduce of the whole arena
+                dist.all_reduce(self.rt.grad_arena)
+            else:
+                self.notify_grad_ready(0)                              # whatever has not been started yet
+                torch.cuda.current_stream(self.dev).wait_stream(self._comm_stream)
+                self._reduced_upto = None
         return world
 
     def _ema_extent(self):
@@ -68,19 +127,22 @@ class FusedSGD_EMA(_FusedBase):
         super().__init__(model, ema_model, ema_alpha, ema_mode)
         self.param_groups[0].update(lr=float(lr), momentum=float(momentum), weight_decay=float(weight_decay))
         self.buf = torch.zeros(self.rt.n_train, dtype=torch.float32, device=self.dev)   # buf=0 makes step 1 "buf = g"
-        self._hyper_host = None
         self.hyper = torch.zeros(8, dtype=torch.float32, device=self.dev)
+        self.broadcast_state((self.buf,))
+        self.refresh_hyper()
 
-    def _sync_hyper(self, world):
+    def refresh_hyper(self):
+        """Upload {lr, momentum, wd, alpha, 1/world, 1-alpha} when they changed (host side; never inside a capture)."""
         g = self.param_groups[0]
-        vals = [g["lr"], g["momentum"], g["weight_decay"], self.ema_alpha, 1.0 / world, 1.0 - self.ema_alpha, 0.0, 0.0]
+        vals = [g["lr"], g["momentum"], g["weight_decay"], self.ema_alpha, 1.0 / _world()[1], 1.0 - self.ema_alpha, 0.0, 0.0]
         if vals != self._hyper_host:
             self.hyper.copy_(torch.tensor(vals, dtype=torch.float32), non_blocking=False)
             self._hyper_host = vals
 
     def step(self):
-        world = self._allreduce()
-        self._sync_hyper(world)
+        self._allreduce()
+        if not _capturing():
+            self.refresh_hyper()
         rt = self.rt
         LIB.call("bcp_sgd_ema_step", ptr(rt.arena), ptr(rt.grad_arena), ptr(self.buf),
                  ptr(self.ert.arena) if self.ert is not None else None, ptr(self.hyper), rt.n_train, self._ema_extent(), stream())
@@ -93,6 +155,8 @@ class FusedSGD_EMA(_FusedBase):
         self.buf.copy_(sd["momentum_buffer"])
         self.param_groups[0].update(sd["param_groups"][0])
         self.step_count = sd.get("step", 0)
+        self.broadcast_state((self.buf,))
+        self.refresh_hyper()
 
 
 class FusedAdam_EMA(_FusedBase):
@@ -102,16 +166,28 @@ class FusedAdam_EMA(_FusedBase):
         self.m = torch.zeros(self.rt.n_train, dtype=torch.float32, device=self.dev)
         self.v = torch.zeros(self.rt.n_train, dtype=torch.float32, device=self.dev)
         self.hyper = torch.zeros(12, dtype=torch.float32, device=self.dev)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)   # advanced by bcp_adam_tick (graph-replayable)
+        self.broadcast_state((self.m, self.v, self.step_dev))
+        self.refresh_hyper()
+
+    def refresh_hyper(self):
+        """Upload {lr, b1, b2, eps, alpha, 1/world, -, -, 1-alpha} when they changed; slots 6, 7, 9 (bias corrections and
+        step size) belong to the device tick kernel and are preserved."""
+        g = self.param_groups[0]
+        b1, b2 = g["betas"]
+        vals = [g["lr"], b1, b2, g["eps"], self.ema_alpha, 1.0 / _world()[1], 1.0 - self.ema_alpha]
+        if vals != self._hyper_host:
+            h = torch.tensor(vals[:6], dtype=torch.float32)
+            self.hyper[:6].copy_(h, non_blocking=False)
+            self.hyper[8:9].copy_(torch.tensor(vals[6:], dtype=torch.float32), non_blocking=False)
+            self._hyper_host = vals
 
     def step(self):
-        world = self._allreduce()
-        g = self.param_groups[0]
-        t = self.step_count + 1
-        b1, b2 = g["betas"]
-        vals = [g["lr"], b1, b2, g["eps"], self.ema_alpha, 1.0 / world, 1.0 - b1 ** t, math.sqrt(1.0 - b2 ** t),
-                1.0 - self.ema_alpha, 0.0, 0.0, 0.0]
-        self.hyper.copy_(torch.tensor(vals, dtype=torch.float32))
+        self._allreduce()
+        if not _capturing():
+            self.refresh_hyper()
         rt = self.rt
+        LIB.call("bcp_adam_tick", ptr(self.hyper), ptr(self.step_dev), stream())
         LIB.call("bcp_adam_ema_step", ptr(rt.arena), ptr(rt.grad_arena), ptr(self.m), ptr(self.v),
                  ptr(self.ert.arena) if self.ert is not None else None, ptr(self.hyper), rt.n_train, self._ema_extent(), stream())
         self._after()
@@ -124,3 +200,6 @@ class FusedAdam_EMA(_FusedBase):
         self.v.copy_(sd["exp_avg_sq"])
         self.param_groups[0].update(sd["param_groups"][0])
         self.step_count = sd.get("step", 0)
+        self.step_dev.fill_(self.step_count)
+        self.broadcast_state((self.m, self.v, self.step_dev))
+        self.refresh_hyper()

@@ -37,12 +37,12 @@ class VNet(nn.Module):
         x1 = self.block_one(input)
         x2 = self.block_two(self.block_one_dw(x1))
         x3 = self.block_three(self.block_two_dw(x2))
-        x4 = self.block_four(self.block_three_dw(x3))
+        x4 = self.block_four(self.block_three_dw(self._rt.boundary(x3, "block_three_dw.conv.0.weight")))
         x4_dw = self.block_four_dw(x4)
         scale = None
         if use_dropout and self.dropout.training:
             scale = NetRuntime.channel_dropout_scale(self.dropout, x4_dw.shape[0], x4_dw.shape[1] * 8, x4_dw.device)
-        return [x1, x2, x3, x4, self.block_five(x4_dw, chan_scale=scale)]
+        return [x1, x2, x3, x4, self._rt.boundary(self.block_five(x4_dw, chan_scale=scale), "block_five_up.conv.0.weight")]
 
     def decoder(self, features):
         x1, x2, x3, x4, x5 = features
@@ -62,7 +62,7 @@ class VNet(nn.Module):
     def forward(self, input, turnoff_drop=False):
         rt = self._rt
         rt.prepare()
-        rt.spg = 1
+        rt.spg = input.shape[0]       # one reference forward call = one BatchNorm group (InstanceNorm uses spg 1 by itself)
         try:
             return self.decoder(self.encoder(input, self.has_dropout and not turnoff_drop))
         finally:

@@ -48,7 +48,7 @@ def la_self_train_step(model, ema_model, optimizer, volume, label, labeled_bs=4,
     un_a, un_b = un[:sub], un[sub:]
     with torch.no_grad():
         t_out, _ = ema_model(un, groups=2, with_features=False)            # ema_model(unimg_a), ema_model(unimg_b)
-        plab = ops.pseudo_label(t_out, "thresh", 0.5)                      # get_cut_mask
+        plab = plab_raw = ops.pseudo_label(t_out, "thresh", 0.5)           # get_cut_mask
         if nms:
             plab = ops.largest_cc(plab)                                    # LargestCC_pancreas, 26-connectivity
         plab_own = plab
@@ -67,8 +67,8 @@ def la_self_train_step(model, ema_model, optimizer, volume, label, labeled_bs=4,
     optimizer.zero_grad()
     loss.backward()
     optimizer.step()                                                        # SGD + EMA teacher update, fused
-    return dict(loss=loss.detach(), loss_l=loss_l.detach(), loss_u=loss_u.detach(), box=box, plab=plab_own, mixed=mixed,
-                out=out.detach())
+    return dict(loss=loss.detach(), loss_l=loss_l.detach(), loss_u=loss_u.detach(), box=box, plab=plab_own, plab_raw=plab_raw,
+                teacher_out=t_out, mixed=mixed, out=out.detach())
 
 
 def la_pre_train_step(model, optimizer, volume, label, labeled_bs=4, mask_ratio=2 / 3, box=None):
@@ -124,7 +124,7 @@ def acdc_self_train_step(model, ema_model, optimizer, volume, label, labeled_bs=
     lab_a, lab_b = label[:ls], label[ls:labeled_bs]
     with torch.no_grad():
         pre = ema_model(un, groups=2)
-        plab = ops.pseudo_label(pre, "argmax")
+        plab = plab_raw = ops.pseudo_label(pre, "argmax")
         if nms:
             plab = ops.largest_cc(plab)                                    # per-class 8-connected largest component
         plab_own = plab
@@ -145,7 +145,7 @@ def acdc_self_train_step(model, ema_model, optimizer, volume, label, labeled_bs=
     loss.backward()
     optimizer.step()                                                        # SGD + state_dict EMA, fused
     return dict(loss=loss.detach(), loss_dice=loss_dice.detach(), loss_ce=loss_ce.detach(), box=box, plab=plab_own,
-                mixed=mixed, out=out.detach())
+                plab_raw=plab_raw, teacher_out=pre, mixed=mixed, out=out.detach())
 
 
 def pan_pre_train_step(net, optimizer, img_a, lab_a, img_b, lab_b, patch_size=64, box=None):

@@ -32,8 +32,9 @@ def box_to_masks(box, batch_size, spatial, device):
         w, h, px, py = box
         mask[w:w + px, h:h + py] = 0
     loss_mask = mask.unsqueeze(0).repeat(batch_size, *([1] * len(spatial)))
-    mask.box = tuple(box)
-    loss_mask.box = tuple(box)
+    for m in (mask, loss_mask):
+        m.box = tuple(box)
+        m._bcp_box_version = m._version        # an in-place edit of the mask afterwards invalidates the attached box
     return mask, loss_mask
 
 
@@ -43,9 +44,13 @@ def context_mask(img, mask_ratio):
 
 
 def _box_of(mask):
+    """The box a mask tensor was built from, or None when there is none / the tensor was modified in place since
+    (then the callers fall back to reading the mask itself)."""
+    if isinstance(mask, (tuple, list)):
+        return tuple(mask)
     box = getattr(mask, "box", None)
-    if box is None and isinstance(mask, (tuple, list)):
-        box = tuple(mask)
+    if box is not None and getattr(mask, "_bcp_box_version", None) != mask._version:
+        return None
     return box
 
 
@@ -64,7 +69,7 @@ def mask_mix(a, b, mask):
     """a*M + b*(1-M) for a mask produced by context_mask (or a box tuple)."""
     box = _box_of(mask)
     if box is None:
-        raise ValueError("mask_mix needs a mask from context_mask()/generate_mask() (carrying .box) or a box tuple")
+        raise ValueError("mask_mix needs an unmodified mask from context_mask()/generate_mask() (carrying .box) or a box tuple")
     return ops.mask_mix(a, b, box)
 
 

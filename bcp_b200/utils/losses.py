@@ -23,7 +23,8 @@ class mask_DiceLoss(nn.Module):
         if logits.shape[1] < 2:
             raise NotImplementedError("single-channel (sigmoid) logits are never used by the entry points")
         t = ops.to_u8_labels(target.reshape((logits.shape[0],) + tuple(logits.shape[2:])))
-        box = getattr(mask, "box", None) if mask is not None else (0, 0, 0, 0, 0, 0)
+        from .BCP_utils import _box_of
+        box = _box_of(mask) if mask is not None else (0, 0, 0, 0, 0, 0)
         m8 = None
         if mask is not None and box is None:
             m8 = (mask.reshape(t.shape) != 0).to(torch.uint8)
@@ -31,24 +32,25 @@ class mask_DiceLoss(nn.Module):
 
 
 class DiceLoss(nn.Module):
-    """Batch-global per-class Dice (utils/losses.py:79-134).  Only the ``softmax=True`` (logits) entry is served by the
-    fused kernel; the ACDC step itself goes through ``bcp_b200.utils.acdc.mix_loss``."""
+    """Batch-global per-class Dice, smooth 1e-10 (utils/losses.py:79-134).  ``softmax=False`` (the call pattern of
+    ACDC_BCP_train.py:170,175: probabilities in, mask [N,1,H,W]) runs the dice-on-probabilities kernel pair;
+    ``softmax=True`` differentiates through the softmax inside the fused Dice/CE kernel."""
 
     def __init__(self, n_classes):
         super().__init__()
         self.n_classes = n_classes
 
     def forward(self, inputs, target, mask=None, weight=None, softmax=False):
-        if not softmax:
-            raise NotImplementedError("DiceLoss on probabilities: pass logits with softmax=True (the fused kernel "
-                                      "differentiates through the softmax), or use acdc.mix_loss")
         if weight is not None:
             raise NotImplementedError("per-class weights are never passed by the entry points")
         n = inputs.shape[0]
+        assert inputs.shape[1] == self.n_classes, "predict & target shape do not match"
         t = ops.to_u8_labels(target.reshape((n,) + tuple(inputs.shape[2:])))
         m8 = None if mask is None else (mask.reshape(t.shape) != 0).to(torch.uint8)
-        box = None if mask is not None else (0, 0, 0, 0)
-        return ops.MixLoss.apply(inputs, t, t, box, m8, 1, 1.0, 0.0)[1]
+        if softmax:
+            box = None if mask is not None else (0, 0, 0, 0)
+            return ops.MixLoss.apply(inputs, t, t, box, m8, 1, 1.0, 0.0)[1]
+        return ops.DiceProb.apply(inputs, t, m8)
 
 
 def to_one_hot(tensor, nClasses):

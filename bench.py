@@ -116,8 +116,7 @@ def run_native(args):
         try:
             from bcp_b200.graph import GraphedLAStep
             graphed = GraphedLAStep(model, ema, opt, (8, 1) + SHAPE)
-            graphed.vol.copy_(vol_d)
-            graphed.lab.copy_(lab_d)
+            graphed.load(vol_d, lab_d)
             graph_note = "whole step captured in one CUDA graph (%d kernels per replay)" % graphed.kernels_per_replay
         except Exception as exc:                 # capture problems must not hide a measurement: fall back to eager launches
             graphed, graph_note = None, "eager (graph capture failed: %s)" % (str(exc).splitlines()[0][:120])
@@ -223,7 +222,7 @@ def run_native(args):
 
 
 def conv_roofline(LIB, step_fn):
-    names = ("bcp_conv_tc_fwd", "bcp_conv_tc_wgrad")
+    names = ("bcp_conv_tc_fwd", "bcp_conv_tc_fold_fwd", "bcp_conv_tc_wgrad")
     recs = []
     orig = LIB.call
 
@@ -233,12 +232,13 @@ def conv_roofline(LIB, step_fn):
             e0.record()
             orig(name, *a)
             e1.record()
-            # args: (in, wpack, bias, out, n, cin, cout, dims, kernel, stream) for fwd
-            n, cin, cout, dims, kernel = a[4], a[5], a[6], a[7], a[8]
+            # args: (in, wpack, bias, out, n, cin, cout, dims, kernel, stream) for fwd; wgrad has (.., ws, counter, n, ...)
+            o = 5 if name == "bcp_conv_tc_wgrad" else 4
+            n, cin, cout, dims, kernel = a[o], a[o + 1], a[o + 2], a[o + 3], a[o + 4]
             vox = n * dims[0] * dims[1] * dims[2]
             taps = kernel[0] * kernel[1] * kernel[2]
             # algorithmic bytes: both activation tensors once (bf16) + the weights (bf16 pack or fp32 gradient)
-            ab = 2.0 * vox * (cin + cout) + taps * cin * cout * (2.0 if name == "bcp_conv_tc_fwd" else 4.0)
+            ab = 2.0 * vox * (cin + cout) + taps * cin * cout * (4.0 if name == "bcp_conv_tc_wgrad" else 2.0)
             recs.append((name, e0, e1, 2.0 * vox * taps * cin * cout, cin, cout, ab))
         else:
             orig(name, *a)
@@ -254,7 +254,7 @@ def conv_roofline(LIB, step_fn):
     tot_fl = sum(r[3] for r in recs)
     per = {}
     for name, e0, e1, f, cin, cout, _ in recs:
-        k = "%s_c%d_%d" % (name.replace("bcp_conv_", ""), cin, cout)
+        k = "%s_c%d_%d" % (name.replace("bcp_conv_", "").replace("tc_fold_fwd", "tc_fwd"), cin, cout)
         d = per.setdefault(k, [0.0, 0.0, 0])
         d[0] += e0.elapsed_time(e1)
         d[1] += f

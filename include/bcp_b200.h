@@ -85,6 +85,9 @@ int bcp_sgd_ema_step(float* params, const float* grads, float* momentum, float* 
                      long long n_train, long long n_total, cudaStream_t stream);
 int bcp_adam_ema_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* ema,
                       const float* hyper, long long n_train, long long n_total, cudaStream_t stream);
+/* advances the DEVICE step counter and writes the bias corrections {hyper[6], hyper[7]} and step_size hyper[9] = lr/bc1
+ * (double precision, like torch.optim.Adam's Python scalars); enqueue once before each bcp_adam_ema_step. */
+int bcp_adam_tick(float* hyper, long long* step, cudaStream_t stream);
 int bcp_ema_i64(long long* ema, const long long* model, int n, float alpha, float one_minus_alpha, cudaStream_t stream);
 
 /* ---- weight repack: fp32 master weights -> bf16 operand layouts (one launch per network).
@@ -208,6 +211,16 @@ int bcp_conv_tc_s2_wgrad_supported(int c_half, int c_full, const int* half_dims)
 long long bcp_conv_tc_s2_wgrad_workspace_floats(int n, int c_half, int c_full, const int* half_dims);
 int bcp_conv_tc_s2_wgrad(const void* full, const void* half, float* dw, float* workspace, int* counter, int n, int c_half,
                          int c_full, const int* half_dims, int accumulate, cudaStream_t stream);
+
+/* ---- DiceLoss on probabilities (utils/losses.py:113-134, called with softmax=False from ACDC_BCP_train.py:170,175):
+ * probs fp32 [n][c][v] (already soft-maxed by the caller), target uint8 [n][v], mask uint8 [n][v] or NULL.
+ * ctx[0] = loss (mean over classes of 1 - batch-global Dice, smooth 1e-10); bwd writes dL/dprobs * grad_out[0]. */
+long long bcp_dice_prob_ctx_floats(int c);
+long long bcp_dice_prob_workspace_floats(int n, int c, long long v);
+int bcp_dice_prob_fwd(const float* probs, const unsigned char* target, const unsigned char* mask, float* ctx, float* workspace,
+                      int n, int c, long long v, cudaStream_t stream);
+int bcp_dice_prob_bwd(const float* probs, const unsigned char* target, const unsigned char* mask, const float* ctx,
+                      const float* grad_out, float* dprobs, int n, int c, long long v, cudaStream_t stream);
 
 /* ---- resampling (networks/unet.py:37 MaxPool2d(2); :50 Upsample(bilinear, align_corners=True);
  * networks/VNet.py:249 MaxPool3d(3, stride=2)).  planes = n * ceil(c/8) * X. */

@@ -1,0 +1,150 @@
+"""Whole BCP self-training steps from the reference's SHIPPED checkpoints (models/LA/LA_10.pth, models/ACDC/ACDC_10.pth,
+rounded to bf16: tests/golden/weights_*_bf16.npz) at the BASELINE configs, against fixtures minted by running the
+unmodified reference modules on the same inputs (tests/golden/make_golden.py: gen_la_ckpt_step / gen_acdc_ckpt_step).
+
+Nothing is handed over from the golden side: the native teacher produces its own pseudo labels, largest-CC, mix, student
+pass, loss, SGD and EMA.  A trained teacher is decided almost everywhere, so its pseudo labels must be bit-identical on
+every voxel whose reference logit margin exceeds SURE_MARGIN (0.25); the rest (< 1 % of voxels, |margin| below the bf16
+noise of the logits) is reported as a flip fraction with a budget.
+
+Budgets (bf16 activations vs the fp32 reference; derivation in DESIGN.md section 4):
+  pseudo-label flips  <= 1e-3 of voxels (LA), <= 2e-3 (ACDC, argmax over 4 classes)
+  step loss           <= 1e-4 relative with the reference's pseudo labels handed to the student (isolates the student)
+                      <= 1e-3 relative fully end to end (a flipped pseudo label is a changed target, not rounding noise)
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests.golden.golden_common import inject_dropout, digest_named, tensor_digest, unpack_weights_bf16, synthetic_scene, unpackbits
+from tests.util import load_golden, T, rel_rms, record
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def _rel(a, b):
+    return abs(float(a) - float(b)) / abs(float(b))
+
+
+def _la_nets(dev):
+    from bcp_b200.networks.net_factory import net_factory
+    from bcp_b200.optim import FusedSGD_EMA
+    sd = unpack_weights_bf16(load_golden("weights_la10_bf16"))
+    model, ema = net_factory("VNet", 1, 2, "train"), net_factory("VNet", 1, 2, "train")
+    for p in ema.parameters():
+        p.detach_()
+    model.load_state_dict(sd)
+    ema.load_state_dict(sd)
+    model.train()
+    ema.train()
+    inject_dropout(model, seed=252)
+    inject_dropout(ema, seed=253)
+    opt = FusedSGD_EMA(model, ema, lr=0.01, momentum=0.9, weight_decay=1e-4, ema_alpha=0.99, ema_mode="params")
+    return model, ema, opt
+
+
+@pytest.mark.parametrize("handover", [False, True])
+def test_la_ckpt_step(dev, handover):
+    """handover=False: fully native, end to end.  handover=True: the student is given the reference's pseudo labels, so
+    its loss isolates the bf16 error of the student pass from the (few) teacher label flips."""
+    from bcp_b200.step import la_self_train_step
+    g = load_golden("la_ckpt_step")
+    shape = tuple(int(v) for v in g["shape"])
+    V = int(np.prod(shape))
+    model, ema, opt = _la_nets(dev)
+    np.random.seed(int(g["box_seed"]))
+    tag = "la_ckpt_handover" if handover else "la_ckpt"
+    for it in range(int(g["nsteps"])):
+        vol, lab = synthetic_scene(8, shape, 260 + 10 * it)
+        gp = T(unpackbits(g[f"s{it}_plab"], (4,) + shape)).to(dev)
+        graw = T(unpackbits(g[f"s{it}_plab_raw"], (4,) + shape)).to(dev)
+        sure = T(unpackbits(g[f"s{it}_sure"], (4,) + shape)).to(dev).bool()
+        r = la_self_train_step(model, ema, opt, vol.to(dev), lab.to(torch.uint8).to(dev), plab_override=gp if handover else None)
+        # teacher: logits, raw pseudo labels (bit-exact where the reference margin is not within bf16 noise), largest-CC
+        e_t = rel_rms(r["teacher_out"][..., ::4, ::4, ::4].cpu(), T(g[f"s{it}_teacher_logits"]))
+        record(f"{tag}_s{it}_teacher_logits_rel_rms", e_t)
+        assert e_t <= 3e-2
+        raw_mis = (r["plab_raw"] != graw)
+        record(f"{tag}_s{it}_plab_raw_flip_frac", float(raw_mis.float().mean()))
+        record(f"{tag}_s{it}_plab_raw_flips_on_sure_voxels", int((raw_mis & sure).sum()))
+        assert int((raw_mis & sure).sum()) == 0
+        flips = float((r["plab"] != gp).float().mean())
+        record(f"{tag}_s{it}_plab_flip_frac", flips)
+        assert flips <= 1e-3, flips
+        # mixed inputs: bit-exact
+        assert np.allclose(tensor_digest(r["mixed"][:2]), g[f"s{it}_mixl_digest"], rtol=1e-12, atol=0)
+        assert np.allclose(tensor_digest(r["mixed"][2:]), g[f"s{it}_mixu_digest"], rtol=1e-12, atol=0)
+        # student
+        e = rel_rms(r["out"][:2][..., ::4, ::4, ::4].cpu(), T(g[f"s{it}_out_l"]))
+        record(f"{tag}_s{it}_out_l_rel_rms", e)
+        assert e <= 3e-2
+        for k in ("loss", "loss_l", "loss_u"):
+            rel = _rel(r[k], g[f"s{it}_{k}"])
+            record(f"{tag}_s{it}_{k}_rel_err", rel)
+            assert rel <= (1e-4 if handover and it == 0 else 1e-3), (k, rel)
+        # post-step weights / EMA teacher (per-tensor |sum| digests; lr 0.01 steps on trained weights)
+        dm, ref = digest_named(model.state_dict()), g[f"s{it}_model_digest"]
+        big = ref[:, 1] > 1e-6
+        relw = np.abs(dm[big, 1] - ref[big, 1]) / ref[big, 1]
+        record(f"{tag}_s{it}_model_abs_sum_rel_max", float(relw.max()))
+        assert relw.max() <= 2e-3
+        de, refe = digest_named(ema.state_dict()), g[f"s{it}_ema_digest"]
+        bige = refe[:, 1] > 1e-6
+        assert (np.abs(de[bige, 1] - refe[bige, 1]) / refe[bige, 1]).max() <= 2e-3
+
+
+def test_acdc_ckpt_step(dev):
+    from bcp_b200.networks.net_factory import BCP_net
+    from bcp_b200.optim import FusedSGD_EMA
+    from bcp_b200.step import acdc_self_train_step
+    g = load_golden("acdc_ckpt_step")
+    H, W = (int(v) for v in g["shape"])
+    B, labeled_bs = int(g["B"]), int(g["labeled_bs"])
+    sd = unpack_weights_bf16(load_golden("weights_acdc10_bf16"))
+    model, ema = BCP_net(1, 4), BCP_net(1, 4, ema=True)
+    model.load_state_dict(sd)
+    ema.load_state_dict(sd)
+    model.train()
+    ema.train()
+    inject_dropout(model, seed=292)
+    inject_dropout(ema, seed=293)
+    opt = FusedSGD_EMA(model, ema, lr=0.01, momentum=0.9, weight_decay=1e-4, ema_alpha=0.99, ema_mode="state_dict")
+    np.random.seed(1337)
+    for it in range(int(g["nsteps"])):
+        vol, lab = synthetic_scene(B, (H, W), 300 + 10 * it, n_classes=4, kind="rand")
+        r = acdc_self_train_step(model, ema, opt, vol.to(dev), lab.to(torch.uint8).to(dev), labeled_bs=labeled_bs)
+        e_t = rel_rms(r["teacher_out"][..., ::4, ::4].cpu(), T(g[f"s{it}_teacher_logits"]))
+        record(f"acdc_ckpt_s{it}_teacher_logits_rel_rms", e_t)
+        assert e_t <= 3e-2
+        graw, gp = T(g[f"s{it}_plab_raw"]).to(dev), T(g[f"s{it}_plab"]).to(dev)
+        sure = T(unpackbits(g[f"s{it}_sure"], tuple(graw.shape))).to(dev).bool()
+        raw_mis = r["plab_raw"] != graw
+        record(f"acdc_ckpt_s{it}_plab_raw_flip_frac", float(raw_mis.float().mean()))
+        assert int((raw_mis & sure).sum()) == 0
+        flips = float((r["plab"] != gp).float().mean())
+        record(f"acdc_ckpt_s{it}_plab_flip_frac", flips)
+        assert flips <= 2e-3, flips
+        for k in ("loss", "loss_dice", "loss_ce"):
+            rel = _rel(r[k], g[f"s{it}_{k}"])
+            record(f"acdc_ckpt_s{it}_{k}_rel_err", rel)
+            assert rel <= 1e-3, (k, rel)
+        e = rel_rms(r["out"][6:][..., ::4, ::4].cpu(), T(g[f"s{it}_out_l"]))
+        record(f"acdc_ckpt_s{it}_out_l_rel_rms", e)
+        assert e <= 3e-2
+        # state_dict EMA (ACDC_BCP_train.py:123-129): parameters, BN running statistics (float buffers) and the int64
+        # counters blended through float and truncated -- all of them against the reference
+        de, refe = digest_named(ema.state_dict()), g[f"s{it}_ema_digest"]
+        keys = list(ema.state_dict().keys())
+        idx = [i for i, k in enumerate(keys) if k.endswith("num_batches_tracked")]
+        assert np.array_equal(de[idx, 0], refe[idx, 0])
+        fl = [i for i, k in enumerate(keys) if not k.endswith("num_batches_tracked") and refe[i, 1] > 1e-6]
+        relf = np.abs(de[fl, 1] - refe[fl, 1]) / refe[fl, 1]
+        record(f"acdc_ckpt_s{it}_ema_abs_sum_rel_max", float(relf.max()))
+        assert relf.max() <= 2e-3
+        bn = [i for i, k in enumerate(keys) if ("running_mean" in k or "running_var" in k) and refe[i, 1] > 1e-6]
+        assert len(bn) > 0 and (np.abs(de[bn, 1] - refe[bn, 1]) / refe[bn, 1]).max() <= 2e-3

@@ -320,3 +320,70 @@ def test_sliding_window_validation():
         sure = np.abs(score[0] - 0.5) > 1e-4
         assert np.array_equal(label[sure], g[tag + "_label"][sure].astype(np.int64))
         assert (~sure).mean() < 1e-3
+
+
+# ---- fixtures on the reference's shipped checkpoints (LA_10 / ACDC_10 rounded to bf16) ---------------------------------
+def test_ckpt_weight_fixture_roundtrip():
+    """weights_*_bf16.npz unpack to fp32 tensors that are exactly bf16-representable and load into the oracle nets."""
+    from tests.golden.golden_common import unpack_weights_bf16
+    sd = unpack_weights_bf16(load("weights_acdc10_bf16"))
+    net = O.BCP_net(1, 4)
+    net.load_state_dict(sd)
+    w = sd["encoder.in_conv.conv_conv.0.weight"]
+    assert torch.equal(w, w.to(torch.bfloat16).float())
+    sd = unpack_weights_bf16(load("weights_la10_bf16"))
+    O.net_factory("VNet", 1, 2, "train").load_state_dict(sd)
+    assert len(sd) == 259
+
+
+@pytest.mark.slow
+def test_la_ckpt_step():
+    """The oracle's restatement of LA_BCP_train.py:234-270 from the shipped LA_10 weights at BASELINE configs[1]."""
+    from tests.golden.golden_common import unpack_weights_bf16, synthetic_scene, unpackbits
+    g = load("la_ckpt_step")
+    shape = tuple(int(v) for v in g["shape"])
+    model, ema = O.net_factory("VNet", 1, 2, "train"), O.net_factory("VNet", 1, 2, "train")
+    for p in ema.parameters():
+        p.detach_()
+    sd = unpack_weights_bf16(load("weights_la10_bf16"))
+    model.load_state_dict(sd)
+    ema.load_state_dict(sd)
+    model.train()
+    ema.train()
+    inject_dropout(model, seed=252)
+    inject_dropout(ema, seed=253)
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=0.0001)
+    rs = np.random.RandomState(int(g["box_seed"]))
+    vol, lab = synthetic_scene(8, shape, 260)
+    r = O.la_self_train_step(model, ema, opt, vol, lab, rng=rs)
+    for k in ("loss", "loss_l", "loss_u"):
+        close(r[k], g[f"s0_{k}"], rtol=2e-5)
+    plab = torch.cat([r["plab_a"], r["plab_b"]]).numpy().astype(np.uint8)
+    assert np.array_equal(plab, unpackbits(g["s0_plab"], plab.shape))
+    close(tensor_digest(r["mixl"]), g["s0_mixl_digest"], rtol=1e-9, atol=0)
+    digests_close(digest_named(model.state_dict()), g["s0_model_digest"])
+    digests_close(digest_named(ema.state_dict()), g["s0_ema_digest"])
+
+
+def test_acdc_ckpt_step():
+    from tests.golden.golden_common import unpack_weights_bf16, synthetic_scene
+    g = load("acdc_ckpt_step")
+    H, W = (int(v) for v in g["shape"])
+    B, labeled_bs = int(g["B"]), int(g["labeled_bs"])
+    model, ema = O.BCP_net(1, 4), O.BCP_net(1, 4, ema=True)
+    sd = unpack_weights_bf16(load("weights_acdc10_bf16"))
+    model.load_state_dict(sd)
+    ema.load_state_dict(sd)
+    model.train()
+    ema.train()
+    inject_dropout(model, seed=292)
+    inject_dropout(ema, seed=293)
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=0.0001)
+    rs = np.random.RandomState(1337)
+    vol, lab = synthetic_scene(B, (H, W), 300, n_classes=4, kind="rand")
+    r = O.acdc_self_train_step(model, ema, opt, vol, lab.to(torch.uint8), labeled_bs=labeled_bs, rng=rs)
+    for k in ("loss", "loss_dice", "loss_ce"):
+        close(r[k], g[f"s0_{k}"], rtol=2e-5)
+    assert np.array_equal(torch.cat([r["plab_a"], r["plab_b"]]).numpy().astype(np.uint8), g["s0_plab"])
+    digests_close(digest_named(model.state_dict()), g["s0_model_digest"])
+    digests_close(digest_named(ema.state_dict()), g["s0_ema_digest"])
