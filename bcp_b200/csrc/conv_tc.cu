@@ -502,11 +502,13 @@ struct FoldParams {
   int mergedA;
 };
 
-constexpr int FOLD_EPI_WARPS = 8;                    // epilogue warps (multiple of 4: TMEM lane quarter = warp % 4); 2 tile subsets
-constexpr int FOLD_THREADS = 64 + 32 * FOLD_EPI_WARPS;
+// EW = epilogue warps (multiple of 4: TMEM lane quarter = warp % 4), EW / 4 tile subsets.  The epilogue (three TMEM loads,
+// 32 shuffles, bf16 pack, two 16-byte stores per 16 channels of a 96-row tile) is latency-bound per warp, so it takes
+// several warps per scheduler to keep up with the MMA stream (9 MMAs of N = 3*Ns per tile).
+constexpr int FOLD_EPI_WARPS_DEFAULT = 8;
 
-template <bool PROF>
-__global__ void __launch_bounds__(FOLD_THREADS, 1)
+template <bool PROF, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 conv_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_w,
                     const float* __restrict__ bias, uint4* __restrict__ out, const FoldParams p,
                     unsigned long long* __restrict__ prof) {
@@ -524,7 +526,7 @@ conv_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.SA; ++i) { mbar_init(full_a + 8 * i, 1); mbar_init(empty_a + 8 * i, 1); }
     for (int i = 0; i < p.SB; ++i) { mbar_init(full_b + 8 * i, 1); mbar_init(empty_b + 8 * i, 1); }
-    for (int i = 0; i < p.AS; ++i) { mbar_init(tmem_full + 8 * i, 1); mbar_init(tmem_empty + 8 * i, FOLD_EPI_WARPS); }
+    for (int i = 0; i < p.AS; ++i) { mbar_init(tmem_full + 8 * i, 1); mbar_init(tmem_empty + 8 * i, EW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
@@ -533,6 +535,8 @@ conv_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  __shared__ float bias_s[32];                       // Ns <= 32 (NS = 1): the layer's bias, read as shared-memory broadcasts
+  if (threadIdx.x < 32) bias_s[threadIdx.x] = (bias != nullptr && (int)threadIdx.x < p.Ns) ? __ldg(bias + threadIdx.x) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -614,9 +618,10 @@ conv_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     }
     __syncwarp();
   } else {
-    // FOLD_EPI_WARPS epilogue warps: warp w reads TMEM lane quarter w % 4 and takes the tiles mt = sub, sub + nsub, ...
+    // EW epilogue warps: warp w reads TMEM lane quarter w % 4 and takes the tiles mt = sub, sub + nsub, ...
     // The frame row of a lane advances by 96*nsub per step; (ix,iy,iz) follow incrementally (no per-row divisions).
-    const int q = warp & 3, sub = (warp - 2) >> 2, nsub = FOLD_EPI_WARPS / 4;
+    const int q = warp & 3, sub = (warp - 2) >> 2, nsub = EW / 4;
+
     Ring rt;
     const long long S = (long long)p.X * p.Y * p.Z;
     const int grp = q * 4 + (lane >> 3), k8 = lane & 7;                               // tile row i = 32q + lane = 8*grp + k8
@@ -635,34 +640,56 @@ conv_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
       const uint32_t d0 = tmem_base + rt.s * (uint32_t)(p.MT * N3) + ((uint32_t)(q * 32) << 16);
       const int L0 = sub * 96 + grp * 6 + k8;                                          // frame row of this lane in its first tile
       int iz = L0 % p.HZ, iy = (L0 / p.HZ) % p.HY, ix = (L0 / p.HZ) / p.HY;
-      for (int mt = sub; mt < p.MT; mt += nsub) {
+      // Software-pipelined drain: a unit = (tile, 16-channel chunk) = three tcgen05.ld.x16.  The loads of unit u+1 are in
+      // flight while unit u is combined (two intra-group shuffles per channel), packed and stored: two register sets, loop
+      // unrolled by two.  Without this the TMEM load latency was exposed once per tile and the epilogue, not the tensor
+      // pipe, set the pace (tools/debug_conv_tc.py --prof-fold: 222 k of 263 k cycles on the 112x112x80 layer).
+      const int nch = p.Ns >> 4;                                                       // 16-channel chunks per tile (1 or 2)
+      const int ntile = (p.MT > sub) ? (p.MT - sub + nsub - 1) / nsub : 0;
+      const int nunit = ntile * nch;
+      uint32_t A0[16], A1[16], A2[16], B0[16], B1[16], B2[16];
+      auto issue = [&](int u, uint32_t (&r0)[16], uint32_t (&r1)[16], uint32_t (&r2)[16]) {
+        const int t = u / nch, c16 = (u - t * nch) << 4;
+        const uint32_t addr = d0 + (uint32_t)((sub + t * nsub) * N3 + c16);
+        tmem_ld16(addr, r0);
+        tmem_ld16(addr + (uint32_t)p.Ns, r1);
+        tmem_ld16(addr + (uint32_t)(2 * p.Ns), r2);
+      };
+      auto consume = [&](int u, const uint32_t (&r0)[16], const uint32_t (&r1)[16], const uint32_t (&r2)[16]) {
+        const int t = u / nch, ch = u - t * nch;
+        float f[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float a1 = __shfl_down_sync(0xffffffffu, __uint_as_float(r1[k]), 1, 8);   // D'[r+1][dz=1]
+          const float a2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[k]), 2, 8);   // D'[r+2][dz=2]
+          f[k] = (__uint_as_float(r0[k]) + a1) + a2 + bias_s[ch * 16 + k];
+        }
         const int x = bx * p.BX + ix, y = by * p.BY + iy, z = bz * p.BZ + iz;
         const bool valid = (k8 < 6) && (ix < p.BX) && (iy < p.BY) && (iz < p.BZ) && (x < p.X) && (y < p.Y) && (z < p.Z);
-        const long long sp = ((long long)x * p.Y + y) * p.Z + z;
-        for (int c16 = 0; c16 < p.Ns; c16 += 16) {
-          uint32_t v0[16], v1[16], v2[16];
-          tmem_ld16(d0 + (uint32_t)(mt * N3 + c16), v0);
-          tmem_ld16(d0 + (uint32_t)(mt * N3 + p.Ns + c16), v1);
-          tmem_ld16(d0 + (uint32_t)(mt * N3 + 2 * p.Ns + c16), v2);
-          tmem_ld_wait();
-          float f[16];
-#pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const float a1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[k]), 1, 8);   // D'[r+1][dz=1]
-            const float a2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[k]), 2, 8);   // D'[r+2][dz=2]
-            f[k] = (__uint_as_float(v0[k]) + a1) + a2 + (bias ? __ldg(bias + n0 + c16 + k) : 0.f);
-          }
-          if (valid) {
-            uint4* dst = out + ((long long)n * Cob + ((n0 + c16) >> 3)) * S + sp;
-            dst[0] = pack8(f);
-            dst[S] = pack8(f + 8);
-          }
+        if (valid) {
+          const long long sp = ((long long)x * p.Y + y) * p.Z + z;
+          uint4* dst = out + ((long long)n * Cob + ((n0 >> 3) + 2 * ch)) * S + sp;
+          dst[0] = pack8(f);
+          dst[S] = pack8(f + 8);
         }
-        iz += sz;
-        if (iz >= p.HZ) { iz -= p.HZ; ++iy; }
-        iy += sy;
-        if (iy >= p.HY) { iy -= p.HY; ++ix; }
-        ix += sx;
+        if (ch == nch - 1) {                         // last chunk of the tile: advance this lane's frame row by 96 * nsub
+          iz += sz;
+          if (iz >= p.HZ) { iz -= p.HZ; ++iy; }
+          iy += sy;
+          if (iy >= p.HY) { iy -= p.HY; ++ix; }
+          ix += sx;
+        }
+      };
+      if (nunit > 0) issue(0, A0, A1, A2);
+      for (int u = 0; u < nunit; u += 2) {
+        tmem_ld_wait();
+        if (u + 1 < nunit) issue(u + 1, B0, B1, B2);
+        consume(u, A0, A1, A2);
+        if (u + 1 < nunit) {
+          tmem_ld_wait();
+          if (u + 2 < nunit) issue(u + 2, A0, A1, A2);
+          consume(u + 1, B0, B1, B2);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -1087,7 +1114,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
   // ---- in-kernel finalize (replaces a separate finalize launch and its ~25 us of launch gap + cold reads): the grid is
-  // launched cooperatively (<= one CTA per SM, all co-resident), every CTA arrives at a device-wide barrier, then ALL
+  // at most one CTA per SM, all co-resident, every CTA arrives at a device-wide barrier, then ALL
   // CTAs sum the partials -- dw[co][ci][t] = sum_split partial[split][t][co][ci] -- each output quad by a fixed set of KS
   // lanes in a fixed order (deterministic, no float atomics).  counter[0] = arrivals, counter[1] = departures; the last
   // CTA to leave resets both, so the pair is reusable by the next launch on the stream.
@@ -1106,34 +1133,56 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const long long items = per >> 2;                                 // float4 outputs (Cin % 16 == 0)
     const float4* part4 = reinterpret_cast<const float4*>(partial);
     const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x;
-    const unsigned KS = (unsigned)p.KS, opw = 32u / KS;               // outputs per warp pass
+    const unsigned KS = (unsigned)p.KS, opw = 32u / KS;               // output quads per warp per sub-pass
     const unsigned ks = lane & (KS - 1), ol = lane / KS;
-    const long long wstride = (long long)nct * (TC_THREADS / 32) * opw;
-    for (long long base = ((long long)cta * (TC_THREADS / 32) + warp) * opw; base < items; base += wstride) {
-      const long long o = base + ol;
-      const bool valid = o < items;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (valid) {
-#pragma unroll 4
-        for (int k = (int)ks; k < p.splits; k += (int)KS) {
-          const float4 v = __ldcg(part4 + (long long)k * items + o);
-          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    constexpr int NO = 4;                                             // independent output quads per thread per pass (ILP:
+                                                                      // the grid has only ~28k threads for up to 9M loads)
+    const long long wstride = (long long)nct * (TC_THREADS / 32) * opw * NO;
+    for (long long base = ((long long)cta * (TC_THREADS / 32) + warp) * opw * NO; base < items; base += wstride) {
+      float4 acc[NO];
+      long long o[NO];
+#pragma unroll
+      for (int j = 0; j < NO; ++j) { acc[j] = make_float4(0.f, 0.f, 0.f, 0.f); o[j] = base + (long long)j * opw + ol; }
+#pragma unroll 2
+      for (int k = (int)ks; k < p.splits; k += (int)KS) {
+        const float4* src = part4 + (long long)k * items;
+#pragma unroll
+        for (int j = 0; j < NO; ++j) {
+          if (o[j] < items) {
+            const float4 v = __ldcg(src + o[j]);
+            acc[j].x += v.x; acc[j].y += v.y; acc[j].z += v.z; acc[j].w += v.w;
+          }
         }
       }
       for (unsigned m = 1; m < KS; m <<= 1) {
-        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, m);
-        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, m);
-        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, m);
-        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, m);
+#pragma unroll
+        for (int j = 0; j < NO; ++j) {
+          acc[j].x += __shfl_xor_sync(0xffffffffu, acc[j].x, m);
+          acc[j].y += __shfl_xor_sync(0xffffffffu, acc[j].y, m);
+          acc[j].z += __shfl_xor_sync(0xffffffffu, acc[j].z, m);
+          acc[j].w += __shfl_xor_sync(0xffffffffu, acc[j].w, m);
+        }
       }
-      if (valid && ks == 0) {
-        const long long i = o << 2;
-        const int ci = (int)(i % p.Cin);
-        const int co = (int)((i / p.Cin) % p.Cout);
-        const int t = (int)(i / ((long long)p.Cin * p.Cout));
-        float* dst = dw + ((long long)co * p.Cin + ci) * p.T + t;
-        if (p.accumulate) { dst[0] += acc.x; dst[p.T] += acc.y; dst[2 * p.T] += acc.z; dst[3 * p.T] += acc.w; }
-        else { dst[0] = acc.x; dst[p.T] = acc.y; dst[2 * p.T] = acc.z; dst[3 * p.T] = acc.w; }
+      if (ks == 0) {
+        float* dst[NO];
+        float old[NO][4];
+#pragma unroll
+        for (int j = 0; j < NO; ++j) {
+          const long long i = o[j] << 2;
+          const int ci = (int)(i % p.Cin);
+          const int co = (int)((i / p.Cin) % p.Cout);
+          const int t = (int)(i / ((long long)p.Cin * p.Cout));
+          dst[j] = dw + ((long long)co * p.Cin + ci) * p.T + t;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) old[j][q] = (p.accumulate && o[j] < items) ? dst[j][q * p.T] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < NO; ++j) {
+          if (o[j] < items) {
+            dst[j][0] = old[j][0] + acc[j].x; dst[j][p.T] = old[j][1] + acc[j].y;
+            dst[j][2 * p.T] = old[j][2] + acc[j].z; dst[j][3 * p.T] = old[j][3] + acc[j].w;
+          }
+        }
       }
     }
   }
@@ -1675,7 +1724,7 @@ int bcp_conv_tc_fold_plan(int n, int cin, int cout, const int* dims, const int* 
 }
 
 static int conv_tc_fold_launch(const void* in, const void* wpack, const float* bias, void* out, int n, int cin, int cout,
-                               const int* dims, const int* kernel, unsigned long long* prof, cudaStream_t stream) {
+                               const int* dims, const int* kernel, unsigned long long* prof, int ew, cudaStream_t stream) {
   BCP_REQUIRE(in && wpack && out && dims && kernel, "conv_tc_fold_fwd: null pointer");
   if (!fold_shape_ok(cin, cout, dims, kernel)) { set_last_error("conv_tc_fold_fwd: unsupported shape"); return BCP_ERR_UNSUPPORTED; }
   EncodeTiledFn enc = get_encode();
@@ -1704,36 +1753,40 @@ static int conv_tc_fold_launch(const void* in, const void* wpack, const float* b
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(conv_tc_fold_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(conv_tc_fold_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    attr_err = cudaFuncSetAttribute(conv_tc_fold_kernel<false, FOLD_EPI_WARPS_DEFAULT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(conv_tc_fold_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(conv_tc_fold_kernel<true, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(conv_tc_fold_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (attr_err != cudaSuccess) cudaGetLastError();
   });
   if (attr_err != cudaSuccess) { set_last_error("conv_tc_fold_fwd: cudaFuncSetAttribute failed"); return BCP_ERR_CUDA; }
   BCP_REQUIRE(smem <= 226 * 1024, "conv_tc_fold_fwd: shared memory plan overflow");
   const int grid = p.nbricks < nsm ? p.nbricks : nsm;
-  if (prof) conv_tc_fold_kernel<true><<<grid, FOLD_THREADS, smem, stream>>>(tmap, tmap_w, bias, (uint4*)out, p, prof);
-  else conv_tc_fold_kernel<false><<<grid, FOLD_THREADS, smem, stream>>>(tmap, tmap_w, bias, (uint4*)out, p, nullptr);
+  if (prof && ew == 8) conv_tc_fold_kernel<true, 8><<<grid, 64 + 32 * 8, smem, stream>>>(tmap, tmap_w, bias, (uint4*)out, p, prof);
+  else if (prof && ew == 12) conv_tc_fold_kernel<true, 12><<<grid, 64 + 32 * 12, smem, stream>>>(tmap, tmap_w, bias, (uint4*)out, p, prof);
+  else if (prof) conv_tc_fold_kernel<true, 16><<<grid, 64 + 32 * 16, smem, stream>>>(tmap, tmap_w, bias, (uint4*)out, p, prof);
+  else conv_tc_fold_kernel<false, FOLD_EPI_WARPS_DEFAULT><<<grid, 64 + 32 * FOLD_EPI_WARPS_DEFAULT, smem, stream>>>(tmap, tmap_w, bias, (uint4*)out, p, nullptr);
   return check_launch("conv_tc_fold_fwd");
 }
 
 int bcp_conv_tc_fold_fwd(const void* in, const void* wpack, const float* bias, void* out, int n, int cin, int cout,
                          const int* dims, const int* kernel, cudaStream_t stream) {
-  return conv_tc_fold_launch(in, wpack, bias, out, n, cin, cout, dims, kernel, nullptr, stream);
+  return conv_tc_fold_launch(in, wpack, bias, out, n, cin, cout, dims, kernel, nullptr, FOLD_EPI_WARPS_DEFAULT, stream);
 }
 
 // Instrumented variants for tools/debug_conv_tc.py: `prof` = device buffer of 16 x uint64 per CTA (>= #SMs CTAs) that
-// receives per-role wait cycles.  fold = 1 selects the dz-folded kernel.  The caller passes the buffer explicitly: the
+// receives per-role wait cycles.  fold = 0: unfolded kernel; fold = 8 / 12 / 16: the dz-folded kernel with that many epilogue warps.  The caller passes the buffer explicitly: the
 // library keeps no profiling state.
 int bcp_conv_tc_fwd_profiled(const void* in, const void* wpack, const float* bias, void* out, int n, int cin, int cout,
                              const int* dims, const int* kernel, int fold, void* prof, cudaStream_t stream) {
   BCP_REQUIRE(prof, "conv_tc_fwd_profiled: null profile buffer");
-  if (fold) return conv_tc_fold_launch(in, wpack, bias, out, n, cin, cout, dims, kernel, (unsigned long long*)prof, stream);
+  if (fold) return conv_tc_fold_launch(in, wpack, bias, out, n, cin, cout, dims, kernel, (unsigned long long*)prof, fold, stream);
   return conv_tc_launch(in, wpack, bias, out, n, cin, cout, dims, kernel, nullptr, (unsigned long long*)prof, stream);
 }
 
 
-// Cooperative launch of the weight-gradient kernel (its in-kernel finalize needs every CTA of the grid co-resident: the grid
-// is splits x passes <= #SMs with one CTA per SM, and the cooperative attribute makes the driver guarantee it).
+// Launch of the weight-gradient kernel (its in-kernel finalize needs every CTA of the grid co-resident: the grid is
+// splits x passes <= #SMs with one CTA per SM).
 static int wg_launch(const CUtensorMap& map_a, const CUtensorMap& map_dy, float* workspace, float* dw, int* counter, WgParams& p,
                      cudaStream_t stream, const char* what) {
   const size_t smem = (size_t)p.offBar + 8 * (2 * p.S + 1) + 16 + 128 + 128;
@@ -1751,18 +1804,13 @@ static int wg_launch(const CUtensorMap& map_a, const CUtensorMap& map_dy, float*
   int ks = 1;
   while (ks < 32 && ks * 2 <= p.splits && items * ks * 2 <= threads) ks *= 2;
   p.KS = ks;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(p.splits, p.npass_t * p.MH);
-  cfg.blockDim = dim3(TC_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeCooperative;
-  at[0].val.cooperative = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_wgrad_kernel, map_a, map_dy, workspace, dw, counter, (const WgParams)p);
-  if (e != cudaSuccess) { cudaGetLastError(); set_last_error("%s: launch failed: %s", what, cudaGetErrorString(e)); return BCP_ERR_CUDA; }
+  // Plain launch: the device-wide barrier inside the kernel needs every CTA co-resident, which holds because the grid is at most
+  // one CTA per SM (220 KB of shared memory each) and a stream-ordered launch starts on an idle device.  (A cooperative
+  // launch would make the driver guarantee it, but measured ~10 us of extra launch latency per call inside a CUDA graph:
+  // 28 calls per step.)  Concurrent kernels of other streams only delay the barrier, they cannot deadlock it, as long as
+  // they terminate on their own.
+  dim3 grid(p.splits, p.npass_t * p.MH);
+  conv_tc_wgrad_kernel<<<grid, TC_THREADS, smem, stream>>>(map_a, map_dy, workspace, dw, counter, p);
   return check_launch(what);
 }
 

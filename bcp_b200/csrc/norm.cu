@@ -52,7 +52,7 @@ __device__ __forceinline__ void fin_reduce_tile(const float* __restrict__ partia
 
 // Per-channel finalize, executed by ONE block (the last one to finish its partial).
 // stat[g][C][2] = {mean, invstd}; coef[g][C][2] = {scale, shift}.
-__device__ void bn_finalize_block(const float* __restrict__ partial, const float* __restrict__ gamma,
+__device__ __noinline__ void bn_finalize_block(const float* __restrict__ partial, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, float* __restrict__ running_mean,
                                   float* __restrict__ running_var, long long* __restrict__ nbt,
                                   float* __restrict__ stat, float* __restrict__ coef,
@@ -98,7 +98,8 @@ __device__ void bn_finalize_block(const float* __restrict__ partial, const float
 }
 
 // partial[((n*Cb + cb)*chunks + chunk)*16 + {0..7: sum, 8..15: sumsq}]; the last block finalises
-__global__ void __launch_bounds__(NT) bn_stats_kernel(const uint4* __restrict__ y, float* __restrict__ partial,
+// (minimum 6 resident blocks per SM: the streaming loop sets the register budget, the rarely-run finalize may spill)
+__global__ void __launch_bounds__(NT, 6) bn_stats_kernel(const uint4* __restrict__ y, float* __restrict__ partial,
                                                        long long S, int chunks, int* __restrict__ counter,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        float* __restrict__ running_mean, float* __restrict__ running_var,
@@ -259,12 +260,12 @@ __global__ void __launch_bounds__(NT) bn_apply_kernel(const uint4* __restrict__ 
   }
 }
 
-__device__ void bn_bwd_finalize_block(const float* __restrict__ partial, float* __restrict__ sums, float* __restrict__ dgamma,
+__device__ __noinline__ void bn_bwd_finalize_block(const float* __restrict__ partial, float* __restrict__ sums, float* __restrict__ dgamma,
                                       float* __restrict__ dbeta, int N, int C, long long S, int chunks, int spg, int accumulate);
 
 // backward pass 1: per (n, cb, chunk) partials of  s1 = sum g,  s2 = sum g*xhat   with
 // g = da * dropout * act'(pre)
-__global__ void __launch_bounds__(NT) bn_bwd_reduce_kernel(const uint4* __restrict__ da, const uint4* __restrict__ y,
+__global__ void __launch_bounds__(NT, 4) bn_bwd_reduce_kernel(const uint4* __restrict__ da, const uint4* __restrict__ y,
                                                             const float* __restrict__ stat, const float* __restrict__ coef,
                                                             const float* __restrict__ chan_scale,
                                                             const unsigned char* __restrict__ elem_keep, float elem_scale,
@@ -334,7 +335,7 @@ __global__ void __launch_bounds__(NT) bn_bwd_reduce_kernel(const uint4* __restri
 }
 
 // sums[g][C][2] = {s1/M, s2/M};  dgamma[c] = sum_g s2, dbeta[c] = sum_g s1   (run by the last block of the reduce pass)
-__device__ void bn_bwd_finalize_block(const float* __restrict__ partial, float* __restrict__ sums,
+__device__ __noinline__ void bn_bwd_finalize_block(const float* __restrict__ partial, float* __restrict__ sums,
                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
                                       int N, int C, long long S, int chunks, int spg, int accumulate) {
   const int Cb = (C + 7) / 8, G = N / spg;

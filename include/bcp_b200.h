@@ -187,12 +187,12 @@ int bcp_conv_tc_fold_plan(int n, int cin, int cout, const int* dims, const int* 
 int bcp_conv_tc_fold_fwd(const void* in, const void* wpack, const float* bias, void* out, int n, int cin, int cout,
                          const int* dims, const int* kernel, cudaStream_t stream);
 /* debug only (tools/debug_conv_tc.py): the instrumented template instance of bcp_conv_tc_fwd (fold = 0) or
- * bcp_conv_tc_fold_fwd (fold = 1); `prof` (device, 16 x uint64 per CTA, >= #SMs CTAs) receives per-role wait cycles. */
+ * bcp_conv_tc_fold_fwd (fold = 8, 12 or 16 = number of epilogue warps); `prof` (device, 16 x uint64 per CTA, >= #SMs CTAs) receives per-role wait cycles. */
 int bcp_conv_tc_fwd_profiled(const void* in, const void* wpack, const float* bias, void* out, int n, int cin, int cout,
                              const int* dims, const int* kernel, int fold, void* prof, cudaStream_t stream);
 
-/* tcgen05 weight gradient for the same family: dw[cout][cin][taps] fp32 (PyTorch layout), deterministic.  ONE cooperative
- * launch: every CTA accumulates its share of the voxels in TMEM, writes a partial to `workspace`, meets the others at a
+/* tcgen05 weight gradient for the same family: dw[cout][cin][taps] fp32 (PyTorch layout), deterministic.  ONE launch
+ * (grid <= #SMs, one CTA per SM, so all CTAs are co-resident): every CTA accumulates its share of the voxels in TMEM, writes a partial to `workspace`, meets the others at a
  * device-wide barrier and then all CTAs reduce the partials in fixed order into dw.  `counter`: TWO device ints, zero
  * before the first call (the kernel resets them), private to the stream. */
 int bcp_conv_tc_wgrad_supported(int cin, int cout, const int* dims, const int* kernel);

@@ -255,7 +255,7 @@ def context_mask_la(img, mask_ratio, rng=np.random):
     w = rng.randint(0, 112 - px)
     h = rng.randint(0, 112 - py)
     z = rng.randint(0, 80 - pz)
-    mask = torch.ones(X, Y, Z)
+    mask = torch.ones(X, Y, Z, device=img.device)          # the reference does .cuda() here
     mask[w:w + px, h:h + py, z:z + pz] = 0
     return mask.long(), mask.long().unsqueeze(0).repeat(b, 1, 1, 1), (w, h, z, px, py, pz)
 
@@ -266,7 +266,7 @@ def generate_mask_acdc(img, rng=np.random):
     px, py = int(X * 2 / 3), int(Y * 2 / 3)
     w = rng.randint(0, X - px)
     h = rng.randint(0, Y - py)
-    mask = torch.ones(X, Y)
+    mask = torch.ones(X, Y, device=img.device)
     mask[w:w + px, h:h + py] = 0
     return mask.long(), mask.long().unsqueeze(0).repeat(b, 1, 1), (w, h, px, py)
 
@@ -277,7 +277,7 @@ def generate_mask_pan(img, patch_size, rng=np.random):
     w = rng.randint(0, 96 - patch_size)
     h = rng.randint(0, 96 - patch_size)
     z = rng.randint(0, 96 - patch_size)
-    mask = torch.ones(96, 96, 96)
+    mask = torch.ones(96, 96, 96, device=img.device)
     mask[w:w + patch_size, h:h + patch_size, z:z + patch_size] = 0
     return mask.long(), mask.long().unsqueeze(0).repeat(b, 1, 1, 1), (w, h, z, patch_size, patch_size, patch_size)
 
@@ -308,7 +308,7 @@ def largest_cc(seg: torch.Tensor, connectivity: int | None = None) -> torch.Tens
             out.append((lab == np.argmax(np.bincount(lab.flat)[1:]) + 1))
         else:
             out.append(v)
-    return torch.from_numpy(np.stack(out).astype(np.float32))
+    return torch.from_numpy(np.stack(out).astype(np.float32)).to(seg.device)     # torch.Tensor(list).cuda() in the reference
 
 
 def get_cut_mask(out, thres=0.5, nms=0, connectivity=None):
@@ -334,7 +334,7 @@ def acdc_2d_largest_cc(seg: torch.Tensor) -> torch.Tensor:
                 keep = v
             acc = keep if acc is None else acc + keep
         out.append(acc)
-    return torch.from_numpy(np.stack(out).astype(np.float32))
+    return torch.from_numpy(np.stack(out).astype(np.float32)).to(seg.device)
 
 
 def get_acdc_masks(output, nms=0):

@@ -18,15 +18,35 @@ import torch.nn.functional as F
 
 from oracle import bcp_oracle as O
 from tests.test_gpu_primitives import _packs
-from tests.util import cb8_from_planar, planar_from_cb8, rel_rms, record
+from tests.util import cb8_from_planar, planar_from_cb8, rel_rms, record, wgrad_fp64
 
 pytestmark = pytest.mark.gpu
 
 FWD_TOL, DGRAD_TOL = 6e-3, 1e-2
 
 
+BIG = 1 << 18      # voxels per weight-gradient sum above which the reference is float64 (see check_wgrad)
+
+
 def wgrad_tol(nvox):
     return 1e-4 if nvox <= (1 << 21) else 3e-4
+
+
+def check_wgrad(tag, got, torch_fp32, a, dy, kernel, nvox):
+    """Weight-gradient criterion.  Up to 2^18 voxels per sum: <= 1e-4 against fp32 torch.  Beyond that fp32 torch (cuDNN)
+    itself is > 1e-4 away from the exact result (summation order over millions of products), so the reference becomes
+    float64 and the requirement is: within 1e-4 of fp64, or at least no further from fp64 than 1.5x stock fp32 torch."""
+    if nvox <= BIG or a is None:
+        e = rel_rms(got, torch_fp32)
+        record(tag, e)
+        assert e <= wgrad_tol(nvox), (tag, e)
+        return e
+    ref = wgrad_fp64(a, dy, kernel, tuple(k // 2 for k in kernel))
+    e, e_t = rel_rms(got, ref), rel_rms(torch_fp32, ref)
+    record(tag + "_vs_fp64", e)
+    record(tag + "_torch_fp32_vs_fp64", e_t)
+    assert e <= max(1e-4, 1.5 * e_t), (tag, e, e_t)
+    return e
 
 
 @pytest.fixture(scope="module")
@@ -85,7 +105,7 @@ def test_conv_same_production_shape(ops, dev, n, cin, cout, dims, kernel):
     tag = "conv_c%d_%d_%s_k%d" % (cin, cout, "x".join(map(str, dims)), kernel[0] * kernel[1])
     _check(tag + "_fwd", planar_from_cb8(y.detach(), cout), yr.detach(), FWD_TOL)
     _check(tag + "_dgrad", planar_from_cb8(xcb.grad, cin), xr.grad, DGRAD_TOL)
-    _check(tag + "_wgrad", w.grad, wr.grad, wgrad_tol(n * int(np.prod(dims))))
+    check_wgrad(tag + "_wgrad", w.grad, wr.grad, x, g, kernel, n * int(np.prod(dims)))
     _check(tag + "_bgrad", b.grad, br.grad, 1e-3)
 
 
@@ -138,7 +158,7 @@ def test_first_layer_and_head_production_shape(ops, dev):
     yr.backward(g)
     y.backward(cb8_from_planar(g))
     _check("first_fwd", planar_from_cb8(y.detach(), 16), yr.detach(), FWD_TOL)
-    _check("first_wgrad", w.grad, wr.grad, 3e-4)
+    check_wgrad("first_wgrad", w.grad, wr.grad, x, g, (3, 3, 3), n * int(np.prod(dims)))
     a = torch.randn(n, 16, *dims, device=dev).to(torch.bfloat16).float()
     w = (torch.randn(2, 16, 1, 1, 1, device=dev) / 4).requires_grad_(True)
     b = (0.1 * torch.randn(2, device=dev)).requires_grad_(True)
@@ -151,7 +171,7 @@ def test_first_layer_and_head_production_shape(ops, dev):
     lo.backward(g)
     _check("head_fwd", lo.detach(), lr.detach(), 1e-5)
     _check("head_dgrad", planar_from_cb8(acb.grad, 16), ar.grad, DGRAD_TOL)
-    _check("head_wgrad", w.grad, wr.grad, 3e-4)
+    check_wgrad("head_wgrad", w.grad, wr.grad, a, g, (1, 1, 1), n * int(np.prod(dims)))
     _check("head_bgrad", b.grad, br.grad, 3e-4)
 
 
@@ -244,10 +264,10 @@ def test_vnet_layers_on_oracle_activations(ops, dev):
         head = m.kernel_size == (1, 1, 1)
         y.backward(gb if head else cb8_from_planar(gb))
         e_f = rel_rms(y.detach() if head else planar_from_cb8(y.detach(), cout), yr.detach())
-        e_w = rel_rms(w.grad, wr.grad)
+        stride1 = isinstance(m, nn.Conv3d) and m.stride == (1, 1, 1)
+        e_w = check_wgrad("layerwise_" + name + "_wgrad", w.grad, wr.grad, ab if stride1 else None, gb, m.kernel_size, nvox)
         worst["fwd"], worst["wgrad"] = max(worst["fwd"], e_f), max(worst["wgrad"], e_w)
         assert e_f <= (1e-5 if head else FWD_TOL), (name, "fwd", e_f)
-        assert e_w <= wgrad_tol(nvox), (name, "wgrad", e_w)
         if acb is not None:
             e_d = rel_rms(planar_from_cb8(acb.grad, cin), ar.grad)
             worst["dgrad"] = max(worst["dgrad"], e_d)

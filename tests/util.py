@@ -55,3 +55,22 @@ def record(key, value):
         json.dump(cur, open(path, "w"), indent=1, sort_keys=True)
     except OSError:
         pass
+
+
+def wgrad_fp64(a: torch.Tensor, dy: torch.Tensor, kernel, pad) -> torch.Tensor:
+    """float64 weight gradient of a stride-1 convolution, dW[co][ci][taps] = sum_{n,v} dy[n,co,v] * a[n,ci,v+tap-pad], as
+    one fp64 matmul per tap (the exact reference for layers whose fp32 sums run over millions of voxels, where stock
+    cuDNN fp32 itself differs from fp64 by >1e-4)."""
+    import torch.nn.functional as F
+    n, ci = a.shape[:2]
+    co = dy.shape[1]
+    X, Y, Z = dy.shape[2:]
+    ap = F.pad(a.double(), (pad[2], pad[2], pad[1], pad[1], pad[0], pad[0]))
+    g = dy.double().reshape(n, co, -1)
+    out = torch.empty((co, ci) + tuple(kernel), dtype=torch.float64, device=a.device)
+    for dx in range(kernel[0]):
+        for dyy in range(kernel[1]):
+            for dz in range(kernel[2]):
+                sl = ap[:, :, dx:dx + X, dyy:dyy + Y, dz:dz + Z].reshape(n, ci, -1)
+                out[:, :, dx, dyy, dz] = torch.einsum("nov,niv->oi", g, sl)
+    return out

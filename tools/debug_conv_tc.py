@@ -71,7 +71,7 @@ def run_prof(n, c, dims, kernel=(3, 3, 3), fold=False):
     out = (ctypes.c_int * 10)()
     LIB.query("bcp_conv_tc_fold_plan" if fold else "bcp_conv_tc_plan", n, c, c, i3(*dims), i3(*kernel), out)
     pl = list(out)
-    ops._TC_FOLD = fold
+    ops._TC_FOLD = bool(fold)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     for _ in range(3):
         ops._conv_same(a, pack.k[0], b, c, kernel, allow_tc=True)
@@ -84,14 +84,14 @@ def run_prof(n, c, dims, kernel=(3, 3, 3), fold=False):
     flops = 2.0 * n * np.prod(dims) * c * c * 27
     buf = torch.zeros(160 * 16, dtype=torch.int64, device=dev)
     y = torch.empty(ops.cb8_shape(n, c, *dims), dtype=torch.bfloat16, device=dev)
-    LIB.call("bcp_conv_tc_fwd_profiled", ptr(a), ptr(pack.k[0]), ptr(b), ptr(y), n, c, c, i3(*dims), i3(*kernel), 1 if fold else 0,
+    LIB.call("bcp_conv_tc_fwd_profiled", ptr(a), ptr(pack.k[0]), ptr(b), ptr(y), n, c, c, i3(*dims), i3(*kernel), int(fold),
              buf.data_ptr(), stream())
     torch.cuda.synchronize()
     p = buf.cpu().numpy().reshape(160, 16)
     p = p[p[:, 0] > 0]
     names = ["total", "prod_wait_emptyA", "prod_wait_emptyB", "mma_wait_fullA", "mma_wait_fullB", "mma_wait_tmem_empty",
              "epi_wait_tmem_full", "epi_work", "mma_loop_end", "items"]
-    print(f"[prof{'-fold' if fold else ''}] n={n} c={c} dims={dims} plan(BX,BY,BZ,MT,SA,SB|NS*100+TG,AS,nb,cols,smem)={pl} {us:.1f} us "
+    print(f"[prof{'-fold(epilogue warps ' + str(fold) + ')' if fold else ''}] n={n} c={c} dims={dims} plan(BX,BY,BZ,MT,SA,SB|NS*100+TG,AS,nb,cols,smem)={pl} {us:.1f} us "
           f"{flops / us * 1e-6:.1f} TF/s ctas={len(p)}", flush=True)
     print("       " + "  ".join(f"{nm}={p[:, i].mean():.0f}(max {p[:, i].max()})" for i, nm in enumerate(names)), flush=True)
 
@@ -219,8 +219,9 @@ if __name__ == "__main__":
         for cfg in [(4, 16, (112, 112, 80)), (4, 32, (56, 56, 40)), (4, 64, (28, 28, 20)), (4, 128, (14, 14, 10)), (4, 256, (7, 7, 5))]:
             run_prof(*cfg)
     if "--prof-fold" in sys.argv:
-        for cfg in [(4, 16, (112, 112, 80)), (4, 32, (56, 56, 40))]:
-            run_prof(*cfg, fold=True)
+        for ew in (8, 12, 16):
+            for cfg in [(4, 16, (112, 112, 80)), (4, 32, (56, 56, 40))]:
+                run_prof(*cfg, fold=ew)
         ops._TC_FOLD = False
     if "--wgrad" in sys.argv:
         ww = 0.0
