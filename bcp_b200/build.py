@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbcp_b200.so")
-SOURCES = ["api.cu", "elementwise.cu", "norm.cu", "loss.cu", "conv_direct.cu", "conv_tc.cu", "pool.cu", "cc.cu", "window.cu"]
+SOURCES = ["api.cu", "elementwise.cu", "norm.cu", "loss.cu", "conv_direct.cu", "conv_tc.cu", "pool.cu", "cc.cu", "window.cu", "augment.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
@@ -24,11 +24,23 @@ def _stamp():
 
 
 def build(force=False, verbose=False):
+    """Compile (if stale) and return the library path.  Serialised across processes with an exclusive file lock: under
+    torchrun every rank may arrive here at once, and only the first one must run nvcc."""
+    import fcntl
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    with open(os.path.join(HERE, "build", "lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force, verbose):
     stamp_file = os.path.join(HERE, "build", "stamp")
     stamp = _stamp()
     if not force and os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
         return LIB
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     objs = []
     procs = []
     for s in SOURCES:

@@ -505,7 +505,7 @@ struct FoldParams {
 // EW = epilogue warps (multiple of 4: TMEM lane quarter = warp % 4), EW / 4 tile subsets.  The epilogue (three TMEM loads,
 // 32 shuffles, bf16 pack, two 16-byte stores per 16 channels of a 96-row tile) is latency-bound per warp, so it takes
 // several warps per scheduler to keep up with the MMA stream (9 MMAs of N = 3*Ns per tile).
-constexpr int FOLD_EPI_WARPS_DEFAULT = 8;
+constexpr int FOLD_EPI_WARPS_DEFAULT = 16;
 
 template <bool PROF, int EW>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
@@ -638,58 +638,46 @@ conv_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
       { long long t0 = PROF ? clock64() : 0; mbar_wait(tmem_full + 8 * rt.s, rt.ph); if (PROF) { t_e0 = clock64(); w0 += t_e0 - t0; } }
       tc_fence_after();
       const uint32_t d0 = tmem_base + rt.s * (uint32_t)(p.MT * N3) + ((uint32_t)(q * 32) << 16);
+      // Lean drain.  ncu (profiles/fold_c16_ncu_r02.txt) showed the epilogue warps latency-bound on short dependencies
+      // (5.6 cycles per issued instruction per warp, two warps per scheduler) and spending a third of their instructions
+      // on per-tile index arithmetic; software-pipelining the TMEM loads did not help.  So: many warps (EW = 16, four per
+      // scheduler), few registers, 32-bit offsets, the row -> voxel map advanced incrementally, no division in the loop.
       const int L0 = sub * 96 + grp * 6 + k8;                                          // frame row of this lane in its first tile
       int iz = L0 % p.HZ, iy = (L0 / p.HZ) % p.HY, ix = (L0 / p.HZ) / p.HY;
-      // Software-pipelined drain: a unit = (tile, 16-channel chunk) = three tcgen05.ld.x16.  The loads of unit u+1 are in
-      // flight while unit u is combined (two intra-group shuffles per channel), packed and stored: two register sets, loop
-      // unrolled by two.  Without this the TMEM load latency was exposed once per tile and the epilogue, not the tensor
-      // pipe, set the pace (tools/debug_conv_tc.py --prof-fold: 222 k of 263 k cycles on the 112x112x80 layer).
-      const int nch = p.Ns >> 4;                                                       // 16-channel chunks per tile (1 or 2)
-      const int ntile = (p.MT > sub) ? (p.MT - sub + nsub - 1) / nsub : 0;
-      const int nunit = ntile * nch;
-      uint32_t A0[16], A1[16], A2[16], B0[16], B1[16], B2[16];
-      auto issue = [&](int u, uint32_t (&r0)[16], uint32_t (&r1)[16], uint32_t (&r2)[16]) {
-        const int t = u / nch, c16 = (u - t * nch) << 4;
-        const uint32_t addr = d0 + (uint32_t)((sub + t * nsub) * N3 + c16);
-        tmem_ld16(addr, r0);
-        tmem_ld16(addr + (uint32_t)p.Ns, r1);
-        tmem_ld16(addr + (uint32_t)(2 * p.Ns), r2);
-      };
-      auto consume = [&](int u, const uint32_t (&r0)[16], const uint32_t (&r1)[16], const uint32_t (&r2)[16]) {
-        const int t = u / nch, ch = u - t * nch;
-        float f[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const float a1 = __shfl_down_sync(0xffffffffu, __uint_as_float(r1[k]), 1, 8);   // D'[r+1][dz=1]
-          const float a2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[k]), 2, 8);   // D'[r+2][dz=2]
-          f[k] = (__uint_as_float(r0[k]) + a1) + a2 + bias_s[ch * 16 + k];
-        }
-        const int x = bx * p.BX + ix, y = by * p.BY + iy, z = bz * p.BZ + iz;
-        const bool valid = (k8 < 6) && (ix < p.BX) && (iy < p.BY) && (iz < p.BZ) && (x < p.X) && (y < p.Y) && (z < p.Z);
-        if (valid) {
-          const long long sp = ((long long)x * p.Y + y) * p.Z + z;
-          uint4* dst = out + ((long long)n * Cob + ((n0 >> 3) + 2 * ch)) * S + sp;
-          dst[0] = pack8(f);
-          dst[S] = pack8(f + 8);
-        }
-        if (ch == nch - 1) {                         // last chunk of the tile: advance this lane's frame row by 96 * nsub
-          iz += sz;
-          if (iz >= p.HZ) { iz -= p.HZ; ++iy; }
-          iy += sy;
-          if (iy >= p.HY) { iy -= p.HY; ++ix; }
-          ix += sx;
-        }
-      };
-      if (nunit > 0) issue(0, A0, A1, A2);
-      for (int u = 0; u < nunit; u += 2) {
-        tmem_ld_wait();
-        if (u + 1 < nunit) issue(u + 1, B0, B1, B2);
-        consume(u, A0, A1, A2);
-        if (u + 1 < nunit) {
+      const int x0 = bx * p.BX, y0 = by * p.BY, z0 = bz * p.BZ;
+      const int xlim = min(p.BX, p.X - x0), ylim = min(p.BY, p.Y - y0), zlim = min(p.BZ, p.Z - z0);
+      uint4* const out_item = out + ((long long)n * Cob + (n0 >> 3)) * S + ((long long)x0 * p.Y + y0) * p.Z + z0;
+      const uint32_t YZ = (uint32_t)(p.Y * p.Z), Zs = (uint32_t)p.Z, S32 = (uint32_t)S;
+      uint32_t taddr = d0 + (uint32_t)(sub * N3);
+      const uint32_t tstep = (uint32_t)(nsub * N3);
+      for (int mt = sub; mt < p.MT; mt += nsub, taddr += tstep) {
+        const bool valid = (k8 < 6) & (ix < xlim) & (iy < ylim) & (iz < zlim);
+        const uint32_t sp = (uint32_t)ix * YZ + (uint32_t)iy * Zs + (uint32_t)iz;
+        uint32_t ca = taddr;
+        uint4* dst = out_item + sp;
+        for (int c16 = 0; c16 < p.Ns; c16 += 16, ca += 16, dst += 2 * S32) {
+          uint32_t v0[16], v1[16], v2[16];
+          tmem_ld16(ca, v0);
+          tmem_ld16(ca + (uint32_t)p.Ns, v1);
+          tmem_ld16(ca + (uint32_t)(2 * p.Ns), v2);
           tmem_ld_wait();
-          if (u + 2 < nunit) issue(u + 2, A0, A1, A2);
-          consume(u + 1, B0, B1, B2);
+          float f[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const float a1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[k]), 1, 8);   // D'[r+1][dz=1]
+            const float a2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[k]), 2, 8);   // D'[r+2][dz=2]
+            f[k] = (__uint_as_float(v0[k]) + a1) + (a2 + bias_s[c16 + k]);
+          }
+          if (valid) {
+            dst[0] = pack8(f);
+            dst[S32] = pack8(f + 8);
+          }
         }
+        iz += sz;
+        if (iz >= p.HZ) { iz -= p.HZ; ++iy; }
+        iy += sy;
+        if (iy >= p.HY) { iy -= p.HY; ++ix; }
+        ix += sx;
       }
       tc_fence_before();
       __syncwarp();
@@ -921,6 +909,11 @@ struct WgParams {
   int fz;                         // 1 or 3
   int KG, ngrp;                   // folded: (dx,dy) groups per pass / in total
   int KS, accumulate;             // in-kernel finalize: lanes sharing one output quad (power of two <= 32); dw += or =
+  // flush mode (layers whose per-CTA accumulation chain is thousands of MMAs long): the tensor core adds into its fp32
+  // accumulator with truncation, a bias that grows linearly with the chain (measured 3e-4 relative on the 112x112x80
+  // 16-channel layer against 1.3e-5 for fp32 cuDNN).  Every `flush` bricks the accumulators of one of two TMEM sets are
+  // drained into round-to-nearest fp32 REGISTER accumulators of the epilogue warps while the MMAs continue on the other set.
+  int flush;                      // 0 = off, else bricks per flush (requires TP*Cin <= 144 columns, i.e. <= 9 accumulators x 16)
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -932,6 +925,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   const uint32_t bar_base = sbase + p.offBar;
   const uint32_t full = bar_base, empty = full + 8 * p.S, tmem_full = empty + 8 * p.S;
   volatile uint32_t* tmem_slot = (volatile uint32_t*)(smem + p.offBar + 8 * (2 * p.S + 1));
+  // flush mode: tmem_full / tmem_empty per accumulator set live behind the tap-offset table
+  const uint32_t fl_full = bar_base + 8 * (2 * p.S + 1) + 128, fl_empty = fl_full + 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int split = blockIdx.x, pass = blockIdx.y;
   const int mh = pass % p.MH, tg = pass / p.MH;
@@ -954,6 +949,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.S; ++i) { mbar_init(full + 8 * i, 1); mbar_init(empty + 8 * i, 1); }
     mbar_init(tmem_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(fl_full + 8 * i, 1); mbar_init(fl_empty + 8 * i, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dy) : "memory");
@@ -1030,8 +1026,17 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         uint32_t acc = 0;
         const uint32_t row_step_y = (uint32_t)(p.s2 ? p.ZP : p.HZ);                 // B-row distance between consecutive lines
         const uint32_t row_step_x = (uint32_t)(p.s2 ? p.BY * p.ZP : p.HY * p.HZ);
+        const uint32_t set_cols = (uint32_t)(p.TP * p.Cin);                          // flush mode: columns per accumulator set
+        uint32_t fcount = 0, fidx = 0, tm = tmem_base;                               // bricks in the current flush group, group index
         for (int brick = split; brick < p.nbricks; brick += p.splits, rs.advance(p.S)) {
           const uint32_t s = rs.s, ph = rs.ph;
+          if (p.flush && fcount == 0) {                                               // first brick of a flush group: claim a set
+            const uint32_t set = fidx & 1u;
+            mbar_wait(fl_empty + 8 * set, ((fidx >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            tm = tmem_base + set * set_cols;
+            acc = 0;
+          }
           mbar_wait(full + 8 * s, ph);
           tc_fence_after();
           const uint32_t a_slot = sbase + s * p.slot_bytes, dy_slot = a_slot + p.a_alloc_bytes;
@@ -1045,11 +1050,11 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 if (ntap == 9) {
 #pragma unroll
                   for (int tl = 0; tl < 9; ++tl)
-                    umma_bf16(tmem_base + (uint32_t)tl * cin, adesc, ((uint64_t)b_hi << 32) | (bz + tapoff[tl]), idesc, acc);
+                    umma_bf16(tm + (uint32_t)tl * cin, adesc, ((uint64_t)b_hi << 32) | (bz + tapoff[tl]), idesc, acc);
                 } else {
 #pragma unroll 4
                   for (int tl = 0; tl < ntap; ++tl)
-                    umma_bf16(tmem_base + (uint32_t)tl * cin, adesc, ((uint64_t)b_hi << 32) | (bz + tapoff[tl]), idesc, acc);
+                    umma_bf16(tm + (uint32_t)tl * cin, adesc, ((uint64_t)b_hi << 32) | (bz + tapoff[tl]), idesc, acc);
                 }
                 acc = 1;
               }
@@ -1060,8 +1065,13 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             brow_x += row_step_x;
           }
           umma_commit(empty + 8 * s);
+          if (p.flush && (++fcount == (uint32_t)p.flush || brick + p.splits >= p.nbricks)) {   // group complete: hand the set over
+            umma_commit(fl_full + 8 * (fidx & 1u));
+            ++fidx;
+            fcount = 0;
+          }
         }
-        umma_commit(tmem_full);
+        if (!p.flush) umma_commit(tmem_full);
       }
       __syncwarp();
     }
@@ -1081,6 +1091,46 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       const int r = co;
       if (r < 3 * p.Cout) { dzl = r / p.Cout; co = r - dzl * p.Cout; } else co = 1 << 30;
     }
+    if (p.flush) {
+      // register accumulators: <= 9 accumulators x 16 input channels per TMEM lane (row)
+      float accr[9][16];
+#pragma unroll
+      for (int tl = 0; tl < 9; ++tl)
+#pragma unroll
+        for (int k = 0; k < 16; ++k) accr[tl][k] = 0.f;
+      const int nb_cta = has_work ? (p.nbricks - split + p.splits - 1) / p.splits : 0;
+      const int ngroups = (nb_cta + p.flush - 1) / p.flush;
+      const uint32_t set_cols = (uint32_t)(p.TP * p.Cin);
+      for (int f = 0; f < ngroups; ++f) {
+        const uint32_t set = (uint32_t)f & 1u;
+        mbar_wait(fl_full + 8 * set, ((uint32_t)f >> 1) & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int tl = 0; tl < 9; ++tl) {
+          if (tl < ntap) {
+            uint32_t v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + set * set_cols + (uint32_t)(tl * 16), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 16; ++k) accr[tl][k] += __uint_as_float(v[k]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(fl_empty + 8 * set);
+      }
+#pragma unroll
+      for (int tl = 0; tl < 9; ++tl) {
+        if (tl < ntap && co < p.Cout) {
+          const int t = (p.fz == 3) ? (t0 + tl) * 3 + dzl : t0 + tl;
+          float4* d4 = reinterpret_cast<float4*>(partial + (((size_t)split * p.T + t) * p.Cout + co) * p.Cin);
+          d4[0] = make_float4(accr[tl][0], accr[tl][1], accr[tl][2], accr[tl][3]);
+          d4[1] = make_float4(accr[tl][4], accr[tl][5], accr[tl][6], accr[tl][7]);
+          d4[2] = make_float4(accr[tl][8], accr[tl][9], accr[tl][10], accr[tl][11]);
+          d4[3] = make_float4(accr[tl][12], accr[tl][13], accr[tl][14], accr[tl][15]);
+        }
+      }
+    } else {
     if (has_work) {
       mbar_wait(tmem_full, 0);
       tc_fence_after();
@@ -1105,6 +1155,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           d4[3] = make_float4(__uint_as_float(v[12]), __uint_as_float(v[13]), __uint_as_float(v[14]), __uint_as_float(v[15]));
         }
       }
+    }
     }
   }
   tc_fence_before();
@@ -1495,6 +1546,18 @@ static bool wg_plan(WgParams& p, int nsm) {
   if (!found) return false;
   p = bp;
   p.offBar = p.S * p.slot_bytes;
+  // flush mode for long accumulation chains (see WgParams::flush): 16 input channels, <= 9 accumulators, two sets in TMEM
+  p.flush = 0;
+  if (p.Cin == 16 && p.TP <= 9 && 2 * p.TP * p.Cin <= 512) {
+    const long long vox_cta = (long long)p.N * p.X * p.Y * p.Z / p.splits;
+    if (vox_cta > 4096) {
+      const int ks = p.BX * p.BY * (p.ZP / 16);          // MMA K-steps per brick
+      p.flush = 96 / ks > 1 ? 96 / ks : 1;
+      int cols2 = 32;
+      while (cols2 < 2 * p.TP * p.Cin) cols2 *= 2;
+      p.tmem_cols = cols2;
+    }
+  }
   return true;
 }
 
@@ -1789,7 +1852,7 @@ int bcp_conv_tc_fwd_profiled(const void* in, const void* wpack, const float* bia
 // splits x passes <= #SMs with one CTA per SM).
 static int wg_launch(const CUtensorMap& map_a, const CUtensorMap& map_dy, float* workspace, float* dw, int* counter, WgParams& p,
                      cudaStream_t stream, const char* what) {
-  const size_t smem = (size_t)p.offBar + 8 * (2 * p.S + 1) + 16 + 128 + 128;
+  const size_t smem = (size_t)p.offBar + 8 * (2 * p.S + 1) + 16 + 128 + 128 + 64;   // barriers, TMEM slot, tap table, flush barriers, alignment slack
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
@@ -1828,7 +1891,7 @@ static int wg_setup(WgParams& p, int n, int cin, int cout, const int* dims, cons
 
 long long bcp_conv_tc_wgrad_workspace_floats(int n, int cin, int cout, const int* dims, const int* kernel) {
   if (!dims || !kernel || !wg_shape_ok(cin, cout, dims, kernel)) return 0;
-  WgParams p;
+  WgParams p{};
   if (wg_setup(p, n, cin, cout, dims, kernel) != 0) return 0;
   return (long long)p.splits * p.T * cout * cin;
 }
@@ -1840,7 +1903,7 @@ int bcp_conv_tc_wgrad(const void* a, const void* dy, float* dw, float* workspace
   if (!wg_shape_ok(cin, cout, dims, kernel)) { set_last_error("conv_tc_wgrad: unsupported shape"); return BCP_ERR_UNSUPPORTED; }
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_last_error("conv_tc_wgrad: cuTensorMapEncodeTiled unavailable"); return BCP_ERR_CUDA; }
-  WgParams p;
+  WgParams p{};
   if (wg_setup(p, n, cin, cout, dims, kernel) != 0) { set_last_error("conv_tc_wgrad: no brick shape fits"); return BCP_ERR_UNSUPPORTED; }
   CUtensorMap map_a, map_dy;
   {
@@ -1962,14 +2025,14 @@ static int wg_s2_setup(WgParams& p, int n, int c_half, int c_full, const int* ha
 
 int bcp_conv_tc_s2_wgrad_supported(int c_half, int c_full, const int* half_dims) {
   if (!half_dims || !s2_shape_ok(c_full, c_half, half_dims)) return 0;
-  WgParams p;
+  WgParams p{};
   if (wg_s2_setup(p, 1, c_half, c_full, half_dims) != 0) return 0;
   return get_encode() != nullptr ? 1 : 0;
 }
 
 long long bcp_conv_tc_s2_wgrad_workspace_floats(int n, int c_half, int c_full, const int* half_dims) {
   if (!half_dims || !s2_shape_ok(c_full, c_half, half_dims)) return 0;
-  WgParams p;
+  WgParams p{};
   if (wg_s2_setup(p, n, c_half, c_full, half_dims) != 0) return 0;
   return (long long)p.splits * 8 * c_half * c_full;
 }
@@ -1980,7 +2043,7 @@ int bcp_conv_tc_s2_wgrad(const void* full, const void* half, float* dw, float* w
   if (!s2_shape_ok(c_full, c_half, half_dims)) { set_last_error("conv_tc_s2_wgrad: unsupported shape"); return BCP_ERR_UNSUPPORTED; }
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_last_error("conv_tc_s2_wgrad: cuTensorMapEncodeTiled unavailable"); return BCP_ERR_CUDA; }
-  WgParams p;
+  WgParams p{};
   if (wg_s2_setup(p, n, c_half, c_full, half_dims) != 0) { set_last_error("conv_tc_s2_wgrad: no tiling fits"); return BCP_ERR_UNSUPPORTED; }
   CUtensorMap map_a, map_dy;
   {

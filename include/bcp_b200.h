@@ -222,6 +222,13 @@ int bcp_dice_prob_fwd(const float* probs, const unsigned char* target, const uns
 int bcp_dice_prob_bwd(const float* probs, const unsigned char* target, const unsigned char* mask, const float* ctx,
                       const float* grad_out, float* dprobs, int n, int c, long long v, cudaStream_t stream);
 
+/* ---- device-side input pipeline.  One sample: RandomRotFlip (np.rot90 by k in the (x,y) plane, then
+ * np.flip along flip_axis), RandomCrop's zero padding `pad` per side and crop at `origin` (in the padded frame), ToTensor
+ * (dataloaders/dataset.py:52-60,173-225,267-277).  img fp32 / lab uint8 [W][H][D] = src_dims resident in HBM; outputs
+ * [OX][OY][OZ] = out_dims (one sample of the batch tensor).  Bit-exact vs the numpy transforms. */
+int bcp_aug_crop_rotflip(const float* img, const unsigned char* lab, float* out_img, unsigned char* out_lab, const int* src_dims,
+                         const int* out_dims, int k, int flip_axis, const int* pad, const int* origin, cudaStream_t stream);
+
 /* ---- resampling (networks/unet.py:37 MaxPool2d(2); :50 Upsample(bilinear, align_corners=True);
  * networks/VNet.py:249 MaxPool3d(3, stride=2)).  planes = n * ceil(c/8) * X. */
 int bcp_maxpool2_fwd(const void* in, void* out, long long planes, int y, int z, cudaStream_t stream);

@@ -94,8 +94,8 @@ def test_flat_grad_allreduce_world2():
 
 def test_rank_sharding_is_disjoint():
     import bench
-    a, la = bench.synthetic_batch(0, None)
-    b, lb = bench.synthetic_batch(1, None)
+    a, la = bench.synthetic_batch("la", 0)
+    b, lb = bench.synthetic_batch("la", 1)
     assert a.shape == (8, 1, 112, 112, 80) and la.dtype == torch.uint8
     assert not torch.equal(a, b)
     assert 0.01 < float(la.float().mean()) < 0.5

@@ -430,12 +430,12 @@ def test_conv_fused_norm_statistics(ops, dev, cin, cout, dims, kernel, spg):
         rm, rv = torch.zeros(cout, device=dev), torch.ones(cout, device=dev)
         nbt = torch.zeros((), dtype=torch.int64, device=dev)
         req = dict(gamma=gamma, beta=beta, running_mean=rm, running_var=rv, nbt=nbt, spg=spg, eps=1e-5, momentum=0.1)
-        old = ops._FUSE_STATS
-        ops._FUSE_STATS = fused
+        old, old_fold = ops._FUSE_STATS, ops._TC_FOLD
+        ops._FUSE_STATS, ops._TC_FOLD = fused, False      # same (unfolded) kernel on both sides: y must be bit-identical
         try:
             y = ops.ConvSame.apply(a, w, b, pack, kernel, False, req)
         finally:
-            ops._FUSE_STATS = old
+            ops._FUSE_STATS, ops._TC_FOLD = old, old_fold
         assert ("out" in req) == fused, "layer expected to be eligible for the fused-statistics epilogue"
         out = ops.NormAct.apply(y, gamma, beta, rm, rv, nbt, "batch", spg, 1e-5, 0.1, 0.0, None, None, 1.0, None, req.get("out"))
         torch.cuda.synchronize()
