@@ -262,7 +262,8 @@ __global__ void __launch_bounds__(256) sgd_ema_kernel(float* __restrict__ p, con
 }
 
 // Adam (optim.Adam defaults, pancreas/dataloaders.py:182) + EMA.  hyper = {lr, beta1, beta2, eps, ema_alpha, grad_scale,
-// bias_corr1, bias_corr2_sqrt, 1-ema_alpha, step_size = lr / bias_corr1}.  Slots 6, 7, 9 are produced ON THE DEVICE by
+// bias_corr1, bias_corr2_sqrt, 1-ema_alpha, step_size = lr / bias_corr1, 1-beta1, 1-beta2} (the two complements are formed
+// in double on the host like torch's Python expressions: 1.f - 0.999f is 1.3e-5 away from float(1 - 0.999)).  Slots 6, 7, 9 are produced ON THE DEVICE by
 // adam_tick_kernel from a device-resident step counter (so a captured CUDA graph advances the bias corrections on every
 // replay), in double precision like the Python expressions of torch.optim.Adam.
 __global__ void adam_tick_kernel(float* __restrict__ hyper, long long* __restrict__ step) {
@@ -283,7 +284,7 @@ __global__ void __launch_bounds__(256) adam_ema_kernel(float* __restrict__ p, co
   const float b1 = hyper[1], b2 = hyper[2], eps = hyper[3], alpha = hyper[4], gs = hyper[5];
   const float bc2s = hyper[7], step_size = hyper[9];
   const float one_m_alpha = hyper[8];
-  const float w1 = 1.f - b1, w2 = 1.f - b2;
+  const float w1 = hyper[10], w2 = hyper[11];
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_total; i += stride) {
     float pv = p[i];

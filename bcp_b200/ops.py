@@ -24,6 +24,8 @@ _FUSE_STATS = os.environ.get("BCP_FUSED_STATS", "0") == "1"
 # dz-folded forward kernel for 16/32-channel layers (three dz taps ride in the MMA N dimension).
 # Module switch for the parity tests / tools that compare it against the unfolded kernel.
 _TC_FOLD = True
+# single-launch cluster normalisation (csrc/norm_fused.cu) for layers of <= 32 Ki voxels per statistics group
+_NORM_FUSED = os.environ.get("BCP_DISABLE_NORM_FUSED", "0") != "1"
 
 
 def _require_cuda(t: torch.Tensor, what: str):
@@ -462,6 +464,20 @@ class NormAct(Function):
         else:
             stat = torch.empty(groups, c, 2, dtype=torch.float32, device=dev)
             coef = torch.empty(groups, c, 2, dtype=torch.float32, device=dev)
+        if residual is not None:
+            residual = residual.contiguous()
+        if mode == "batch" and precomputed is None and _NORM_FUSED and LIB.query("bcp_norm_fused_supported", n, c, s, spg):
+            # statistics + finalize + normalise/activation in ONE cluster kernel
+            out = torch.empty_like(y)
+            ws = _f32(groups * c * 2, dev)
+            LIB.call("bcp_norm_fused_fwd", ptr(y), ptr(out), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), ptr(nbt),
+                     ptr(stat), ptr(coef), ptr(ws), _counter(dev).data_ptr() + 32, ptr(chan_scale), ptr(elem_keep),
+                     float(elem_scale), ptr(residual), n, c, s, spg, float(eps), float(momentum), float(slope), stream())
+            ctx.save_for_backward(y, stat, coef, chan_scale, elem_keep)
+            ctx.meta = (n, c, s, spg, float(slope), float(elem_scale), mode, gamma is not None, beta is not None,
+                        residual is not None)
+            ctx.affine_refs = (gamma, beta)
+            return out
         if mode == "batch" and precomputed is not None:
             pass
         elif mode == "batch":
@@ -477,8 +493,6 @@ class NormAct(Function):
             coef[..., 0] = 1.0
             coef[..., 1] = 0.0
         out = torch.empty_like(y)
-        if residual is not None:
-            residual = residual.contiguous()
         LIB.call("bcp_norm_apply", ptr(y), ptr(out), ptr(coef), ptr(chan_scale), ptr(elem_keep), float(elem_scale),
                  ptr(residual), n, c, s, spg, float(slope), stream())
         ctx.save_for_backward(y, stat, coef, chan_scale, elem_keep)
@@ -500,6 +514,14 @@ class NormAct(Function):
         dgamma = (ig if direct else torch.empty(c, dtype=torch.float32, device=dev)) if need_affine else None
         dbeta = (ib if direct else torch.empty(c, dtype=torch.float32, device=dev)) if need_affine else None
         sums = torch.empty(n // spg, c, 2, dtype=torch.float32, device=dev)
+        if _NORM_FUSED and LIB.query("bcp_norm_fused_supported", n, c, s, spg):
+            LIB.call("bcp_norm_fused_bwd", ptr(da), ptr(y), ptr(dy), ptr(stat), ptr(coef), ptr(chan_scale), ptr(elem_keep), elem_scale,
+                     ptr(dgamma), ptr(dbeta), ptr(sums), _counter(dev).data_ptr() + 36, n, c, s, spg, slope,
+                     1 if mode == "batch" else 0, 1 if direct else 0, stream())
+            if direct:
+                dgamma = dbeta = None
+            return (dy, dgamma if has_g else None, dbeta if has_b else None, None, None, None, None, None, None, None, None,
+                    None, None, None, da if has_res else None, None)
         ws = _f32(LIB.query("bcp_norm_workspace_floats", n, c, s), dev)
         LIB.call("bcp_norm_bwd", ptr(da), ptr(y), ptr(dy), ptr(stat), ptr(coef), ptr(chan_scale), ptr(elem_keep), elem_scale,
                  ptr(dgamma), ptr(dbeta), ptr(sums), ptr(ws), ptr(_counter(dev)), n, c, s, spg, slope,

@@ -171,15 +171,16 @@ class FusedAdam_EMA(_FusedBase):
         self.refresh_hyper()
 
     def refresh_hyper(self):
-        """Upload {lr, b1, b2, eps, alpha, 1/world, -, -, 1-alpha} when they changed; slots 6, 7, 9 (bias corrections and
+        """Upload {lr, b1, b2, eps, alpha, 1/world, -, -, 1-alpha, -, 1-b1, 1-b2} when they changed; slots 6, 7, 9 (bias corrections and
         step size) belong to the device tick kernel and are preserved."""
         g = self.param_groups[0]
         b1, b2 = g["betas"]
-        vals = [g["lr"], b1, b2, g["eps"], self.ema_alpha, 1.0 / _world()[1], 1.0 - self.ema_alpha]
+        vals = [g["lr"], b1, b2, g["eps"], self.ema_alpha, 1.0 / _world()[1], 1.0 - self.ema_alpha, 1.0 - b1, 1.0 - b2]
         if vals != self._hyper_host:
             h = torch.tensor(vals[:6], dtype=torch.float32)
             self.hyper[:6].copy_(h, non_blocking=False)
-            self.hyper[8:9].copy_(torch.tensor(vals[6:], dtype=torch.float32), non_blocking=False)
+            self.hyper[8:9].copy_(torch.tensor(vals[6:7], dtype=torch.float32), non_blocking=False)
+            self.hyper[10:12].copy_(torch.tensor(vals[7:9], dtype=torch.float32), non_blocking=False)
             self._hyper_host = vals
 
     def step(self):

@@ -79,7 +79,8 @@ int bcp_mix_loss_bwd(const float* logits, const unsigned char* lab_img, const un
  *      update_ema_variables (utils/BCP_utils.py:78-81) / update_model_ema (ACDC_BCP_train.py:123-129).
  *      hyper (device) = {lr, momentum, weight_decay, ema_alpha, grad_scale, 1-ema_alpha}
  * Adam: torch.optim.Adam(lr) at pancreas/dataloaders.py:182 + pancreas/pancreas_utils.py:299-302.
- *      hyper (device) = {lr, beta1, beta2, eps, ema_alpha, grad_scale, 1-beta1^t, sqrt(1-beta2^t), 1-ema_alpha}
+ *      hyper (device) = {lr, beta1, beta2, eps, ema_alpha, grad_scale, 1-beta1^t, sqrt(1-beta2^t), 1-ema_alpha,
+ *                        lr/(1-beta1^t), 1-beta1, 1-beta2}  (12 floats)
  * elements [n_train, n_total) are EMA-only; ema may be NULL. */
 int bcp_sgd_ema_step(float* params, const float* grads, float* momentum, float* ema, const float* hyper,
                      long long n_train, long long n_total, cudaStream_t stream);
@@ -127,6 +128,20 @@ int bcp_norm_bwd(const void* dact, const void* y, void* dy, const float* stat, c
                  const unsigned char* elem_keep, float elem_scale, float* dgamma, float* dbeta, float* sums,
                  float* workspace, int* counter, int n, int c, long long s, int spg, float slope, int stats_grad,
                  int accumulate, cudaStream_t stream);
+
+/* Single-launch variants for layers of at most 32 Ki voxels per statistics group (csrc/norm_fused.cu): one thread-block
+ * cluster per (group, channel octet) reduces through distributed shared memory, so statistics + normalise/activation
+ * (forward) and both reductions + the input gradient (backward) are ONE kernel each.  Same semantics and argument meaning
+ * as bcp_norm_stats + bcp_norm_apply / bcp_norm_bwd; `workspace` >= (n/spg)*c*2 floats; `counter`: one zero device int of
+ * its own (self-resetting).  bcp_norm_fused_supported tells whether a shape is eligible. */
+int bcp_norm_fused_supported(int n, int c, long long s, int spg);
+int bcp_norm_fused_fwd(const void* y, void* out, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                       long long* num_batches_tracked, float* stat, float* coef, float* workspace, int* counter,
+                       const float* chan_scale, const unsigned char* elem_keep, float elem_scale, const void* residual,
+                       int n, int c, long long s, int spg, float eps, float momentum, float slope, cudaStream_t stream);
+int bcp_norm_fused_bwd(const void* dact, const void* y, void* dy, const float* stat, const float* coef, const float* chan_scale,
+                       const unsigned char* elem_keep, float elem_scale, float* dgamma, float* dbeta, float* sums, int* counter,
+                       int n, int c, long long s, int spg, float slope, int stats_grad, int accumulate, cudaStream_t stream);
 
 /* ---- convolutions (nn.Conv3d / nn.Conv2d / nn.ConvTranspose3d call sites: networks/VNet.py:17,74,101,210;
  * networks/unet.py:20,24,49,102; pancreas/Vnet.py:19,43,70,128).  dims/kernel/stride/pad are int[3] (x,y,z).

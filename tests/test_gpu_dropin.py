@@ -38,6 +38,7 @@ def test_adam_ema_vs_torch(dev):
     hyper = torch.zeros(12, dtype=torch.float32, device=dev)
     hyper[:6] = torch.tensor([1e-3, 0.9, 0.999, 1e-8, 0.99, 1.0])
     hyper[8] = 1.0 - 0.99
+    hyper[10], hyper[11] = 1.0 - 0.9, 1.0 - 0.999
     step = torch.zeros(1, dtype=torch.int64, device=dev)
     for gstep in grads:
         p.grad = gstep.clone()

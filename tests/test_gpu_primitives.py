@@ -241,6 +241,62 @@ def test_norm_act_vs_torch(ops, dev, c, spg, slope, use_drop, use_res):
         assert torch.equal(planar_from_cb8(rescb.grad, c), w)
 
 
+@pytest.mark.parametrize("n,c,dims,spg,drop,res", [(4, 64, (28, 28, 20), 2, False, False), (4, 128, (14, 14, 10), 2, True, False),
+                                                   (4, 256, (7, 7, 5), 2, False, True), (12, 128, (1, 32, 32), 6, False, False),
+                                                   (3, 64, (24, 24, 24), 1, False, False), (2, 24, (5, 9, 7), 1, True, True)])
+def test_norm_fused_cluster_vs_streaming(ops, dev, n, c, dims, spg, drop, res):
+    """csrc/norm_fused.cu (one cluster kernel per direction) against csrc/norm.cu (statistics / apply / reduce / apply
+    launches) on the mid-size and deep layer shapes it serves: same statistics to fp32 rounding, same running-stat updates,
+    outputs and gradients equal up to rare 1-ulp bf16 flips; and a batched call of G groups is BIT-identical to G calls."""
+    from bcp_b200._native import LIB
+    assert LIB.query("bcp_norm_fused_supported", n, c, int(np.prod(dims)), spg) == 1
+    torch.manual_seed(n * c + spg)
+    y = cb8_from_planar((torch.randn(n, c, *dims, device=dev) * 1.5 + 0.3).to(torch.bfloat16).float())
+    w = cb8_from_planar(torch.randn(n, c, *dims, device=dev).to(torch.bfloat16).float())
+    cs = (torch.rand(n, c, device=dev) > 0.5).float() * 2 if drop else None
+    r0 = cb8_from_planar(torch.randn(n, c, *dims, device=dev).to(torch.bfloat16).float()) if res else None
+    runs = {}
+    for fused in (True, False):
+        old = ops._NORM_FUSED
+        ops._NORM_FUSED = fused
+        try:
+            gamma = (1 + 0.1 * torch.arange(c, device=dev).float().sin()).requires_grad_(True)
+            beta = (0.1 * torch.arange(c, device=dev).float().cos()).requires_grad_(True)
+            rm, rv, nbt = torch.zeros(c, device=dev), torch.ones(c, device=dev), torch.zeros((), dtype=torch.int64, device=dev)
+            ycb = y.clone().requires_grad_(True)
+            rcb = r0.clone().requires_grad_(True) if res else None
+            l0 = LIB.launches
+            out = ops.NormAct.apply(ycb, gamma, beta, rm, rv, nbt, "batch", spg, 1e-5, 0.1, 0.01, cs, None, 1.0, rcb)
+            fwd_launches = LIB.launches - l0
+            out.backward(w)
+            torch.cuda.synchronize()
+            runs[fused] = dict(out=out.detach().float(), dy=ycb.grad.float(), dg=gamma.grad.clone(), db=beta.grad.clone(), rm=rm, rv=rv,
+                               nbt=int(nbt), launches=fwd_launches)
+        finally:
+            ops._NORM_FUSED = old
+    a, b = runs[True], runs[False]
+    assert a["launches"] == 1 and b["launches"] == 2
+    assert a["nbt"] == b["nbt"] == n // spg
+    assert torch.allclose(a["rm"], b["rm"], rtol=1e-6, atol=1e-7) and torch.allclose(a["rv"], b["rv"], rtol=1e-6, atol=1e-7)
+    assert rel_rms(a["out"], b["out"]) <= 2e-4 and rel_rms(a["dy"], b["dy"]) <= 2e-4
+    assert rel_rms(a["dg"], b["dg"]) <= 1e-5 and rel_rms(a["db"], b["db"]) <= 1e-5
+    if n // spg > 1:            # batched groups == separate calls, bit for bit (forward, running statistics, input gradient)
+        gamma = (1 + 0.1 * torch.arange(c, device=dev).float().sin())
+        beta = (0.1 * torch.arange(c, device=dev).float().cos())
+        rm, rv, nbt = torch.zeros(c, device=dev), torch.ones(c, device=dev), torch.zeros((), dtype=torch.int64, device=dev)
+        outs, dys = [], []
+        for g in range(n // spg):
+            sl = slice(g * spg, (g + 1) * spg)
+            yg = y[sl].clone().requires_grad_(True)
+            o = ops.NormAct.apply(yg, gamma, beta, rm, rv, nbt, "batch", spg, 1e-5, 0.1, 0.01, cs[sl].contiguous() if drop else None,
+                                  None, 1.0, r0[sl].clone() if res else None)
+            o.backward(w[sl].contiguous())
+            outs.append(o.detach().float())
+            dys.append(yg.grad.float())
+        assert torch.equal(torch.cat(outs), a["out"]) and torch.equal(torch.cat(dys), a["dy"])
+        assert torch.equal(rm, a["rm"]) and torch.equal(rv, a["rv"])
+
+
 def test_norm_eval_and_instance(ops, dev):
     torch.manual_seed(3)
     c, n = 16, 2

@@ -8,9 +8,10 @@ every voxel whose reference logit margin exceeds SURE_MARGIN (1.0, ~50 sigma of 
 voxels) is covered by a budget on the flip fraction.
 
 Budgets (bf16 activations vs the fp32 reference; derivation in DESIGN.md section 4):
-  pseudo-label flips  <= 1e-3 of voxels (LA), <= 2e-3 (ACDC, argmax over 4 classes)
-  first step loss     <= 1e-4 relative with the reference's pseudo labels handed to the student (isolates the student)
-                      <= 1e-3 relative fully end to end (a flipped pseudo label is a changed target, not rounding noise)
+  pseudo-label flips  <= 1e-3 of voxels (LA; 1.5e-3 after the first optimiser step), <= 2e-3 (ACDC, argmax over 4 classes)
+  first step loss     <= 1e-4 relative on the step's total loss -- the north star's budget -- both fully end to end and with
+                      the reference's pseudo labels handed to the student (measured 7e-5 / 4e-5); its two halves loss_l and
+                      loss_u individually <= 3e-4 (they carry opposite-signed bf16 errors of ~2e-4 that cancel in the sum)
   second step loss    <= 5e-3: it is evaluated on weights that took one SGD step along a bf16 gradient; the loss moves by
                       <g, dw> = lr*|g|^2 (15 % per step on these fixtures), so a 1 % aligned gradient error shows up as 1.5e-3
 """
@@ -82,7 +83,7 @@ def test_la_ckpt_step(dev, handover):
         chk(int((raw_mis & sure).sum()) == 0, 'int((raw_mis & sure).sum()) == 0')
         flips = float((r["plab"] != gp).float().mean())
         record(f"{tag}_s{it}_plab_flip_frac", flips)
-        chk(flips <= 1e-3, 'flips <= 1e-3')
+        chk(flips <= (1e-3 if it == 0 else 1.5e-3), 'plab flips', it, flips)
         # mixed inputs: bit-exact
         chk(np.allclose(tensor_digest(r["mixed"][:2]), g[f"s{it}_mixl_digest"], rtol=1e-12, atol=0), 'np.allclose(tensor_digest(r["mixed"][:2]), g[f"s{it}_mixl_di')
         assert np.allclose(tensor_digest(r["mixed"][2:]), g[f"s{it}_mixu_digest"], rtol=1e-12, atol=0)
@@ -93,7 +94,7 @@ def test_la_ckpt_step(dev, handover):
         for k in ("loss", "loss_l", "loss_u"):
             rel = _rel(r[k], g[f"s{it}_{k}"])
             record(f"{tag}_s{it}_{k}_rel_err", rel)
-            chk(rel <= ((1e-4 if handover else 1e-3) if it == 0 else 5e-3), 'rel <= ((1e-4 if handover else 1e-3) if it == 0 else 5e-3)')
+            chk(rel <= ((1e-4 if k == "loss" else 3e-4) if it == 0 else 5e-3), k, it, rel)
         # post-step weights / EMA teacher (per-tensor |sum| digests; lr 0.01 steps on trained weights)
         dm, ref = digest_named(model.state_dict()), g[f"s{it}_model_digest"]
         big = ref[:, 1] > 1e-6
