@@ -24,7 +24,7 @@ _FUSE_STATS = os.environ.get("BCP_FUSED_STATS", "0") == "1"
 # dz-folded forward kernel for 16/32-channel layers (three dz taps ride in the MMA N dimension).
 # Module switch for the parity tests / tools that compare it against the unfolded kernel.
 _TC_FOLD = True
-# single-launch cluster normalisation (csrc/norm_fused.cu) for layers of <= 32 Ki voxels per statistics group
+# single-launch cluster normalisation (csrc/norm_fused.cu) for layers of <= 64 Ki voxels per statistics group
 _NORM_FUSED = os.environ.get("BCP_DISABLE_NORM_FUSED", "0") != "1"
 
 

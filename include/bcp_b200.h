@@ -129,7 +129,7 @@ int bcp_norm_bwd(const void* dact, const void* y, void* dy, const float* stat, c
                  float* workspace, int* counter, int n, int c, long long s, int spg, float slope, int stats_grad,
                  int accumulate, cudaStream_t stream);
 
-/* Single-launch variants for layers of at most 32 Ki voxels per statistics group (csrc/norm_fused.cu): one thread-block
+/* Single-launch variants for layers of at most 64 Ki voxels per statistics group (csrc/norm_fused.cu): one thread-block
  * cluster per (group, channel octet) reduces through distributed shared memory, so statistics + normalise/activation
  * (forward) and both reductions + the input gradient (backward) are ONE kernel each.  Same semantics and argument meaning
  * as bcp_norm_stats + bcp_norm_apply / bcp_norm_bwd; `workspace` >= (n/spg)*c*2 floats; `counter`: one zero device int of

@@ -589,9 +589,62 @@ def gen_pan_step():
     save("pan_step", **out)
 
 
+def gen_dataset():
+    """dataloaders/dataset.py: the reference's LAHeart + Compose([RandomRotFlip, RandomCrop, ToTensor]) + TwoStreamBatchSampler
+    driven by a single-process torch DataLoader (num_workers=0: one np.random stream, sampler permutations interleaved
+    with the per-sample transform draws) over seeded in-memory 'scans'.  h5py is absent here: a stub ``h5py.File`` serves
+    the volumes by case name, every line of the reference module runs unmodified."""
+    import importlib.util
+    import tempfile
+    import types
+    from oracle import dataset_oracle as D
+    vols = D.synthetic_la_volumes(6, 4242)
+    names = ["case%02d" % i for i in range(len(vols))]
+
+    class _File(dict):
+        def __init__(self, path, mode="r"):
+            name = os.path.basename(os.path.dirname(path))
+            im, lb = vols[names.index(name)]
+            super().__init__(image=im, label=lb)
+    h5 = types.ModuleType("h5py")
+    h5.File = _File
+    sys.modules["h5py"] = h5
+    ref_shims._install_stubs()
+    if not hasattr(sys.modules["skimage"], "transform"):
+        tr = types.ModuleType("skimage.transform")
+        sys.modules["skimage"].transform = tr
+        sys.modules["skimage.transform"] = tr
+    spec = importlib.util.spec_from_file_location("ref_dataloaders_dataset", os.path.join(ref_shims.REF_CODE, "dataloaders", "dataset.py"))
+    ds = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ds)
+    from torchvision import transforms as TV
+    patch = (24, 20, 16)
+    out = dict(patch=np.array(patch), nvol=len(vols), seed=99, labeled=2, batch_size=4, labeled_bs=2, epochs=3)
+    with tempfile.TemporaryDirectory() as d:
+        with open(os.path.join(d, "train.list"), "w") as f:
+            f.write("\n".join(names) + "\n")
+        db = ds.LAHeart(base_dir=d, split="train", transform=TV.Compose([ds.RandomRotFlip(), ds.RandomCrop(patch), ds.ToTensor()]))
+        sampler = ds.TwoStreamBatchSampler(list(range(2)), list(range(2, 6)), 4, 4 - 2)
+        loader = torch.utils.data.DataLoader(db, batch_sampler=sampler, num_workers=0)
+        np.random.seed(99)
+        b = 0
+        for epoch in range(3):
+            for batch in loader:
+                out[f"b{b}_image"] = batch["image"].numpy().astype(np.float32)
+                out[f"b{b}_label"] = batch["label"].numpy().astype(np.uint8)
+                b += 1
+        out["nbatches"] = b
+        # the index stream alone (same seed, sampler only)
+        np.random.seed(7)
+        out["sampler_indices"] = np.array([list(t) for _ in range(3) for t in sampler], dtype=np.int64)
+    save("dataset", **out)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["functions", "networks", "la_small", "la_pre", "acdc", "la_full", "pan", "acdc_pre", "pan_pre", "sliding",
-                             "ckpt_weights", "la_ckpt", "acdc_ckpt"]
+                             "ckpt_weights", "la_ckpt", "acdc_ckpt", "dataset"]
+    if "dataset" in which:
+        gen_dataset()
     if "ckpt_weights" in which:
         gen_ckpt_weights()
     if "la_ckpt" in which:

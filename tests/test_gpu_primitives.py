@@ -243,7 +243,8 @@ def test_norm_act_vs_torch(ops, dev, c, spg, slope, use_drop, use_res):
 
 @pytest.mark.parametrize("n,c,dims,spg,drop,res", [(4, 64, (28, 28, 20), 2, False, False), (4, 128, (14, 14, 10), 2, True, False),
                                                    (4, 256, (7, 7, 5), 2, False, True), (12, 128, (1, 32, 32), 6, False, False),
-                                                   (3, 64, (24, 24, 24), 1, False, False), (2, 24, (5, 9, 7), 1, True, True)])
+                                                   (3, 64, (24, 24, 24), 1, False, False), (2, 24, (5, 9, 7), 1, True, True),
+                                                   (4, 32, (28, 28, 40), 2, False, False), (4, 32, (40, 40, 40), 1, True, True)])
 def test_norm_fused_cluster_vs_streaming(ops, dev, n, c, dims, spg, drop, res):
     """csrc/norm_fused.cu (one cluster kernel per direction) against csrc/norm.cu (statistics / apply / reduce / apply
     launches) on the mid-size and deep layer shapes it serves: same statistics to fp32 rounding, same running-stat updates,

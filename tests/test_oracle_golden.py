@@ -387,3 +387,55 @@ def test_acdc_ckpt_step():
     assert np.array_equal(torch.cat([r["plab_a"], r["plab_b"]]).numpy().astype(np.uint8), g["s0_plab"])
     digests_close(digest_named(model.state_dict()), g["s0_model_digest"])
     digests_close(digest_named(ema.state_dict()), g["s0_ema_digest"])
+
+
+def test_dataset_pipeline():
+    """oracle/dataset_oracle.py against tests/golden/dataset.npz (the reference's LAHeart + RandomRotFlip + RandomCrop +
+    ToTensor + TwoStreamBatchSampler under a single-process DataLoader): same np.random stream, bit-identical batches."""
+    from oracle import dataset_oracle as D
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "dataset.npz"))
+    vols = D.synthetic_la_volumes(int(g["nvol"]), 4242)
+    patch = tuple(int(v) for v in g["patch"])
+    lab_n, bs, lbs = int(g["labeled"]), int(g["batch_size"]), int(g["labeled_bs"])
+    np.random.seed(7)
+    idx = [list(t) for _ in range(int(g["epochs"])) for t in D.two_stream_batches(list(range(lab_n)), list(range(lab_n, len(vols))), bs, bs - lbs)]
+    assert np.array_equal(np.array(idx), g["sampler_indices"])
+    np.random.seed(int(g["seed"]))
+    b = 0
+    for _ in range(int(g["epochs"])):
+        for indices in D.two_stream_batches(list(range(lab_n)), list(range(lab_n, len(vols))), bs, bs - lbs):
+            im, lb = D.la_batch(vols, indices, patch)
+            assert np.array_equal(im, g[f"b{b}_image"]) and np.array_equal(lb.astype(np.uint8), g[f"b{b}_label"])
+            b += 1
+    assert b == int(g["nbatches"])
+    assert any(v[0].shape[0] <= patch[0] or v[0].shape[1] <= patch[1] or v[0].shape[2] <= patch[2] for v in vols), "padding branch not exercised"
+
+
+def test_dataset_host_draws_match_oracle():
+    """bcp_b200.dataloaders.dataset (host side: sampler + parameter draws, no kernels) consumes np.random exactly like the
+    reference pipeline: same index tuples, and the drawn (k, axis, pad, origin) reproduce the golden batches when applied
+    with numpy."""
+    from bcp_b200.dataloaders import dataset as P
+    from oracle import dataset_oracle as D
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "dataset.npz"))
+    vols = D.synthetic_la_volumes(int(g["nvol"]), 4242)
+    patch = tuple(int(v) for v in g["patch"])
+    lab_n, bs, lbs = int(g["labeled"]), int(g["batch_size"]), int(g["labeled_bs"])
+    sampler = P.TwoStreamBatchSampler(list(range(lab_n)), list(range(lab_n, len(vols))), bs, bs - lbs)
+    assert len(sampler) == lab_n // lbs
+    np.random.seed(7)
+    idx = [[int(v) for v in t] for _ in range(int(g["epochs"])) for t in sampler]
+    assert np.array_equal(np.array(idx), g["sampler_indices"])
+    np.random.seed(int(g["seed"]))
+    b = 0
+    for _ in range(int(g["epochs"])):
+        for indices in sampler:
+            for j, i in enumerate(indices):
+                im, lb = vols[int(i)]
+                p = P.draw_rotflip_crop(im.shape, patch)
+                r = np.flip(np.rot90(im, p["k"]), axis=p["axis"])
+                pw, ph, pd = p["pad"]
+                r = np.pad(r, [(pw, pw), (ph, ph), (pd, pd)], mode="constant")
+                w1, h1, d1 = p["origin"]
+                assert np.array_equal(r[w1:w1 + patch[0], h1:h1 + patch[1], d1:d1 + patch[2]], g[f"b{b}_image"][j, 0])
+            b += 1
