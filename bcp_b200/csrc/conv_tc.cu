@@ -914,6 +914,13 @@ struct WgParams {
   // 16-channel layer against 1.3e-5 for fp32 cuDNN).  Every `flush` bricks the accumulators of one of two TMEM sets are
   // drained into round-to-nearest fp32 REGISTER accumulators of the epilogue warps while the MMAs continue on the other set.
   int flush;                      // 0 = off, else bricks per flush (requires TP*Cin <= 144 columns, i.e. <= 9 accumulators x 16)
+  // dx-folded mode (dz-folded layers with 3*Cin <= 256 and bricks one x-plane thick, BX = 1): the halo'd a brick holds its
+  // three x-planes [plane][x = dx][y][z]; with HX = 3 the channel-plane stride is exactly 3 x-plane strides, so an MN-major
+  // B descriptor whose N-group stride is ONE x-plane walks (plane, dx) uniformly: N = 3*Cin columns = the three dx taps of
+  // every input channel in ONE MMA.  A K-step then issues 3 MMAs (dy = address offset) of N = 3*Cin instead of 9 of N = Cin:
+  // 132 instead of 351 tensor-pipe cycles for 16 channels, 168 instead of 360 for 32 (cost max(N/2, 32 + N/4) per MMA).
+  // Accumulator dy: column (plane*3 + dx)*8 + c8.
+  int dxf;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -932,6 +939,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   const int mh = pass % p.MH, tg = pass / p.MH;
   const int t0 = (p.fz == 3) ? tg * p.KG : tg * p.TP;                           // first tap (folded: first (dx,dy) group)
   const int ntap = (p.fz == 3) ? min(p.KG, p.ngrp - t0) : min(p.TP, p.T - t0);  // accumulators this CTA owns
+  const int acc_cols = p.dxf ? 3 * p.Cin : p.Cin;                                // columns per accumulator
   const int Cib = p.Cin >> 3, Cob = p.Cout >> 3;
 
   // zero the regions TMA never writes (unused dy planes, slack rows after the a planes): they feed MMAs
@@ -1001,10 +1009,11 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   } else if (warp == 1) {
     if (has_work) {
       // M = 128, N = Cin, both operands MN-major (bits 15, 16)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.Cin >> 3) << 17) | ((uint32_t)(p.MM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(acc_cols >> 3) << 17) | ((uint32_t)(p.MM >> 4) << 24);
       // constant descriptor parts; per MMA only the 16-byte-unit start address changes
       const uint64_t adesc0 = make_desc(0, 128u, (uint32_t)p.rows_dy * 16u);
-      const uint64_t bdesc0 = make_desc(0, 128u, (uint32_t)p.rows_a * 16u);
+      // B N-group stride: the next 8-channel plane -- or, dx-folded, the next x-plane of the halo'd brick
+      const uint64_t bdesc0 = make_desc(0, 128u, p.dxf ? (uint32_t)(p.HY * p.HZ) * 16u : (uint32_t)p.rows_a * 16u);
       // per-accumulator B row offset (same-conv: halo shift of the tap; folded: (dx,dy) shift only; stride-2: separate
       // gathered brick per tap)
       uint32_t* tapoff = reinterpret_cast<uint32_t*>(smem + p.offBar + 8 * (2 * p.S + 1) + 16);
@@ -1012,6 +1021,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         const int t = t0 + lane;
         uint32_t off;
         if (p.s2) off = (uint32_t)lane * (p.tap_bytes >> 4);
+        else if (p.dxf) off = (uint32_t)(t * p.HZ);                                 // accumulator = dy
         else if (p.fz == 3) off = (p.kx == 3) ? (uint32_t)(((t / 3) * p.HY + (t % 3)) * p.HZ) : (uint32_t)(t * p.HZ);
         else { const int tz = t % 3, ty = (t / 3) % 3, tx = t / 9; off = (uint32_t)((tx * p.HY + ty) * p.HZ + tz); }
         tapoff[lane] = off;
@@ -1021,12 +1031,12 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       if (elect_one()) {
         const uint32_t a_hi = (uint32_t)(adesc0 >> 32), b_hi = (uint32_t)(bdesc0 >> 32);
         const uint32_t a_lo0 = (uint32_t)adesc0, b_lo0 = (uint32_t)bdesc0;
-        const uint32_t cin = (uint32_t)p.Cin;
+        const uint32_t cin = (uint32_t)acc_cols;
         Ring rs;
         uint32_t acc = 0;
         const uint32_t row_step_y = (uint32_t)(p.s2 ? p.ZP : p.HZ);                 // B-row distance between consecutive lines
         const uint32_t row_step_x = (uint32_t)(p.s2 ? p.BY * p.ZP : p.HY * p.HZ);
-        const uint32_t set_cols = (uint32_t)(p.TP * p.Cin);                          // flush mode: columns per accumulator set
+        const uint32_t set_cols = (uint32_t)(p.TP * acc_cols);                       // flush mode: columns per accumulator set
         uint32_t fcount = 0, fidx = 0, tm = tmem_base;                               // bricks in the current flush group, group index
         for (int brick = split; brick < p.nbricks; brick += p.splits, rs.advance(p.S)) {
           const uint32_t s = rs.s, ph = rs.ph;
@@ -1050,6 +1060,10 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 if (ntap == 9) {
 #pragma unroll
                   for (int tl = 0; tl < 9; ++tl)
+                    umma_bf16(tm + (uint32_t)tl * cin, adesc, ((uint64_t)b_hi << 32) | (bz + tapoff[tl]), idesc, acc);
+                } else if (ntap == 3) {
+#pragma unroll
+                  for (int tl = 0; tl < 3; ++tl)
                     umma_bf16(tm + (uint32_t)tl * cin, adesc, ((uint64_t)b_hi << 32) | (bz + tapoff[tl]), idesc, acc);
                 } else {
 #pragma unroll 4
@@ -1100,14 +1114,15 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         for (int k = 0; k < 16; ++k) accr[tl][k] = 0.f;
       const int nb_cta = has_work ? (p.nbricks - split + p.splits - 1) / p.splits : 0;
       const int ngroups = (nb_cta + p.flush - 1) / p.flush;
-      const uint32_t set_cols = (uint32_t)(p.TP * p.Cin);
+      const uint32_t set_cols = (uint32_t)(p.TP * acc_cols);
+      const int nblk = p.dxf ? 9 : ntap;                 // 16-column blocks per accumulator set (dx-folded: 3 accumulators x 48)
       for (int f = 0; f < ngroups; ++f) {
         const uint32_t set = (uint32_t)f & 1u;
         mbar_wait(fl_full + 8 * set, ((uint32_t)f >> 1) & 1u);
         tc_fence_after();
 #pragma unroll
         for (int tl = 0; tl < 9; ++tl) {
-          if (tl < ntap) {
+          if (tl < nblk) {
             uint32_t v[16];
             tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + set * set_cols + (uint32_t)(tl * 16), v);
             tmem_ld_wait();
@@ -1121,13 +1136,25 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       }
 #pragma unroll
       for (int tl = 0; tl < 9; ++tl) {
-        if (tl < ntap && co < p.Cout) {
+        if (tl < nblk && co < p.Cout) {
+          if (p.dxf) {                     // block tl = (dy, 16-column chunk): two (plane, dx) octets (Cin = 16)
+            const int dy = tl / 3, ch = tl - dy * 3;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int gidx = ch * 2 + h, plane = gidx / 3, dx = gidx - plane * 3;
+              const int t = (dx * 3 + dy) * 3 + dzl;
+              float4* d4 = reinterpret_cast<float4*>(partial + (((size_t)split * p.T + t) * p.Cout + co) * p.Cin + plane * 8);
+              d4[0] = make_float4(accr[tl][8 * h + 0], accr[tl][8 * h + 1], accr[tl][8 * h + 2], accr[tl][8 * h + 3]);
+              d4[1] = make_float4(accr[tl][8 * h + 4], accr[tl][8 * h + 5], accr[tl][8 * h + 6], accr[tl][8 * h + 7]);
+            }
+          } else {
           const int t = (p.fz == 3) ? (t0 + tl) * 3 + dzl : t0 + tl;
           float4* d4 = reinterpret_cast<float4*>(partial + (((size_t)split * p.T + t) * p.Cout + co) * p.Cin);
           d4[0] = make_float4(accr[tl][0], accr[tl][1], accr[tl][2], accr[tl][3]);
           d4[1] = make_float4(accr[tl][4], accr[tl][5], accr[tl][6], accr[tl][7]);
           d4[2] = make_float4(accr[tl][8], accr[tl][9], accr[tl][10], accr[tl][11]);
           d4[3] = make_float4(accr[tl][12], accr[tl][13], accr[tl][14], accr[tl][15]);
+          }
         }
       }
     } else {
@@ -1135,6 +1162,31 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       mbar_wait(tmem_full, 0);
       tc_fence_after();
     }
+    if (p.dxf) {
+      // accumulator tl = dy; its 3*Cin columns are (plane, dx) octets
+      for (int tl = 0; tl < ntap; ++tl) {
+        for (int c16 = 0; c16 < acc_cols; c16 += 16) {
+          uint32_t v[16];
+          if (has_work) {
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tl * acc_cols + c16), v);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = 0u;
+          }
+          if (co < p.Cout) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int gidx = (c16 >> 3) + h, plane = gidx / 3, dx = gidx - plane * 3;
+              const int t = (dx * 3 + tl) * 3 + dzl;
+              float4* d4 = reinterpret_cast<float4*>(partial + (((size_t)split * p.T + t) * p.Cout + co) * p.Cin + plane * 8);
+              d4[0] = make_float4(__uint_as_float(v[8 * h + 0]), __uint_as_float(v[8 * h + 1]), __uint_as_float(v[8 * h + 2]), __uint_as_float(v[8 * h + 3]));
+              d4[1] = make_float4(__uint_as_float(v[8 * h + 4]), __uint_as_float(v[8 * h + 5]), __uint_as_float(v[8 * h + 6]), __uint_as_float(v[8 * h + 7]));
+            }
+          }
+        }
+      }
+    } else
     for (int tl = 0; tl < ntap; ++tl) {
       const int t = (p.fz == 3) ? (t0 + tl) * 3 + dzl : t0 + tl;
       float* dst = partial + (((size_t)split * p.T + t) * p.Cout + co) * p.Cin;
@@ -1488,7 +1540,7 @@ static bool wg_plan(WgParams& p, int nsm) {
   p.m64map = wg_m64_mode() < 0 ? 0 : wg_m64_mode();
   p.HZ = p.Z + 2;
   p.ZP = (p.Z + 15) / 16 * 16;
-  p.fz = 1; p.KG = 0; p.ngrp = 0;
+  p.fz = 1; p.KG = 0; p.ngrp = 0; p.dxf = 0;
   if (3 * p.Cout <= 128 && (p.Z + 2 + 15) / 16 * 16 <= 256 && p.Cin <= 512 / 3 && (wg_m64_mode() >= 0 || 3 * p.Cout > 64)) {
     // dz-folded: K runs over the halo'd z-line (Z+2 rows, rounded up to 16); both bricks use that z extent
     p.fz = 3;
@@ -1502,16 +1554,21 @@ static bool wg_plan(WgParams& p, int nsm) {
     p.MH = 1;
     p.PL = p.Cout / 8;
     p.MM = (3 * p.Cout <= 64) ? 64 : 128;
+    if (p.kx == 3 && 3 * p.Cin <= 256 && 9 * p.Cin <= 512) {      // dx-folded (WgParams::dxf): three dy accumulators of 3*Cin columns
+      p.dxf = 1;
+      p.ngrp = 3; p.KG = 3; p.TP = 3; p.npass_t = 1;
+    }
   }
   const int npass = p.npass_t * p.MH;
+  const int acc_cols = p.dxf ? 3 * p.Cin : p.Cin;
   int cols = 32;
-  while (cols < p.TP * p.Cin) cols *= 2;
+  while (cols < p.TP * acc_cols) cols *= 2;
   p.tmem_cols = cols;
   double best = 1e300;
   bool found = false;
   WgParams bp = p;
   const int Cib = p.Cin / 8;
-  const int bxmax = (p.kx == 1) ? 1 : p.X;
+  const int bxmax = (p.kx == 1 || p.dxf) ? 1 : p.X;            // dx-folded: HX must be 3 (plane stride = 3 x-plane strides)
   for (int BY = 1; BY <= p.Y && BY + 2 <= 256; ++BY) {
     for (int BX = 1; BX <= bxmax; ++BX) {
       const int HX = BX + p.kx - 1, HY = BY + 2;
@@ -1530,7 +1587,7 @@ static bool wg_plan(WgParams& p, int nsm) {
       if (splits < 1) splits = 1;
       if (splits > nb) splits = nb;
       const long long per_cta = (nb + splits - 1) / splits;
-      const double per_mma = (p.Cin / 2.0 > 32.0 + p.Cin / 4.0) ? p.Cin / 2.0 : 32.0 + p.Cin / 4.0;
+      const double per_mma = (acc_cols / 2.0 > 32.0 + acc_cols / 4.0) ? acc_cols / 2.0 : 32.0 + acc_cols / 4.0;
       const double mma_cyc = (double)BX * BY * (p.ZP / 16) * p.TP * per_mma;
       const double load_cyc = (double)(a_tx + dy_tx) / 40.0;
       const double cost = (double)per_cta * ((mma_cyc > load_cyc ? mma_cyc : load_cyc) + 1200.0);
@@ -1548,13 +1605,13 @@ static bool wg_plan(WgParams& p, int nsm) {
   p.offBar = p.S * p.slot_bytes;
   // flush mode for long accumulation chains (see WgParams::flush): 16 input channels, <= 9 accumulators, two sets in TMEM
   p.flush = 0;
-  if (p.Cin == 16 && p.TP <= 9 && 2 * p.TP * p.Cin <= 512) {
+  if (p.Cin == 16 && p.TP * acc_cols <= 144 && 2 * p.TP * acc_cols <= 512) {
     const long long vox_cta = (long long)p.N * p.X * p.Y * p.Z / p.splits;
     if (vox_cta > 4096) {
       const int ks = p.BX * p.BY * (p.ZP / 16);          // MMA K-steps per brick
       p.flush = 96 / ks > 1 ? 96 / ks : 1;
       int cols2 = 32;
-      while (cols2 < 2 * p.TP * p.Cin) cols2 *= 2;
+      while (cols2 < 2 * p.TP * acc_cols) cols2 *= 2;
       p.tmem_cols = cols2;
     }
   }
