@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(LT) mix_loss_fwd_kernel(const float* __restric
   float acc[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) acc[k] = 0.f;
+#pragma unroll 2
   for (long long v = v0 + threadIdx.x; v < v1; v += LT) {
     float x[C];
     float m = -INFINITY;
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(LT) dice_prob_bwd_kernel(const float* __restri
 }
 
 static inline int loss_blocks(long long V) {
-  long long b = (V + 8191) / 8192;
+  long long b = (V + 4095) / 4096;       // with the per-sample grid dimension: ~4 resident blocks per SM on the LA volumes
   if (b < 1) b = 1;
   if (b > 296) b = 296;
   return (int)b;

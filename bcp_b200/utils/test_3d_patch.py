@@ -4,7 +4,7 @@
 Differences that do not change the arithmetic: windows go through the network ``batch`` at a time (eval-mode BatchNorm uses
 running statistics, so batching cannot change a window's logits); the score / count maps live on the GPU and are updated
 by ``bcp_window_accumulate`` window by window in the reference's order; one D2H copy at the end instead of one per window.
-EXPERIMENTAL: first GPU run pending."""
+Parity: tests/test_gpu_networks.py::test_sliding_window_validation (fixture minted from the reference function)."""
 from __future__ import annotations
 
 import math
@@ -71,3 +71,40 @@ def test_single_case(model, image, stride_xy, stride_z, patch_size, num_classes=
         score_np = score_np[lo[0]:lo[0] + w, lo[1]:lo[1] + h, lo[2]:lo[2] + d]
     # the reference keeps `num_classes` identical planes (it adds the class-1 probability to every plane)
     return label_np, np.broadcast_to(score_np[None], (num_classes,) + score_np.shape).copy()
+
+
+def _read_case(root_path, name):
+    import os
+    h5 = os.path.join(root_path, "2018LA_Seg_Training Set", name, "mri_norm2.h5")
+    if os.path.exists(h5):
+        import h5py
+        with h5py.File(h5, "r") as f:
+            return f["image"][:], f["label"][:]
+    z = np.load(os.path.join(root_path, name + ".npz"))
+    return z["image"], z["label"]
+
+
+def dice_binary(pred, gt):
+    """medpy.metric.binary.dc: 2|A & B| / (|A| + |B|), 0 when both are empty."""
+    a, b = np.asarray(pred) > 0, np.asarray(gt) > 0
+    den = int(a.sum()) + int(b.sum())
+    return 2.0 * int((a & b).sum()) / den if den else 0.0
+
+
+def var_all_case_LA(model, num_classes, patch_size=(112, 112, 80), stride_xy=18, stride_z=4, root_path="/data/byh_data/SSNet_data/LA",
+                    cases=None):
+    """utils/test_3d_patch.py:20-39: mean Dice of the sliding-window prediction over the test list.  ``cases``: optional
+    [(image, label)] already in memory (tests)."""
+    if cases is None:
+        import os
+        with open(os.path.join(root_path, "test.list"), "r") as f:
+            names = [l.replace("\n", "") for l in f.readlines()]
+        cases = (_read_case(root_path, n) for n in names)
+    total, count = 0.0, 0
+    for image, label in cases:
+        prediction, _ = test_single_case(model, image, stride_xy, stride_z, patch_size, num_classes=num_classes)
+        total += 0.0 if np.sum(prediction) == 0 else dice_binary(prediction, label)
+        count += 1
+    avg = total / max(count, 1)
+    print("average metric is {}".format(avg))
+    return avg

@@ -11,6 +11,7 @@ import argparse
 import logging
 import os
 import random
+import time
 import sys
 
 import numpy as np
@@ -41,24 +42,34 @@ parser.add_argument('--s_param', type=int, default=6, help='multinum of random m
 parser.add_argument('--synthetic', type=int, default=1)
 parser.add_argument('--max_steps', type=int, default=0)
 parser.add_argument('--log_every', type=int, default=10)
+parser.add_argument('--graph', type=int, default=1, help='replay each step as one CUDA graph (0: eager step functions)')
+parser.add_argument('--resume', type=int, default=0, help='continue a stage from <snapshot>/resume.pth when it exists')
+parser.add_argument('--ckpt_every', type=int, default=0, help='write the resume artefact every N iterations (0: never)')
 
 
 class SyntheticACDC:
     """{'image': [B,1,256,256] fp32 in [0,1], 'label': [B,256,256] uint8 in 0..3}, labeled slices first
-    (dataloaders/dataset.py:15-50,69-88,280-307)."""
+    (dataloaders/dataset.py:15-50,69-88,280-307).  A few pinned host batches are cycled: the per-step H2D copy stays, the
+    host RNG does not sit in the training loop."""
 
-    def __init__(self, batch_size, patch, seed, device):
+    def __init__(self, batch_size, patch, seed, device, pool=4):
         self.bs, self.patch, self.dev = batch_size, tuple(patch), device
-        self.gen = torch.Generator(device="cpu").manual_seed(seed)
-
-    def __iter__(self):
-        while True:
-            img = torch.rand((self.bs, 1) + self.patch, generator=self.gen)
-            noise = torch.randn((self.bs, 1) + self.patch, generator=self.gen)
+        gen = torch.Generator(device="cpu").manual_seed(seed)
+        self.pool = []
+        for _ in range(pool):
+            img = torch.rand((self.bs, 1) + self.patch, generator=gen)
+            noise = torch.randn((self.bs, 1) + self.patch, generator=gen)
             sm = torch.nn.functional.avg_pool2d(noise, 9, stride=1, padding=4)[:, 0]
             sm = sm / sm.std()
             lab = torch.bucketize(sm, torch.tensor([0.6, 1.0, 1.5])).to(torch.uint8)
-            yield {"image": img.pin_memory().to(self.dev, non_blocking=True), "label": lab.pin_memory().to(self.dev, non_blocking=True)}
+            self.pool.append((img.pin_memory(), lab.pin_memory()))
+
+    def __iter__(self):
+        k = 0
+        while True:
+            img, lab = self.pool[k % len(self.pool)]
+            k += 1
+            yield {"image": img, "label": lab}
 
 
 def make_loader(args, device, rank):
@@ -67,23 +78,57 @@ def make_loader(args, device, rank):
     raise RuntimeError("real ACDC data needs h5py and the dataset at --root_path (use --synthetic 1)")
 
 
+def run_stage(args, stage, model, ema_model, optimizer, snapshot_path, device, rank, max_iterations):
+    """One stage's loop.  Every step is ONE CUDA-graph replay (bcp_b200/graph.py): the U-Net step is ~330 launches of a few
+    microseconds each, so the eager step functions (--graph 0) are bound by the Python enqueue, not by the GPU."""
+    from bcp_b200.graph import GraphedStep
+    from bcp_b200.step import acdc_pre_train_step, acdc_self_train_step
+    from bcp_b200.utils.checkpoint import load_resume, save_resume
+    kind = "acdc_pre" if stage == "pre_train" else "acdc"
+    iters = max_iterations if not args.max_steps else min(args.max_steps, max_iterations)
+    resume_path = os.path.join(snapshot_path, "resume.pth")
+    it = 0
+    if args.resume and os.path.exists(resume_path):
+        it, _, _ = load_resume(resume_path, model, optimizer, ema_model)
+        logging.info("resumed %s at iteration %d from %s" % (stage, it, resume_path))
+    gs = None
+    if args.graph:
+        kw = dict(labeled_bs=args.labeled_bs)
+        if kind == "acdc":
+            kw["u_weight"] = args.u_weight
+        state = np.random.get_state()                  # the capture warm-up draws boxes
+        gs = GraphedStep(kind, model, ema_model, optimizer, (args.batch_size, 1) + tuple(args.patch_size), device=device, **kw)
+        np.random.set_state(state)
+    t0, it0 = time.time(), it
+    for batch in make_loader(args, device, rank):
+        if it >= iters:
+            break
+        if gs is not None:
+            r = gs(batch['image'], batch['label'])
+        else:
+            vol, lab = batch['image'].to(device, non_blocking=True), batch['label'].to(device, non_blocking=True)
+            if kind == "acdc_pre":
+                r = acdc_pre_train_step(model, optimizer, vol, lab, args.labeled_bs)           # ACDC_BCP_train.py:237-255
+            else:
+                r = acdc_self_train_step(model, ema_model, optimizer, vol, lab, args.labeled_bs, args.u_weight)   # :354-390
+        it += 1
+        if it % args.log_every == 0 and rank == 0:
+            logging.info('iteration %d: loss: %f, mix_dice: %f, mix_ce: %f' % (it, float(r['loss']), float(r['loss_dice']), float(r['loss_ce'])))
+        if args.ckpt_every and it % args.ckpt_every == 0 and rank == 0:
+            save_resume(resume_path, model, optimizer, ema_model, it, stage)
+    torch.cuda.synchronize(device)
+    if rank == 0:
+        logging.info("%s: %d iterations, %.2f it/s" % (stage, it - it0, (it - it0) / max(time.time() - t0, 1e-9)))
+    return it
+
+
 def pre_train(args, snapshot_path, device, rank):
     from bcp_b200.networks.net_factory import BCP_net
     from bcp_b200.optim import FusedSGD_EMA
-    from bcp_b200.step import acdc_pre_train_step
     model = BCP_net(in_chns=1, class_num=args.num_classes)
     optimizer = FusedSGD_EMA(model, None, lr=args.base_lr, momentum=0.9, weight_decay=0.0001)
     model.train()
-    iters = args.pre_iterations if not args.max_steps else min(args.max_steps, args.pre_iterations)
-    it = 0
-    for batch in make_loader(args, device, rank):
-        res = acdc_pre_train_step(model, optimizer, batch['image'], batch['label'], args.labeled_bs)   # ACDC_BCP_train.py:237-255
-        loss, r = res["loss"], (None, res["loss_dice"], res["loss_ce"])
-        it += 1
-        if it % args.log_every == 0 and rank == 0:
-            logging.info('iteration %d: loss: %f, mix_dice: %f, mix_ce: %f' % (it, float(loss), float(r[1]), float(r[2])))
-        if it >= iters:
-            break
+    run_stage(args, "pre_train", model, None, optimizer, snapshot_path, device, rank, args.pre_iterations)
     if rank == 0:
         torch.save({'net': model.state_dict(), 'opt': optimizer.state_dict()}, os.path.join(snapshot_path, '{}_best_model.pth'.format(args.model)))
 
@@ -91,25 +136,16 @@ def pre_train(args, snapshot_path, device, rank):
 def self_train(args, pre_snapshot_path, snapshot_path, device, rank):
     from bcp_b200.networks.net_factory import BCP_net
     from bcp_b200.optim import FusedSGD_EMA
-    from bcp_b200.step import acdc_self_train_step
     model = BCP_net(in_chns=1, class_num=args.num_classes)
     ema_model = BCP_net(in_chns=1, class_num=args.num_classes, ema=True)
-    state = torch.load(os.path.join(pre_snapshot_path, '{}_best_model.pth'.format(args.model)))
+    state = torch.load(os.path.join(pre_snapshot_path, '{}_best_model.pth'.format(args.model)), weights_only=False)
     model.load_state_dict(state['net'])
     ema_model.load_state_dict(state['net'])
     optimizer = FusedSGD_EMA(model, ema_model, lr=args.base_lr, momentum=0.9, weight_decay=0.0001, ema_alpha=0.99, ema_mode="state_dict")
     optimizer.load_state_dict(state['opt'])                                          # load_net_opt(model, optimizer, ...) :335
     model.train()
     ema_model.train()
-    iters = args.max_iterations if not args.max_steps else min(args.max_steps, args.max_iterations)
-    it = 0
-    for batch in make_loader(args, device, rank):
-        r = acdc_self_train_step(model, ema_model, optimizer, batch['image'], batch['label'], args.labeled_bs, args.u_weight)
-        it += 1
-        if it % args.log_every == 0 and rank == 0:
-            logging.info('iteration %d: loss: %f, mix_dice: %f, mix_ce: %f' % (it, float(r['loss']), float(r['loss_dice']), float(r['loss_ce'])))
-        if it >= iters:
-            break
+    run_stage(args, "self_train", model, ema_model, optimizer, snapshot_path, device, rank, args.max_iterations)
     if rank == 0:
         torch.save(model.state_dict(), os.path.join(snapshot_path, '{}_best_model.pth'.format(args.model)))
 

@@ -428,6 +428,35 @@ def gen_sliding_window():
     save("sliding_window", **out)
 
 
+def gen_val_2d():
+    """utils/val_2d.py:10-41 (calculate_metric_percase, test_single_volume), sources taken verbatim from the reference file,
+    run on the shipped ACDC_10 weights; ``medpy`` (absent) is stubbed by oracle/metrics_oracle.py."""
+    import types
+    from scipy.ndimage import zoom
+    from oracle import metrics_oracle as M
+    metric = types.SimpleNamespace(binary=types.SimpleNamespace(dc=M.dc, hd95=M.hd95))
+    ns, glb = ref_shims.extract_defs(os.path.join(ref_shims.REF_CODE, "utils", "val_2d.py"), ["calculate_metric_percase", "test_single_volume"])
+    glb.update(metric=metric, zoom=zoom)
+    model = R.net_factory.BCP_net(1, 4)
+    model.load_state_dict(unpack_weights_bf16(np.load(os.path.join(HERE, "weights_acdc10_bf16.npz"))))
+    # the shipped running statistics describe real MR slices; on the synthetic scenes eval mode predicts background only.
+    # Re-estimate the BatchNorm buffers on synthetic scenes (train-mode forwards, no weight update) and ship them.
+    model.train()
+    with torch.no_grad():
+        for i in range(24):
+            model(synthetic_scene(12, (256, 256), 710 + i, n_classes=4, kind="rand")[0])
+    model.eval()
+    vol, lab = synthetic_scene(6, (200, 180), 700, n_classes=4, kind="rand")          # [6,1,200,180], [6,200,180]
+    image, label = vol[:, 0].unsqueeze(0), lab.unsqueeze(0)                             # DataLoader batch of one volume
+    res = ns.test_single_volume(image, label, model, classes=4)
+    out = dict(metrics=np.array(res, dtype=np.float64), depth=6, hw=np.array([200, 180]), seed=700)
+    for k, v in model.state_dict().items():
+        if "running_" in k or "num_batches" in k:
+            out["buf." + k] = v.numpy()
+    print("val_2d metrics", res)
+    save("val_2d", **out)
+
+
 # ------------------------------------------------------------------ fixtures on the SHIPPED checkpoints
 CKPT = {"la10": os.path.join(ref_shims.REF_ROOT, "models", "LA", "LA_10.pth"),
         "acdc10": os.path.join(ref_shims.REF_ROOT, "models", "ACDC", "ACDC_10.pth")}
@@ -642,9 +671,11 @@ def gen_dataset():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["functions", "networks", "la_small", "la_pre", "acdc", "la_full", "pan", "acdc_pre", "pan_pre", "sliding",
-                             "ckpt_weights", "la_ckpt", "acdc_ckpt", "dataset"]
+                             "ckpt_weights", "la_ckpt", "acdc_ckpt", "dataset", "val_2d"]
     if "dataset" in which:
         gen_dataset()
+    if "val_2d" in which:
+        gen_val_2d()
     if "ckpt_weights" in which:
         gen_ckpt_weights()
     if "la_ckpt" in which:

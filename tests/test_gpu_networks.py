@@ -372,3 +372,28 @@ def test_sliding_window_validation(dev):
         assert err.max() <= 3e-2                      # bf16 activations in eval mode: logits carry ~6e-3 relative noise
         sure = np.abs(score[0] - 0.5) > 5e-2
         assert np.array_equal(label[sure], g[tag + "_label"][sure].astype(np.int64))
+
+
+def test_val_2d_single_volume(dev):
+    """bcp_b200/utils/val_2d.py::test_single_volume (batched slices, device argmax) against the reference's own function run on
+    the same volume, shipped ACDC_10 weights and re-estimated BatchNorm buffers (tests/golden/val_2d.npz)."""
+    from bcp_b200.networks.net_factory import BCP_net
+    from bcp_b200.utils.val_2d import test_single_volume
+    from tests.golden.golden_common import synthetic_scene, unpack_weights_bf16
+    g = load_golden("val_2d")
+    sd = unpack_weights_bf16(load_golden("weights_acdc10_bf16"))
+    for k in g.files:
+        if k.startswith("buf."):
+            sd[k[4:]] = torch.from_numpy(g[k])
+    model = BCP_net(1, 4)
+    model.load_state_dict(sd)
+    model.eval()
+    h, w = (int(v) for v in g["hw"])
+    vol, lab = synthetic_scene(int(g["depth"]), (h, w), int(g["seed"]), n_classes=4, kind="rand")
+    res = test_single_volume(vol[:, 0].unsqueeze(0), lab.unsqueeze(0), model, classes=4)
+    ref = g["metrics"]
+    assert len(res) == 3
+    for i, (dice, hd) in enumerate(res):
+        record(f"val_2d_class{i + 1}_dice_abs_err", abs(dice - ref[i, 0]))
+        record(f"val_2d_class{i + 1}_hd95_abs_err", abs(hd - ref[i, 1]))
+        assert abs(dice - ref[i, 0]) <= 2e-3 and abs(hd - ref[i, 1]) <= 1.5, (i, dice, hd, ref[i])

@@ -439,3 +439,24 @@ def test_dataset_host_draws_match_oracle():
                 w1, h1, d1 = p["origin"]
                 assert np.array_equal(r[w1:w1 + patch[0], h1:h1 + patch[1], d1:d1 + patch[2]], g[f"b{b}_image"][j, 0])
             b += 1
+
+
+def test_metric_closed_forms():
+    """oracle/metrics_oracle.py (medpy restatement, parity unpinned) on cases with known answers, and the product's own
+    host-side metrics (bcp_b200/utils/val_2d.py) against it on random masks."""
+    from oracle import metrics_oracle as M
+    a = np.zeros((20, 20), bool)
+    b = np.zeros((20, 20), bool)
+    a[5:10, 5:10] = True
+    b[5:10, 8:13] = True                       # same square shifted by 3 columns: overlap 5x2
+    assert abs(M.dc(a, b) - 2 * 10 / 50) < 1e-12
+    assert M.dc(a, a) == 1.0 and M.dc(np.zeros(4, bool), np.zeros(4, bool)) == 0.0
+    assert abs(M.hd95(a, b) - 3.0) < 1e-9      # every border pixel is <= 3 away, the far edges exactly 3
+    assert M.hd95(a, a) == 0.0
+    from bcp_b200.utils import val_2d as V
+    rs = np.random.RandomState(0)
+    for _ in range(5):
+        p, q = rs.random_sample((12, 30, 28)) > 0.6, rs.random_sample((12, 30, 28)) > 0.5
+        assert V.dc(p, q) == M.dc(p, q) and V.hd95(p, q) == M.hd95(p, q)
+        assert V.calculate_metric_percase(p.astype(np.int64) * 3, q.astype(np.int64)) == (M.dc(p, q), M.hd95(p, q))
+    assert V.calculate_metric_percase(np.zeros((3, 3)), np.ones((3, 3))) == (0, 0)
