@@ -1528,7 +1528,7 @@ static bool wg_shape_ok(int cin, int cout, const int* dims, const int* kernel) {
   return true;
 }
 
-static bool wg_plan(WgParams& p, int nsm) {
+static bool wg_plan(WgParams& p, int nsm, int max_splits = 0) {
   p.T = p.kx * 9;
   p.TP = 512 / p.Cin;
   if (p.TP > p.T) p.TP = p.T;
@@ -1584,6 +1584,7 @@ static bool wg_plan(WgParams& p, int nsm) {
       const int nbx = (p.X + BX - 1) / BX, nby = (p.Y + BY - 1) / BY;
       const long long nb = (long long)p.N * nbx * nby;
       long long splits = nsm / npass;
+      if (max_splits > 0 && splits > max_splits) splits = max_splits;
       if (splits < 1) splits = 1;
       if (splits > nb) splits = nb;
       const long long per_cta = (nb + splits - 1) / splits;
@@ -1940,10 +1941,10 @@ int bcp_conv_tc_wgrad_supported(int cin, int cout, const int* dims, const int* k
   return get_encode() != nullptr ? 1 : 0;
 }
 
-static int wg_setup(WgParams& p, int n, int cin, int cout, const int* dims, const int* kernel) {
+static int wg_setup(WgParams& p, int n, int cin, int cout, const int* dims, const int* kernel, int max_splits = 0) {
   p = WgParams{};
   p.N = n; p.X = dims[0]; p.Y = dims[1]; p.Z = dims[2]; p.Cin = cin; p.Cout = cout; p.kx = kernel[0];
-  return wg_plan(p, sm_count()) ? 0 : -1;
+  return wg_plan(p, sm_count(), max_splits) ? 0 : -1;
 }
 
 long long bcp_conv_tc_wgrad_workspace_floats(int n, int cin, int cout, const int* dims, const int* kernel) {
@@ -1954,14 +1955,28 @@ long long bcp_conv_tc_wgrad_workspace_floats(int n, int cin, int cout, const int
 }
 
 // dw[cout][cin][T] fp32; `a` = layer input (cin channels), `dy` = output gradient (cout channels), both CB8 at `dims`
+static int conv_tc_wgrad_impl(const void* a, const void* dy, float* dw, float* workspace, int* counter, int n, int cin, int cout,
+                              const int* dims, const int* kernel, int accumulate, int max_splits, cudaStream_t stream);
+
 int bcp_conv_tc_wgrad(const void* a, const void* dy, float* dw, float* workspace, int* counter, int n, int cin, int cout,
                       const int* dims, const int* kernel, int accumulate, cudaStream_t stream) {
+  return conv_tc_wgrad_impl(a, dy, dw, workspace, counter, n, cin, cout, dims, kernel, accumulate, 0, stream);
+}
+
+// tools/debug_conv_tc.py --wgrad-splits: the same launch with the split-K factor capped (plan exploration; workspace as above)
+int bcp_conv_tc_wgrad_capped(const void* a, const void* dy, float* dw, float* workspace, int* counter, int n, int cin, int cout,
+                             const int* dims, const int* kernel, int accumulate, int max_splits, cudaStream_t stream) {
+  return conv_tc_wgrad_impl(a, dy, dw, workspace, counter, n, cin, cout, dims, kernel, accumulate, max_splits, stream);
+}
+
+static int conv_tc_wgrad_impl(const void* a, const void* dy, float* dw, float* workspace, int* counter, int n, int cin, int cout,
+                              const int* dims, const int* kernel, int accumulate, int max_splits, cudaStream_t stream) {
   BCP_REQUIRE(a && dy && dw && workspace && counter && dims && kernel, "conv_tc_wgrad: null pointer");
   if (!wg_shape_ok(cin, cout, dims, kernel)) { set_last_error("conv_tc_wgrad: unsupported shape"); return BCP_ERR_UNSUPPORTED; }
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_last_error("conv_tc_wgrad: cuTensorMapEncodeTiled unavailable"); return BCP_ERR_CUDA; }
   WgParams p{};
-  if (wg_setup(p, n, cin, cout, dims, kernel) != 0) { set_last_error("conv_tc_wgrad: no brick shape fits"); return BCP_ERR_UNSUPPORTED; }
+  if (wg_setup(p, n, cin, cout, dims, kernel, max_splits) != 0) { set_last_error("conv_tc_wgrad: no brick shape fits"); return BCP_ERR_UNSUPPORTED; }
   CUtensorMap map_a, map_dy;
   {
     const CUresult cr = encode_cb8(enc, &map_a, a, p.Z, p.Y, p.X, (long long)n * (cin / 8), p.HZ, p.HY, p.HX, cin / 8, &p.mergedA);

@@ -582,6 +582,9 @@ def maxpool3d_k3s2(a, c):
 # ----------------------------------------------------------------------------------------------
 # step primitives
 # ----------------------------------------------------------------------------------------------
+_CONST_BOXES = {}
+
+
 def box_tensor(box, device):
     """{x0,y0,z0,px,py,pz} int32 on the device.  Accepts a 6-/4-tuple (2-D boxes get z0=0,pz=1) or an int32 device tensor
     (used as is -- the captured-graph path keeps one static tensor and refreshes it before each replay)."""
@@ -591,6 +594,16 @@ def box_tensor(box, device):
     box = tuple(int(v) for v in box)
     if len(box) == 4:
         box = (box[0], box[1], 0, box[2], box[3], 1)
+    if torch.cuda.is_current_stream_capturing():
+        # a host constant inside a captured step (e.g. the all-zero box of the pre-training loss): one cached device tensor per
+        # value, fed from a pinned buffer that stays alive, so the capture records at most one memcpy node for it
+        key = (device.type, device.index, box)
+        hit = _CONST_BOXES.get(key)
+        if hit is None:
+            pinned = torch.tensor(box, dtype=torch.int32).pin_memory()
+            hit = (pinned, pinned.to(device, non_blocking=True))
+            _CONST_BOXES[key] = hit
+        return hit[1]
     return torch.tensor(box, dtype=torch.int32).to(device, non_blocking=True)
 
 

@@ -53,7 +53,7 @@ def save_resume(path, model, optimizer, ema_model=None, iteration=0, stage="", e
 def load_resume(path, model, optimizer, ema_model=None, restore_rng=True):
     """Restores everything ``save_resume`` stored; returns (iteration, stage, extra)."""
     dev = next(model.parameters()).device
-    sd = torch.load(str(path), map_location=dev, weights_only=False)
+    sd = torch.load(str(path), map_location="cpu", weights_only=False)      # RNG states must stay CPU byte tensors
     model.load_state_dict(sd["net"])
     if ema_model is not None:
         if sd.get("ema") is None:

@@ -214,6 +214,10 @@ int bcp_conv_tc_wgrad_supported(int cin, int cout, const int* dims, const int* k
 long long bcp_conv_tc_wgrad_workspace_floats(int n, int cin, int cout, const int* dims, const int* kernel);
 int bcp_conv_tc_wgrad(const void* a, const void* dy, float* dw, float* workspace, int* counter, int n, int cin, int cout,
                       const int* dims, const int* kernel, int accumulate, cudaStream_t stream);
+/* plan exploration (tools/debug_conv_tc.py): the same launch with the split-K factor capped at max_splits (0 = planner's choice) */
+int bcp_conv_tc_wgrad_capped(const void* a, const void* dy, float* dw, float* workspace, int* counter, int n, int cin, int cout,
+                      const int* dims, const int* kernel, int accumulate, int max_splits,
+                             cudaStream_t stream);
 
 /* tcgen05 stride-2 family (nn.Conv3d(k=2,s=2) networks/VNet.py:74, nn.ConvTranspose3d(k=2,s=2) networks/VNet.py:101).
  * half_dims = half-resolution grid.  mode 1 gather: in = full-res [cin], wpack kind 0, out = half-res [cout].

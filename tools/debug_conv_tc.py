@@ -223,6 +223,29 @@ if __name__ == "__main__":
             for cfg in [(4, 16, (112, 112, 80)), (4, 32, (56, 56, 40))]:
                 run_prof(*cfg, fold=ew)
         ops._TC_FOLD = False
+    if "--wgrad-splits" in sys.argv:
+        from bcp_b200._native import LIB, i3, ptr, stream
+        for n, c, dims in ((4, 64, (28, 28, 20)), (4, 128, (14, 14, 10)), (4, 256, (7, 7, 5)), (4, 32, (56, 56, 40))):
+            x = torch.randn(n, c, *dims, device=dev).to(torch.bfloat16).float()
+            a, dy = cb8_from_planar(x), cb8_from_planar(x.flip(1))
+            dw = torch.zeros(c, c, 27, device=dev)
+            ws = torch.empty(LIB.query("bcp_conv_tc_wgrad_workspace_floats", n, c, c, i3(*dims), i3(3, 3, 3)), device=dev)
+            cnt = torch.zeros(4, dtype=torch.int32, device=dev)
+            ref = None
+            for ms in (0, 1, 2, 3, 4, 6, 8, 12, 16, 24, 37):
+                args = (ptr(a), ptr(dy), ptr(dw), ptr(ws), ptr(cnt), n, c, c, i3(*dims), i3(3, 3, 3), 0, ms, stream())
+                LIB.call("bcp_conv_tc_wgrad_capped", *args)
+                torch.cuda.synchronize()
+                if ref is None:
+                    ref = dw.clone()
+                err = rel_rms(dw, ref)
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+                ev[0].record()
+                for _ in range(5):
+                    LIB.call("bcp_conv_tc_wgrad_capped", *args)
+                ev[1].record()
+                torch.cuda.synchronize()
+                print(f"[wgrad-splits] c={c} dims={dims} max_splits={ms:3d}  {ev[0].elapsed_time(ev[1]) * 200.0:7.1f} us  vs planner's result {err:.1e}", flush=True)
     if "--wgrad" in sys.argv:
         ww = 0.0
         for cfg in [(1, 16, 16, (4, 6, 8), (3, 3, 3)), (2, 16, 16, (8, 12, 20), (3, 3, 3)), (2, 32, 32, (6, 10, 12), (3, 3, 3)),
