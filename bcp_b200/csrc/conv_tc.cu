@@ -921,6 +921,14 @@ struct WgParams {
   // 132 instead of 351 tensor-pipe cycles for 16 channels, 168 instead of 360 for 32 (cost max(N/2, 32 + N/4) per MMA).
   // Accumulator dy: column (plane*3 + dx)*8 + c8.
   int dxf;
+  // per-tap compact mode (s2 == 2; small-volume layers, Cout > 32): instead of ONE halo'd a brick whose taps are address
+  // offsets -- which forces z-lines padded to 16 rows (a 7x7x5 layer runs at 31 % K efficiency), tiny bricks with 6x halo
+  // inflation and all Cin planes in every CTA -- every tap gets its OWN shifted copy of the brick, loaded by TMA at
+  // coordinates (x+dx-1, y+dy-1, z+dz-1) with out-of-bounds zero fill, in the SAME compact [BX][BY][Z] row order as the dy
+  // brick.  K then runs over the linear row index in steps of 16 (BX*BY*Z % 16 == 0, no padding inside the volume), and the
+  // input channels are split NH ways across CTAs (pass = (tap group, M half, N slice)): more passes, fewer or no split-K
+  // partials.  Deep layers are tiny, so the 27 shifted reads of a all hit L2.
+  int NH;                         // N slices (input-channel groups) across passes; 1 outside the per-tap mode
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -936,10 +944,10 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   const uint32_t fl_full = bar_base + 8 * (2 * p.S + 1) + 128, fl_empty = fl_full + 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int split = blockIdx.x, pass = blockIdx.y;
-  const int mh = pass % p.MH, tg = pass / p.MH;
+  const int nh = pass % p.NH, mh = (pass / p.NH) % p.MH, tg = pass / (p.NH * p.MH);
   const int t0 = (p.fz == 3) ? tg * p.KG : tg * p.TP;                           // first tap (folded: first (dx,dy) group)
   const int ntap = (p.fz == 3) ? min(p.KG, p.ngrp - t0) : min(p.TP, p.T - t0);  // accumulators this CTA owns
-  const int acc_cols = p.dxf ? 3 * p.Cin : p.Cin;                                // columns per accumulator
+  const int acc_cols = p.dxf ? 3 * p.Cin : p.Cin / p.NH;                         // columns per accumulator
   const int Cib = p.Cin >> 3, Cob = p.Cout >> 3;
 
   // zero the regions TMA never writes (unused dy planes, slack rows after the a planes): they feed MMAs
@@ -984,7 +992,15 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         mbar_wait(empty + 8 * s, ph ^ 1);
         const uint32_t slot = sbase + s * p.slot_bytes;
         if (elect_one()) {
-        if (p.s2) {
+        if (p.s2 == 2) {               // per-tap compact mode: shifted copies of the (Cin/NH)-channel brick
+          mbar_expect_tx(full + 8 * s, (uint32_t)ntap * p.tap_bytes + p.dy_tx_bytes);
+          const int pl0 = n * Cib + nh * (Cib / p.NH);
+          for (int tl = 0; tl < ntap; ++tl) {
+            const int t = t0 + tl;
+            const int tz = t % 3, ty = (t / 3) % 3, tx = (p.kx == 3) ? t / 9 : 1;
+            tma_load_cb8(slot + (uint32_t)tl * p.tap_bytes, &map_a, full + 8 * s, p.mergedA, tz - 1, by * p.BY + ty - 1, bx * p.BX + tx - 1, pl0);
+          }
+        } else if (p.s2) {
           mbar_expect_tx(full + 8 * s, (uint32_t)ntap * p.tap_bytes + p.dy_tx_bytes);
           for (int tl = 0; tl < ntap; ++tl) {
             const int t = t0 + tl;
@@ -1051,6 +1067,16 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           tc_fence_after();
           const uint32_t a_slot = sbase + s * p.slot_bytes, dy_slot = a_slot + p.a_alloc_bytes;
           uint32_t arow_x = a_lo0 + (dy_slot >> 4), brow_x = b_lo0 + (a_slot >> 4);
+          if (p.s2 == 2) {                                                            // compact bricks: K over the linear row index
+            for (uint32_t zc = 0; zc < (uint32_t)p.rows_dy; zc += 16) {
+              const uint64_t adesc = ((uint64_t)a_hi << 32) | (arow_x + zc);
+              const uint32_t bz = brow_x + zc;
+#pragma unroll 4
+              for (int tl = 0; tl < ntap; ++tl)
+                umma_bf16(tm + (uint32_t)tl * cin, adesc, ((uint64_t)b_hi << 32) | (bz + tapoff[tl]), idesc, acc);
+              acc = 1;
+            }
+          } else
           for (int ix = 0; ix < p.BX; ++ix) {
             uint32_t arow = arow_x, brow = brow_x;
             for (int iy = 0; iy < p.BY; ++iy) {
@@ -1189,11 +1215,11 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     } else
     for (int tl = 0; tl < ntap; ++tl) {
       const int t = (p.fz == 3) ? (t0 + tl) * 3 + dzl : t0 + tl;
-      float* dst = partial + (((size_t)split * p.T + t) * p.Cout + co) * p.Cin;
-      for (int c16 = 0; c16 < p.Cin; c16 += 16) {
+      float* dst = partial + (((size_t)split * p.T + t) * p.Cout + co) * p.Cin + nh * acc_cols;
+      for (int c16 = 0; c16 < acc_cols; c16 += 16) {
         uint32_t v[16];
         if (has_work) {
-          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tl * p.Cin + c16), v);
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tl * acc_cols + c16), v);
           tmem_ld_wait();
         } else {
 #pragma unroll
@@ -1528,7 +1554,75 @@ static bool wg_shape_ok(int cin, int cout, const int* dims, const int* kernel) {
   return true;
 }
 
+// Plan of the per-tap compact mode (WgParams::NH).  Returns the modelled cost in cycles, or a negative value.
+static double wg_plan_pertap(WgParams& p, int nsm) {
+  p.T = p.kx * 9;
+  p.MH = (p.Cout > 128) ? 2 : 1;
+  p.PL = (p.Cout / 8 < 16) ? p.Cout / 8 : 16;
+  p.MM = (p.Cout <= 64 && wg_m64_mode() >= 0) ? 64 : 128;
+  p.m64map = wg_m64_mode() < 0 ? 0 : wg_m64_mode();
+  p.ZP = p.Z; p.HX = p.HY = p.HZ = 0; p.s2 = 2;
+  p.fz = 1; p.KG = 0; p.ngrp = 0; p.dxf = 0; p.flush = 0;
+  if (p.Z > 128) return -1.0;
+  const double out_bytes = (double)p.T * p.Cout * p.Cin * 4.0;
+  double best = 1e300; bool found = false; WgParams bp = p;
+  for (int NH = 1; NH <= 4; NH *= 2) {
+    const int accc = p.Cin / NH;
+    if (accc < 32 || accc % 16) break;
+    const int tpmax = (512 / accc < p.T) ? 512 / accc : p.T;
+    const double per_mma = (accc / 2.0 > 32.0 + accc / 4.0) ? accc / 2.0 : 32.0 + accc / 4.0;
+    for (int TP = 1; TP <= tpmax; ++TP) {
+      const int npass_t = (p.T + TP - 1) / TP, npass = npass_t * p.MH * NH;
+      if (npass > nsm) continue;
+      const int bxmax = (p.kx == 1) ? 1 : p.X;
+      for (int BY = 1; BY <= p.Y && BY <= 128; ++BY) {
+        for (int BX = 1; BX <= bxmax; ++BX) {
+          const long long rows = (long long)BX * BY * p.Z;
+          if (rows >= 16384) break;
+          if (rows % 16) continue;
+          const long long tap_bytes = rows * 16 * (accc / 8), a_alloc = ((long long)TP * tap_bytes + 127) / 128 * 128;
+          const long long dy_tx = rows * 16 * p.PL, dy_alloc = (rows * 16 * (p.MM / 8) + 127) / 128 * 128;
+          const long long slot = a_alloc + dy_alloc;
+          int S = (int)((SMEM_BUDGET - 1024) / slot);
+          if (S < 2) break;
+          if (S > 4) S = 4;
+          const int nbx = (p.X + BX - 1) / BX, nby = (p.Y + BY - 1) / BY;
+          const long long nb = (long long)p.N * nbx * nby;
+          long long splits = nsm / npass; if (splits < 1) splits = 1; if (splits > nb) splits = nb;
+          const long long per_cta = (nb + splits - 1) / splits;
+          const double mma_cyc = (double)(rows / 16) * TP * per_mma;
+          const double load_cyc = (double)(TP * tap_bytes + dy_tx) / 40.0;
+          // split-K partials: written by every CTA, read back by the in-kernel finalize (through L2, ~32 B/clk per SM)
+          const double fin_cyc = 2.0 * (double)splits * out_bytes / ((double)nsm * 32.0);
+          const double cost = (double)per_cta * ((mma_cyc > load_cyc ? mma_cyc : load_cyc) + 1200.0) + fin_cyc;
+          if (cost < best) {
+            best = cost; found = true; bp = p;
+            bp.NH = NH; bp.TP = TP; bp.npass_t = npass_t;
+            bp.BX = BX; bp.BY = BY; bp.nbx = nbx; bp.nby = nby; bp.nbricks = (int)nb;
+            bp.rows_a = (int)rows; bp.rows_dy = (int)rows; bp.S = S; bp.splits = (int)splits;
+            bp.tap_bytes = (unsigned)tap_bytes; bp.a_tx_bytes = (unsigned)a_alloc; bp.a_alloc_bytes = (unsigned)a_alloc;
+            bp.dy_tx_bytes = (unsigned)dy_tx; bp.dy_alloc_bytes = (unsigned)dy_alloc; bp.slot_bytes = (unsigned)slot;
+          }
+        }
+      }
+    }
+  }
+  if (!found) return -1.0;
+  p = bp;
+  int cols = 32;
+  while (cols < p.TP * (p.Cin / p.NH)) cols *= 2;
+  p.tmem_cols = cols;
+  p.offBar = p.S * p.slot_bytes;
+  return best;
+}
+
 static bool wg_plan(WgParams& p, int nsm, int max_splits = 0) {
+  // small volumes with wide channels: the per-tap compact mode (no z padding, channel-sliced passes)
+  if (max_splits >= 0 && 3 * p.Cout > 128 && (long long)p.X * p.Y * p.Z <= 16384 && p.Cin >= 32) {
+    WgParams q = p;
+    if (wg_plan_pertap(q, nsm) > 0.0) { p = q; return true; }
+  }
+  if (max_splits < 0) max_splits = 0;
   p.T = p.kx * 9;
   p.TP = 512 / p.Cin;
   if (p.TP > p.T) p.TP = p.T;
@@ -1540,7 +1634,7 @@ static bool wg_plan(WgParams& p, int nsm, int max_splits = 0) {
   p.m64map = wg_m64_mode() < 0 ? 0 : wg_m64_mode();
   p.HZ = p.Z + 2;
   p.ZP = (p.Z + 15) / 16 * 16;
-  p.fz = 1; p.KG = 0; p.ngrp = 0; p.dxf = 0;
+  p.fz = 1; p.KG = 0; p.ngrp = 0; p.dxf = 0; p.NH = 1;
   if (3 * p.Cout <= 128 && (p.Z + 2 + 15) / 16 * 16 <= 256 && p.Cin <= 512 / 3 && (wg_m64_mode() >= 0 || 3 * p.Cout > 64)) {
     // dz-folded: K runs over the halo'd z-line (Z+2 rows, rounded up to 16); both bricks use that z extent
     p.fz = 3;
@@ -1918,7 +2012,8 @@ static int wg_launch(const CUtensorMap& map_a, const CUtensorMap& map_dy, float*
     if (attr_err != cudaSuccess) cudaGetLastError();
   });
   if (attr_err != cudaSuccess) { set_last_error("%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(attr_err)); return BCP_ERR_CUDA; }
-  const int nct = p.splits * p.npass_t * p.MH;
+  if (p.NH < 1) p.NH = 1;
+  const int nct = p.splits * p.npass_t * p.MH * p.NH;
   if (nct > sm_count()) { set_last_error("%s: grid of %d CTAs cannot be co-resident", what, nct); return BCP_ERR_UNSUPPORTED; }
   // lanes per output quad: spread the `splits` partials of an output over KS lanes when there are more threads than quads
   const long long items = (long long)p.T * p.Cout * p.Cin / 4, threads = (long long)nct * TC_THREADS;
@@ -1930,7 +2025,7 @@ static int wg_launch(const CUtensorMap& map_a, const CUtensorMap& map_dy, float*
   // launch would make the driver guarantee it, but measured ~10 us of extra launch latency per call inside a CUDA graph:
   // 28 calls per step.)  Concurrent kernels of other streams only delay the barrier, they cannot deadlock it, as long as
   // they terminate on their own.
-  dim3 grid(p.splits, p.npass_t * p.MH);
+  dim3 grid(p.splits, p.npass_t * p.MH * p.NH);
   conv_tc_wgrad_kernel<<<grid, TC_THREADS, smem, stream>>>(map_a, map_dy, workspace, dw, counter, p);
   return check_launch(what);
 }
@@ -1979,7 +2074,9 @@ static int conv_tc_wgrad_impl(const void* a, const void* dy, float* dw, float* w
   if (wg_setup(p, n, cin, cout, dims, kernel, max_splits) != 0) { set_last_error("conv_tc_wgrad: no brick shape fits"); return BCP_ERR_UNSUPPORTED; }
   CUtensorMap map_a, map_dy;
   {
-    const CUresult cr = encode_cb8(enc, &map_a, a, p.Z, p.Y, p.X, (long long)n * (cin / 8), p.HZ, p.HY, p.HX, cin / 8, &p.mergedA);
+    const CUresult cr = (p.s2 == 2)
+        ? encode_cb8(enc, &map_a, a, p.Z, p.Y, p.X, (long long)n * (cin / 8), p.Z, p.BY, p.BX, (cin / 8) / p.NH, &p.mergedA)
+        : encode_cb8(enc, &map_a, a, p.Z, p.Y, p.X, (long long)n * (cin / 8), p.HZ, p.HY, p.HX, cin / 8, &p.mergedA);
     if (cr != CUDA_SUCCESS) { set_last_error("conv_tc_wgrad: tensor map (a) failed (%d)", (int)cr); return BCP_ERR_CUDA; }
   }
   {

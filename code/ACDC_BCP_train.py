@@ -99,8 +99,10 @@ def run_stage(args, stage, model, ema_model, optimizer, snapshot_path, device, r
         state = np.random.get_state()                  # the capture warm-up draws boxes
         gs = GraphedStep(kind, model, ema_model, optimizer, (args.batch_size, 1) + tuple(args.patch_size), device=device, **kw)
         np.random.set_state(state)
-    t0, it0 = time.time(), it
-    for batch in make_loader(args, device, rank):
+    loader = make_loader(args, device, rank)
+    torch.cuda.synchronize(device)
+    t0, it0, t_io = time.time(), it, 0.0          # t_io: validation + checkpoint time, excluded from the reported step rate
+    for batch in loader:
         if it >= iters:
             break
         if gs is not None:
@@ -115,10 +117,12 @@ def run_stage(args, stage, model, ema_model, optimizer, snapshot_path, device, r
         if it % args.log_every == 0 and rank == 0:
             logging.info('iteration %d: loss: %f, mix_dice: %f, mix_ce: %f' % (it, float(r['loss']), float(r['loss_dice']), float(r['loss_ce'])))
         if args.ckpt_every and it % args.ckpt_every == 0 and rank == 0:
+            t_v = time.time()
             save_resume(resume_path, model, optimizer, ema_model, it, stage)
+            t_io += time.time() - t_v
     torch.cuda.synchronize(device)
     if rank == 0:
-        logging.info("%s: %d iterations, %.2f it/s" % (stage, it - it0, (it - it0) / max(time.time() - t0, 1e-9)))
+        logging.info("%s: %d iterations, %.2f it/s" % (stage, it - it0, (it - it0) / max(time.time() - t0 - t_io, 1e-9)))
     return it
 
 

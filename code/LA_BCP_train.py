@@ -147,8 +147,10 @@ def run_stage(args, stage, model, ema_model, optimizer, snapshot_path, device, r
         state = np.random.get_state()            # capture warm-up draws boxes: keep the stream where the reference would be
         gs = GraphedStep(kind, model, ema_model, optimizer, (args.batch_size, 1) + patch_size, device=device, **kw)
         np.random.set_state(state)
-    t0, it0 = time.time(), it
-    for batch in make_loader(args, device, rank):
+    loader = make_loader(args, device, rank)
+    torch.cuda.synchronize(device)
+    t0, it0, t_io = time.time(), it, 0.0          # t_io: validation + checkpoint time, excluded from the reported step rate
+    for batch in loader:
         if it >= iters:
             break
         if gs is not None:
@@ -163,12 +165,13 @@ def run_stage(args, stage, model, ema_model, optimizer, snapshot_path, device, r
         if it % args.log_every == 0 and rank == 0:
             names = ('loss', 'loss_dice', 'loss_ce') if kind == "la_pre" else ('loss', 'loss_l', 'loss_u')
             vals = tuple(float(r[k]) for k in names)                     # the only device sync of the loop
-            rate = (it - it0) / max(time.time() - t0, 1e-9)
+            rate = (it - it0) / max(time.time() - t0 - t_io, 1e-9)
             logging.info('iteration %d : %s: %03f, %s: %03f, %s: %03f  (%.1f it/s, %.0f patches/s)' %
                          (it, names[0], vals[0], names[1], vals[1], names[2], vals[2], rate, rate * args.labeled_bs))
         if kind == "la" and it % 2500 == 0:                                               # LA_BCP_train.py:273-276
             optimizer.param_groups[0]['lr'] = args.base_lr * 0.1 ** (it // 2500)
         if it % 200 == 0:                                                                 # LA_BCP_train.py:172-186,278-291
+            t_v = time.time()
             dice = validate(args, model)
             if dice is not None and dice > best_dice and rank == 0:
                 best_dice = round(dice, 4)
@@ -179,11 +182,14 @@ def run_stage(args, stage, model, ema_model, optimizer, snapshot_path, device, r
                     else:
                         torch.save(model.state_dict(), path)
                 logging.info("save best model to {}".format(os.path.join(snapshot_path, 'iter_{}_dice_{}.pth'.format(it, best_dice))))
+            t_io += time.time() - t_v
         if args.ckpt_every and it % args.ckpt_every == 0 and rank == 0:
+            t_v = time.time()
             save_resume(resume_path, model, optimizer, ema_model, it, stage, {"best_dice": best_dice})
+            t_io += time.time() - t_v
     torch.cuda.synchronize(device)
     if rank == 0:
-        logging.info("%s: %d iterations, %.2f it/s" % (stage, it - it0, (it - it0) / max(time.time() - t0, 1e-9)))
+        logging.info("%s: %d iterations, %.2f it/s" % (stage, it - it0, (it - it0) / max(time.time() - t0 - t_io, 1e-9)))
     return it, best_dice
 
 

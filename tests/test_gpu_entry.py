@@ -93,15 +93,15 @@ def test_resume_is_bit_identical(tmp_path, graphed):
 
 
 def test_la_entry_script_runs_graphed(tmp_path):
-    """code/LA_BCP_train.py --max_steps 30 (synthetic volumes, both stages): finishes, logs finite losses, writes the
+    """code/LA_BCP_train.py --max_steps 60 (synthetic volumes, both stages): finishes, logs finite losses, writes the
     reference's snapshot files, and its self-training rate is that of the graphed step, not of an eager Python loop
     (eager enqueue alone costs ~10 ms per step; the graphed step with the per-step H2D copy runs > 80 it/s on a B200)."""
-    cmd = [sys.executable, os.path.join(ROOT, "code", "LA_BCP_train.py"), "--max_steps", "30", "--log_every", "10", "--ckpt_every", "20"]
+    cmd = [sys.executable, os.path.join(ROOT, "code", "LA_BCP_train.py"), "--max_steps", "60", "--log_every", "20", "--ckpt_every", "40"]
     out = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     losses = [float(m.group(1)) for m in re.finditer(r"iteration \d+ : loss: ([0-9.naninf-]+)", out.stdout)]
     assert len(losses) == 6 and all(np.isfinite(losses)), out.stdout[-1500:]
-    rates = {m.group(1): float(m.group(2)) for m in re.finditer(r"(pre_train|self_train): 30 iterations, ([0-9.]+) it/s", out.stdout)}
+    rates = {m.group(1): float(m.group(2)) for m in re.finditer(r"(pre_train|self_train): 60 iterations, ([0-9.]+) it/s", out.stdout)}
     record("entry_script_self_train_it_per_s", rates.get("self_train", 0.0))
     record("entry_script_pre_train_it_per_s", rates.get("pre_train", 0.0))
     base = tmp_path / "model" / "BCP" / "LA_BCP_8_labeled"
