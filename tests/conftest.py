@@ -11,6 +11,7 @@ if ROOT not in sys.path:
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
     config.addinivalue_line("markers", "slow: full-size CPU oracle checks (tens of seconds each)")
+    config.addinivalue_line("markers", "multigpu: needs >= 2 CUDA devices and NCCL (gpurun --gpus 2 -- python -m pytest tests -m multigpu)")
 
 
 def pytest_collection_modifyitems(config, items):
@@ -19,5 +20,5 @@ def pytest_collection_modifyitems(config, items):
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:
-        if "gpu" in item.keywords:
+        if "gpu" in item.keywords or "multigpu" in item.keywords:
             item.add_marker(skip)

@@ -1,4 +1,4 @@
-"""torchrun worker of tests/test_gpu_dp.py: two data-parallel LA self-training steps per rank (NCCL), results to <out>/rank<r>.pt.
+"""torchrun worker of tests/test_multigpu_dp.py: two data-parallel LA self-training steps per rank (NCCL), results to <out>/rank<r>.pt.
 
 usage: python -m torch.distributed.run --nproc-per-node N ... tests/dp_worker.py <out_dir> <graphed 0|1> <overlap 0|1>"""
 import os

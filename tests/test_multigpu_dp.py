@@ -1,6 +1,7 @@
 """N-rank data parallelism on real GPUs over NCCL: after two steps on different per-rank
 batches the replicas' parameters, EMA-teacher parameters and momentum are bit-identical, and equal to a single-process
-emulation that sums the per-rank gradients by hand.  Needs >= 2 GPUs (``gpurun --gpus 2``); the single-GPU box skips it."""
+emulation that sums the per-rank gradients by hand.  Marker ``multigpu``: run with
+``gpurun --gpus 2 -- python -m pytest tests -m multigpu`` (log of the last run: profiles/multigpu_r02.log)."""
 import os
 import socket
 import subprocess
@@ -10,7 +11,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = pytest.mark.gpu
+pytestmark = pytest.mark.multigpu       # NOT part of -m gpu: a single-GPU box cannot run it (NCCL refuses two ranks on one device)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
