@@ -423,6 +423,124 @@ __global__ void __launch_bounds__(128) head_fwd_kernel(const uint4* __restrict__
   }
 }
 
+// ---- 1x1x1 head (the out_conv of every network here: networks/VNet.py:210, networks/unet.py:102, pancreas/Vnet.py:128): no taps, no
+// borders, input index == output index.  The generic kernels above spend most of their instructions on 64-bit index
+// decomposition; these stream: one thread per voxel, all channel octets in registers, coalesced 16-byte / 4-byte accesses.
+// HBM-bound: fwd / dgrad / wgrad each move |activation| + |logits| bytes.
+template <int NC, int CIB>
+__global__ void __launch_bounds__(256) head1_fwd_kernel(const uint4* __restrict__ in, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, float* __restrict__ out, long long S, int Cin) {
+  __shared__ float wsm[CIB * 8 * NC];
+  for (int i = threadIdx.x; i < CIB * 8 * NC; i += 256) {
+    const int k = i % NC, ci = i / NC;
+    wsm[i] = (ci < Cin) ? w[(long long)k * Cin + ci] : 0.f;
+  }
+  __syncthreads();
+  const int n = blockIdx.y;
+  const uint4* src = in + (long long)n * CIB * S;
+  float* dst = out + (long long)n * NC * S;
+  const long long stride = (long long)gridDim.x * 256;
+#pragma unroll 2
+  for (long long sp = (long long)blockIdx.x * 256 + threadIdx.x; sp < S; sp += stride) {
+    uint4 v[CIB];
+#pragma unroll
+    for (int cib = 0; cib < CIB; ++cib) v[cib] = ldg_nc_u4(src + (long long)cib * S + sp);
+    float acc[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) acc[k] = bias ? __ldg(bias + k) : 0.f;
+#pragma unroll
+    for (int cib = 0; cib < CIB; ++cib) {
+      float a[8];
+      unpack8(v[cib], a);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int k = 0; k < NC; ++k) acc[k] = fmaf(a[i], wsm[(cib * 8 + i) * NC + k], acc[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < NC; ++k) dst[(long long)k * S + sp] = acc[k];
+  }
+}
+
+template <int NC, int CIB>
+__global__ void __launch_bounds__(256) head1_dgrad_kernel(const float* __restrict__ dlog, const float* __restrict__ w,
+                                                           uint4* __restrict__ din, long long S, int Cin) {
+  __shared__ float wsm[CIB * 8 * NC];
+  for (int i = threadIdx.x; i < CIB * 8 * NC; i += 256) {
+    const int k = i % NC, ci = i / NC;
+    wsm[i] = (ci < Cin) ? w[(long long)k * Cin + ci] : 0.f;
+  }
+  __syncthreads();
+  const int n = blockIdx.y;
+  const float* src = dlog + (long long)n * NC * S;
+  uint4* dst = din + (long long)n * CIB * S;
+  const long long stride = (long long)gridDim.x * 256;
+#pragma unroll 2
+  for (long long sp = (long long)blockIdx.x * 256 + threadIdx.x; sp < S; sp += stride) {
+    float d[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) d[k] = __ldg(src + (long long)k * S + sp);
+#pragma unroll
+    for (int cib = 0; cib < CIB; ++cib) {
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) a += d[k] * wsm[(cib * 8 + i) * NC + k];     // same order as the generic kernel
+        acc[i] = a;
+      }
+      dst[(long long)cib * S + sp] = pack8(acc);
+    }
+  }
+}
+
+// partial[chunk][cib][NC*8 + NC] (the generic layout with T = 1): one pass over the voxels for ALL channel octets
+template <int NC, int CIB>
+__global__ void __launch_bounds__(128) head1_wgrad_partial_kernel(const uint4* __restrict__ in, const float* __restrict__ dlog,
+                                                                   float* __restrict__ partial, long long S, int N) {
+  constexpr int K = NC * 8 + NC;
+  const long long total = (long long)N * S;
+  const long long o0 = (long long)blockIdx.x * 4096, o1 = min(total, o0 + 4096);
+  float acc[CIB][NC * 8], accb[NC];
+#pragma unroll
+  for (int c = 0; c < CIB; ++c)
+#pragma unroll
+    for (int k = 0; k < NC * 8; ++k) acc[c][k] = 0.f;
+#pragma unroll
+  for (int k = 0; k < NC; ++k) accb[k] = 0.f;
+  for (long long o = o0 + threadIdx.x; o < o1; o += 128) {
+    const long long n = o / S, sp = o - n * S;
+    float d[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) { d[k] = __ldg(dlog + (n * NC + k) * S + sp); accb[k] += d[k]; }
+#pragma unroll
+    for (int c = 0; c < CIB; ++c) {
+      float a[8];
+      unpack8(ldg_nc_u4(in + (n * CIB + c) * S + sp), a);
+#pragma unroll
+      for (int k = 0; k < NC; ++k)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[c][k * 8 + i] += d[k] * a[i];
+    }
+  }
+  __shared__ float red[K * 4];
+#pragma unroll
+  for (int c = 0; c < CIB; ++c) {
+    float v[K];
+#pragma unroll
+    for (int k = 0; k < NC * 8; ++k) v[k] = acc[c][k];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) v[NC * 8 + k] = accb[k];
+    block_sum<K, 128>(v, red);
+    if (threadIdx.x == 0) {
+      float* dst = partial + ((long long)blockIdx.x * CIB + c) * K;
+#pragma unroll
+      for (int k = 0; k < K; ++k) dst[k] = v[k];
+    }
+  }
+}
+
 // d_in[v][ci] = sum_t sum_k dlogits[v - t + p][k] * W[k][ci][t]
 template <int NC>
 __global__ void __launch_bounds__(128) head_dgrad_kernel(const float* __restrict__ dlog, const float* __restrict__ w,
@@ -671,6 +789,17 @@ int bcp_head_fwd(const void* in, const float* w, const float* bias, float* logit
   long long blocks = (total + 127) / 128;
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
+  if (g.kx * g.ky * g.kz == 1 && (cin == 16 || cin == 8) && (ncls == 2 || ncls == 4)) {
+    const long long S = (long long)g.Xo * g.Yo * g.Zo;
+    long long bx = (S + 511) / 512;
+    const long long capx = (long long)sm_count() * 8 / n + 1;
+    if (bx > capx) bx = capx;
+    dim3 grid((unsigned)bx, (unsigned)n);
+#define H1F(NC, CIB) head1_fwd_kernel<NC, CIB><<<grid, 256, 0, stream>>>((const uint4*)in, w, bias, logits, S, cin)
+    if (ncls == 2 && cin == 16) H1F(2, 2); else if (ncls == 4 && cin == 16) H1F(4, 2); else if (ncls == 2) H1F(2, 1); else H1F(4, 1);
+#undef H1F
+    return check_launch("head_fwd");
+  }
   const size_t smem = (size_t)g.kx * g.ky * g.kz * ((cin + 7) / 8) * 8 * ncls * sizeof(float);
   BCP_REQUIRE(smem <= 48 * 1024, "head_fwd: weights do not fit shared memory");
   HEAD_DISPATCH(ncls, (head_fwd_kernel<NC><<<(unsigned)blocks, 128, smem, stream>>>((const uint4*)in, w, bias, logits, g, cin)));
@@ -686,6 +815,17 @@ int bcp_head_dgrad(const float* dlogits, const float* w, void* din, int n, int c
   long long blocks = (total + 127) / 128;
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
+  if (g.kx * g.ky * g.kz == 1 && (cin == 16 || cin == 8) && (ncls == 2 || ncls == 4)) {
+    const long long S = (long long)g.Xo * g.Yo * g.Zo;
+    long long bx = (S + 511) / 512;
+    const long long capx = (long long)sm_count() * 8 / n + 1;
+    if (bx > capx) bx = capx;
+    dim3 grid((unsigned)bx, (unsigned)n);
+#define H1D(NC, CIB) head1_dgrad_kernel<NC, CIB><<<grid, 256, 0, stream>>>(dlogits, w, (uint4*)din, S, cin)
+    if (ncls == 2 && cin == 16) H1D(2, 2); else if (ncls == 4 && cin == 16) H1D(4, 2); else if (ncls == 2) H1D(2, 1); else H1D(4, 1);
+#undef H1D
+    return check_launch("head_dgrad");
+  }
   const size_t smem = (size_t)g.kx * g.ky * g.kz * ((cin + 7) / 8) * 8 * ncls * sizeof(float);
   BCP_REQUIRE(smem <= 48 * 1024, "head_dgrad: weights do not fit shared memory");
   HEAD_DISPATCH(ncls, (head_dgrad_kernel<NC><<<(unsigned)blocks, 128, smem, stream>>>(dlogits, w, (uint4*)din, g, cin)));
@@ -704,8 +844,15 @@ int bcp_head_wgrad(const void* in, const float* dlogits, float* dw, float* db, f
   BCP_REQUIRE(head_geom(g, n, dims, kernel) == 0, "head_wgrad: bad geometry");
   const long long total = (long long)n * g.Xo * g.Yo * g.Zo;
   const int chunks = (int)((total + 4095) / 4096), T = g.kx * g.ky * g.kz, Cib = (cin + 7) / 8;
+  if (T == 1 && (cin == 16 || cin == 8) && (ncls == 2 || ncls == 4)) {
+    const long long S = (long long)g.Xo * g.Yo * g.Zo;
+#define H1W(NC, CIB) head1_wgrad_partial_kernel<NC, CIB><<<chunks, 128, 0, stream>>>((const uint4*)in, dlogits, workspace, S, n)
+    if (ncls == 2 && cin == 16) H1W(2, 2); else if (ncls == 4 && cin == 16) H1W(4, 2); else if (ncls == 2) H1W(2, 1); else H1W(4, 1);
+#undef H1W
+  } else {
   dim3 grid(chunks, Cib, T);
   HEAD_DISPATCH(ncls, (head_wgrad_partial_kernel<NC><<<grid, 128, 0, stream>>>((const uint4*)in, dlogits, workspace, g, cin)));
+  }
   const int nout = ncls * cin * T + ncls;
   HEAD_DISPATCH(ncls, (head_wgrad_finalize_kernel<NC><<<(nout * 32 + 127) / 128, 128, 0, stream>>>(workspace, dw, db, chunks, T, cin, accumulate)));
   return check_launch("head_wgrad");
