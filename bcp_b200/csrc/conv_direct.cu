@@ -331,15 +331,17 @@ __global__ void __launch_bounds__(128) conv_first_wgrad_partial_kernel(const flo
     float win[3][3];
     load_row(y0 - 1, win[0]);
     load_row(y0, win[1]);
+    load_row(y0 + 1, win[2]);
     const uint4* dyp = og + ((long long)n * Cob + cob) * So + ((long long)x * g.Yo + y0) * g.Zo + z;
+    uint4 dcur = zok ? __ldg(dyp) : make_uint4(0, 0, 0, 0);
     for (int y = y0; y < y1; ++y, dyp += g.Zo) {
-      load_row(y + 1, win[2]);
+      // software prefetch: the NEXT step's dy vector and input row are in flight during this step's 72 FMAs (the register
+      // budget allows only ~4 warps per scheduler, too few to hide an L2 round trip per step otherwise)
+      float nxt[3];
+      load_row(y + 2, nxt);
+      const uint4 dnext = (zok && y + 1 < y1) ? __ldg(dyp + g.Zo) : make_uint4(0, 0, 0, 0);
       float d[8];
-      if (zok) unpack8(__ldg(dyp), d);
-      else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) d[j] = 0.f;
-      }
+      unpack8(dcur, d);
 #pragma unroll
       for (int i = 0; i < 9; ++i) {
         const float v = win[i / 3][i % 3];
@@ -347,7 +349,8 @@ __global__ void __launch_bounds__(128) conv_first_wgrad_partial_kernel(const flo
         for (int j = 0; j < 8; ++j) acc[i][j] += v * d[j];
       }
 #pragma unroll
-      for (int k = 0; k < 3; ++k) { win[0][k] = win[1][k]; win[1][k] = win[2][k]; }
+      for (int k = 0; k < 3; ++k) { win[0][k] = win[1][k]; win[1][k] = win[2][k]; win[2][k] = nxt[k]; }
+      dcur = dnext;
     }
   }
   __shared__ float red[72 * 4];

@@ -483,8 +483,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 }
 
 // =========================================================================================================
-// EXPERIMENTAL (round-2 plan; not on the default path, enabled by BCP_TC_FOLD=1 in ops.py and not
-// yet run on a GPU): the same convolution with the three dz taps of a (dx,dy) pair folded into the MMA N dimension.
+// dz-folded forward / data-gradient kernel, the default for 16- and 32-channel layers (ops._TC_FOLD; parity:
+// tests/test_gpu_primitives.py::test_conv_tc_fold_vs_torch, tests/test_gpu_conv_shapes.py): the same convolution with the
+// three dz taps of a (dx,dy) pair folded into the MMA N dimension.
 //   B tile of a group g=(dx,dy): [W(g,dz=0) | W(g,dz=1) | W(g,dz=2)]  -> N = 3*Ns, D'[row][dz*Ns + co]
 //   A tile: 8-row core-matrix groups start every SIX rows (descriptor SBO = 96 B): tile row i is frame row
 //           96*mt + 6*(i/8) + (i%8), so an 8-lane group of the epilogue holds rows r..r+7 and produces outputs r..r+5 as
@@ -1842,7 +1843,7 @@ int bcp_conv_tc_fwd_stats(const void* in, const void* wpack, const float* bias, 
   return conv_tc_launch(in, wpack, bias, out, n, cin, cout, dims, kernel, &sa, nullptr, stream);
 }
 
-// ---- EXPERIMENTAL dz-folded forward (conv_tc_fold_kernel): brick plan + launch.  Not used unless ops.py is told to.
+// ---- dz-folded forward (conv_tc_fold_kernel): brick plan + launch
 static bool fold_shape_ok(int cin, int cout, const int* dims, const int* kernel) {
   if (!shape_ok(cin, cout, dims, kernel)) return false;
   return cout == 16 || cout == 32;                 // N = 3*Cout <= 96; wider layers are already near the tensor rate

@@ -2,7 +2,7 @@
 // test_single_case): the class-`cls` softmax probability of one window's logits is added into a score map and the visit
 // count is bumped, one launch per window in the reference's x,y,z window order (windows overlap, so accumulating them one
 // after the other keeps the sums in the reference's order and needs no atomics); a second kernel divides by the count
-// and thresholds.  EXPERIMENTAL: added after round 1's GPU budget was spent, first GPU run pending.
+// and thresholds.  Parity: tests/test_gpu_networks.py::test_sliding_window_validation (fixture minted from the reference function).
 #include "common.cuh"
 #include "../../include/bcp_b200.h"
 

@@ -187,7 +187,7 @@ int bcp_conv_tc_fwd_stats(const void* in, const void* wpack, const float* bias, 
                           const int* dims, const int* kernel, const float* gamma, const float* beta, float* running_mean,
                           float* running_var, long long* num_batches_tracked, float* stat, float* coef, void* workspace,
                           int* counter, int spg, float eps, float momentum, cudaStream_t stream);
-/* EXPERIMENTAL (first GPU run pending): sliding-window validation, reference utils/test_3d_patch.py:82-141.
+/* Sliding-window validation, reference utils/test_3d_patch.py:82-141 (parity: tests/test_gpu_networks.py::test_sliding_window_validation).
  * bcp_window_accumulate adds softmax(logits)[cls] of ONE window (logits planar fp32 [c][patch]) into score/count
  * ([vol] fp32) at `origin3`; call it window by window in the reference's x,y,z order.  bcp_window_finalize turns score into
  * the mean probability in place and writes label = (mean > threshold). */
@@ -195,8 +195,8 @@ int bcp_window_accumulate(const float* logits, float* score, float* count, int c
                           const int* origin3, cudaStream_t stream);
 int bcp_window_finalize(float* score, const float* count, unsigned char* label, long long n, float threshold, cudaStream_t stream);
 
-/* EXPERIMENTAL (not on the default path, first GPU run pending): the same convolution for Cout in {16, 32} with the three
- * dz taps folded into the MMA N dimension.  Same arguments and packs as bcp_conv_tc_fwd. */
+/* The same convolution for Cout in {16, 32} with the three dz taps folded into the MMA N dimension;
+ * the default forward / data-gradient kernel of those layers.  Same arguments and packs as bcp_conv_tc_fwd. */
 int bcp_conv_tc_fold_supported(int cin, int cout, const int* dims, const int* kernel);
 int bcp_conv_tc_fold_plan(int n, int cin, int cout, const int* dims, const int* kernel, int* plan10);
 int bcp_conv_tc_fold_fwd(const void* in, const void* wpack, const float* bias, void* out, int n, int cin, int cout,
