@@ -61,8 +61,10 @@ _COUNTERS = {}
 
 
 def _counter(device):
-    """Zero-initialised device int used by the 'last block finalises' reductions (self-resetting, stream-ordered)."""
-    key = (device.type, device.index)
+    """Zero-initialised device ints used by the 'last block finalises' reductions (self-resetting, stream-ordered).  One set
+    per (device, stream): the step bodies run the teacher's forward on a side stream next to the student's, and two kernels
+    in flight must not share an arrival counter."""
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
     c = _COUNTERS.get(key)
     if c is None:
         c = torch.zeros(16, dtype=torch.int32, device=device)

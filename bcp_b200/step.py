@@ -18,6 +18,20 @@ from . import ops
 from .utils.BCP_utils import context_box
 
 
+# teacher pass concurrent with the student's forward (see la_self_train_step); module switch for A/B measurements and tests
+TEACHER_ON_SIDE_STREAM = True
+_SIDE = {}
+
+
+def _side_stream(dev):
+    key = (dev.type, dev.index)
+    s = _SIDE.get(key)
+    if s is None:
+        s = torch.cuda.Stream(device=dev)
+        _SIDE[key] = s
+    return s
+
+
 def _acdc_box(shape):
     """ACDC_BCP_train.py:131-140: 2/3 box, origin from two np.random.randint calls (w then h)."""
     X, Y = shape[-2], shape[-1]
@@ -46,21 +60,32 @@ def la_self_train_step(model, ema_model, optimizer, volume, label, labeled_bs=4,
     lab_a, lab_b = label[:sub], label[sub:labeled_bs]
     un = volume[labeled_bs:]
     un_a, un_b = un[:sub], un[sub:]
-    with torch.no_grad():
+    # The student's INPUT needs only the images and the box; the teacher's pseudo labels enter at the loss.  So the teacher
+    # pass (forward -> pseudo labels -> largest-CC) runs on a side stream next to the student's forward: the deep layers and
+    # the small normalisation kernels of either network leave SMs idle that the other one fills.
+    dev = volume.device
+    cur = torch.cuda.current_stream(dev)
+    side = _side_stream(dev) if TEACHER_ON_SIDE_STREAM else cur
+    side.wait_stream(cur)
+    with torch.no_grad(), torch.cuda.stream(side):
         t_out, _ = ema_model(un, groups=2, with_features=False)            # ema_model(unimg_a), ema_model(unimg_b)
         plab = plab_raw = ops.pseudo_label(t_out, "thresh", 0.5)           # get_cut_mask
         if nms:
             plab = ops.largest_cc(plab)                                    # LargestCC_pancreas, 26-connectivity
-        plab_own = plab
-        if plab_override is not None:
-            plab = ops.to_u8_labels(plab_override).contiguous()
-        plab_a, plab_b = plab[:sub], plab[sub:]
+    with torch.no_grad():
         if box is None:
             box = context_box(img_a.shape, mask_ratio)
         mixed = torch.empty((2 * sub,) + tuple(volume.shape[1:]), dtype=torch.float32, device=volume.device)
         ops.mask_mix(img_a, un_a, box, out=mixed[:sub])                    # mixl_img
         ops.mask_mix(un_b, img_b, box, out=mixed[sub:])                    # mixu_img
     out, _ = model(mixed, groups=2, with_features=False)
+    cur.wait_stream(side)
+    for t in (t_out, plab, plab_raw):
+        t.record_stream(cur)
+    plab_own = plab
+    if plab_override is not None:
+        plab = ops.to_u8_labels(plab_override).contiguous()
+    plab_a, plab_b = plab[:sub], plab[sub:]
     loss_l = ops.MixLoss.apply(out[:sub], lab_a, plab_a, box, None, 0, 1.0, u_weight)[0]
     loss_u = ops.MixLoss.apply(out[sub:], plab_b, lab_b, box, None, 0, u_weight, 1.0)[0]
     loss = loss_l + loss_u
