@@ -169,6 +169,51 @@ def _conv_same_stats(a, wpack, bias, cout, kernel, req):
     return out
 
 
+# ---- weight gradients on their own stream --------------------------------------------------------------------------------
+# Within a layer's backward the weight gradient and the data gradient are independent, and nothing downstream in backward
+# needs dW: only the optimiser does.  When the gradient accumulates straight into the flat arena (``into`` is given) the
+# launch goes to ONE dedicated side stream per device and is joined when the autograd engine finishes the backward pass.
+# The tensor-core weight-gradient kernels (tensor-pipe-bound, one CTA per SM) then run next to the normalisation backward
+# kernels (HBM-bound, small shared memory, co-resident on the same SMs) and the data-gradient chain.  ONE stream, because
+# those kernels meet at an in-kernel grid barrier: two of them in flight at once could each hold SMs the other waits for.
+WGRAD_ON_SIDE_STREAM = os.environ.get("BCP_WGRAD_STREAM", "1") != "0"
+_WG_STREAMS, _WG_PENDING = {}, set()
+
+
+def _wgrad_stream(dev):
+    key = (dev.type, dev.index)
+    st = _WG_STREAMS.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=dev)
+        _WG_STREAMS[key] = st
+    return st
+
+
+def join_wgrad_stream(dev):
+    """Make the current stream wait for every weight-gradient launch issued so far (no-op when none is pending)."""
+    key = (dev.type, dev.index)
+    if key in _WG_PENDING:
+        torch.cuda.current_stream(dev).wait_stream(_WG_STREAMS[key])
+        _WG_PENDING.discard(key)
+
+
+def _wgrad_async(dev, tensors, fn):
+    if not WGRAD_ON_SIDE_STREAM:
+        return fn()
+    key = (dev.type, dev.index)
+    cur, side = torch.cuda.current_stream(dev), _wgrad_stream(dev)
+    side.wait_stream(cur)                              # the operands (dy just produced on `cur`) are ready
+    with torch.cuda.stream(side):
+        r = fn()
+    for t in tensors:
+        t.record_stream(side)                          # keep the operands alive until the side stream has consumed them
+    if key not in _WG_PENDING:
+        _WG_PENDING.add(key)
+        from torch.autograd import Variable
+        Variable._execution_engine.queue_callback(lambda: join_wgrad_stream(dev))      # end of this backward pass
+    return r
+
+
 def _wgrad(inp, outgrad, cin, cout, in_dims, kernel, stride, pad, wshape, allow_tc=True, into=None):
     """Weight gradient [cout][cin][taps].  ``into``: accumulate into this tensor (flat-arena view) and return None."""
     n = inp.shape[0]
@@ -240,8 +285,12 @@ class ConvSame(Function):
         if ctx.needs_input_grad[0]:
             da = _conv_same(dy, ctx.pack.k[1], None, cin, k)
         if ctx.needs_input_grad[1]:
-            dw = _wgrad(a, dy, cin, cout, (x, y, z), k, (1, 1, 1), (k[0] // 2, k[1] // 2, k[2] // 2), weight.shape,
-                        into=_direct(weight))
+            into = _direct(weight)
+            args = (a, dy, cin, cout, (x, y, z), k, (1, 1, 1), (k[0] // 2, k[1] // 2, k[2] // 2), weight.shape)
+            if into is not None:
+                _wgrad_async(a.device, (a, dy), lambda: _wgrad(*args, into=into))
+            else:
+                dw = _wgrad(*args)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = _bias_grad(dy, cout, ctx.bz, _direct(ctx.bias_ref))
         return da, dw, db, None, None, None, None
@@ -302,7 +351,11 @@ class ConvDown2(Function):
         if ctx.needs_input_grad[0]:
             da = _s2_fwd(dy, ctx.pack, None, cout, cin, half, 2)
         if ctx.needs_input_grad[1]:
-            dw = _s2_wgrad(a, dy, cin, cout, half, weight.shape, into=_direct(weight))
+            into = _direct(weight)
+            if into is not None:
+                _wgrad_async(a.device, (a, dy), lambda: _s2_wgrad(a, dy, cin, cout, half, weight.shape, into=into))
+            else:
+                dw = _s2_wgrad(a, dy, cin, cout, half, weight.shape)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = _bias_grad(dy, cout, ctx.bz, _direct(ctx.bias_ref))
         return da, dw, db, None, None
@@ -332,7 +385,11 @@ class ConvUp2(Function):
         if ctx.needs_input_grad[0]:
             da = _s2_fwd(dy, ctx.pack, None, cout, cin, (x, y, z), 1)
         if ctx.needs_input_grad[1]:
-            dw = _s2_wgrad(dy, a, cout, cin, (x, y, z), weight.shape, into=_direct(weight))     # half = layer input, full = dy
+            into = _direct(weight)                                                                # half = layer input, full = dy
+            if into is not None:
+                _wgrad_async(a.device, (a, dy), lambda: _s2_wgrad(dy, a, cout, cin, (x, y, z), weight.shape, into=into))
+            else:
+                dw = _s2_wgrad(dy, a, cout, cin, (x, y, z), weight.shape)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = _bias_grad(dy, cout, ctx.bz, _direct(ctx.bias_ref))
         return da, dw, db, None, None
@@ -366,13 +423,16 @@ class ConvFirst(Function):
         dy = dy.contiguous()
         dw = db = None
         if ctx.needs_input_grad[1]:
-            ws = _f32(LIB.query("bcp_conv_first_wgrad_workspace_floats", n, cout, i3(*dims), i3(*kernel)), x.device)
             into = _direct(weight)
-            dw = into if into is not None else torch.empty(weight.shape, dtype=torch.float32, device=x.device)
-            LIB.call("bcp_conv_first_wgrad", ptr(x), ptr(dy), ptr(dw), ptr(ws), n, cout, i3(*dims), i3(*kernel),
-                     1 if into is not None else 0, stream())
+
+            def run(dst, acc):
+                ws = _f32(LIB.query("bcp_conv_first_wgrad_workspace_floats", n, cout, i3(*dims), i3(*kernel)), x.device)
+                LIB.call("bcp_conv_first_wgrad", ptr(x), ptr(dy), ptr(dst), ptr(ws), n, cout, i3(*dims), i3(*kernel), acc, stream())
             if into is not None:
-                dw = None
+                _wgrad_async(x.device, (x, dy), lambda: run(into, 1))
+            else:
+                dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)
+                run(dw, 0)
         if has_bias and ctx.needs_input_grad[2]:
             db = _bias_grad(dy, cout, ctx.bz, _direct(ctx.bias_ref))
         return None, dw, db, None

@@ -83,6 +83,8 @@ class _FusedBase:
         dist, world = _world()
         if world <= 1:
             return
+        from .ops import join_wgrad_stream
+        join_wgrad_stream(self.dev)
         hi = self.rt.n_train if self._reduced_upto is None else self._reduced_upto
         lo = max(0, min(int(lo), hi))
         if lo >= hi:
@@ -96,6 +98,8 @@ class _FusedBase:
         self._reduced_upto = lo
 
     def _allreduce(self):
+        from .ops import join_wgrad_stream
+        join_wgrad_stream(self.dev)                  # weight gradients run on their own stream (ops._wgrad_async)
         dist, world = _world()
         if world > 1:
             if self._reduced_upto is None:                             # nothing in flight: one all-reduce of the whole arena

@@ -206,9 +206,12 @@ def run_native(args):
         torch.cuda.nvtx.range_pop()
         return
 
-    if os.environ.get("BENCH_SERIAL_TEACHER", "0") == "1":          # A/B switch: teacher pass on the main stream
+    if os.environ.get("BENCH_SERIAL_TEACHER", "0") == "1":          # A/B switches: teacher pass / weight gradients on the main stream
         import bcp_b200.step as _S
         _S.TEACHER_ON_SIDE_STREAM = False
+    if os.environ.get("BENCH_SERIAL_WGRAD", "0") == "1":
+        import bcp_b200.ops as _O
+        _O.WGRAD_ON_SIDE_STREAM = False
     graphed, graph_note = None, "eager launches (BENCH_NO_GRAPH=1)"
     if os.environ.get("BENCH_NO_GRAPH", "0") != "1":
         from bcp_b200.graph import GraphedStep
