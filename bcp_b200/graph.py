@@ -59,7 +59,10 @@ class GraphedStep:
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         l0 = LIB.launches
-        with torch.cuda.graph(self.graph):
+        # capture on a HIGH-priority stream: the step forks side streams (teacher pass, weight gradients) of default priority,
+        # and the chain on the capturing stream is the critical path -- its kernels should get free SMs first
+        cap = torch.cuda.Stream(device=dev, priority=-1)           # measured: 6.88 vs 6.94 ms/step at default priority
+        with torch.cuda.graph(self.graph, stream=cap):
             self.out = self._body()
         self.kernels_per_replay = LIB.launches - l0
         self._restore(snap)
@@ -147,7 +150,7 @@ class GraphedStep:
         cs = self._copy_stream
         with torch.cuda.stream(cs):
             sv.copy_(volume, non_blocking=True)
-            sl.copy_(label, non_blocking=True)
+            sl.copy_(label[:sl.shape[0]], non_blocking=True)       # pancreas: labels of the labeled half only
             ev = torch.cuda.Event()
             ev.record(cs)
         self._stage_ev[w] = ev

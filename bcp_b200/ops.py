@@ -469,15 +469,20 @@ class Head(Function):
             da = torch.empty_like(a)
             LIB.call("bcp_head_dgrad", ptr(dlog), ptr(w), ptr(da), n, cin, ncls, i3(*dims), i3(*kernel), stream())
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
-            ws = _f32(LIB.query("bcp_head_wgrad_workspace_floats", n, cin, ncls, i3(*dims), i3(*kernel)), a.device)
             iw, ib = _direct(weight), _direct(ctx.bias_ref)
             direct = iw is not None and (ib is not None or not has_bias)
             dw = iw if direct else torch.empty(weight.shape, dtype=torch.float32, device=a.device)
             db = (ib if direct else torch.empty(ncls, dtype=torch.float32, device=a.device)) if has_bias else None
-            LIB.call("bcp_head_wgrad", ptr(a), ptr(dlog), ptr(dw), ptr(db), ptr(ws), n, cin, ncls, i3(*dims), i3(*kernel),
-                     1 if direct else 0, stream())
+
+            def run():
+                ws = _f32(LIB.query("bcp_head_wgrad_workspace_floats", n, cin, ncls, i3(*dims), i3(*kernel)), a.device)
+                LIB.call("bcp_head_wgrad", ptr(a), ptr(dlog), ptr(dw), ptr(db), ptr(ws), n, cin, ncls, i3(*dims), i3(*kernel),
+                         1 if direct else 0, stream())
             if direct:
+                _wgrad_async(a.device, (a, dlog), run)
                 dw = db = None
+            else:
+                run()
         return da, dw, db, None
 
 

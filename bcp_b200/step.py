@@ -32,6 +32,30 @@ def _side_stream(dev):
     return s
 
 
+class _TeacherPass:
+    """``with _TeacherPass(dev) as tp:`` runs its body on the side stream (forked from the current one); ``tp.join(*tensors)``
+    makes the current stream wait for it and hands the tensors over."""
+
+    def __init__(self, dev):
+        self.dev = dev
+        self.cur = torch.cuda.current_stream(dev)
+        self.side = _side_stream(dev) if TEACHER_ON_SIDE_STREAM else self.cur
+
+    def __enter__(self):
+        self.side.wait_stream(self.cur)
+        self._ctx = torch.cuda.stream(self.side)
+        self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        return self._ctx.__exit__(*exc)
+
+    def join(self, *tensors):
+        self.cur.wait_stream(self.side)
+        for t in tensors:
+            t.record_stream(self.cur)
+
+
 def _acdc_box(shape):
     """ACDC_BCP_train.py:131-140: 2/3 box, origin from two np.random.randint calls (w then h)."""
     X, Y = shape[-2], shape[-1]
@@ -63,11 +87,7 @@ def la_self_train_step(model, ema_model, optimizer, volume, label, labeled_bs=4,
     # The student's INPUT needs only the images and the box; the teacher's pseudo labels enter at the loss.  So the teacher
     # pass (forward -> pseudo labels -> largest-CC) runs on a side stream next to the student's forward: the deep layers and
     # the small normalisation kernels of either network leave SMs idle that the other one fills.
-    dev = volume.device
-    cur = torch.cuda.current_stream(dev)
-    side = _side_stream(dev) if TEACHER_ON_SIDE_STREAM else cur
-    side.wait_stream(cur)
-    with torch.no_grad(), torch.cuda.stream(side):
+    with torch.no_grad(), _TeacherPass(volume.device) as tp:
         t_out, _ = ema_model(un, groups=2, with_features=False)            # ema_model(unimg_a), ema_model(unimg_b)
         plab = plab_raw = ops.pseudo_label(t_out, "thresh", 0.5)           # get_cut_mask
         if nms:
@@ -79,9 +99,7 @@ def la_self_train_step(model, ema_model, optimizer, volume, label, labeled_bs=4,
         ops.mask_mix(img_a, un_a, box, out=mixed[:sub])                    # mixl_img
         ops.mask_mix(un_b, img_b, box, out=mixed[sub:])                    # mixu_img
     out, _ = model(mixed, groups=2, with_features=False)
-    cur.wait_stream(side)
-    for t in (t_out, plab, plab_raw):
-        t.record_stream(cur)
+    tp.join(t_out, plab, plab_raw)
     plab_own = plab
     if plab_override is not None:
         plab = ops.to_u8_labels(plab_override).contiguous()
@@ -147,21 +165,23 @@ def acdc_self_train_step(model, ema_model, optimizer, volume, label, labeled_bs=
     un = volume[labeled_bs:]
     uimg_a, uimg_b = un[:us], un[us:]
     lab_a, lab_b = label[:ls], label[ls:labeled_bs]
-    with torch.no_grad():
+    with torch.no_grad(), _TeacherPass(volume.device) as tp:              # teacher pass next to the student's forward
         pre = ema_model(un, groups=2)
         plab = plab_raw = ops.pseudo_label(pre, "argmax")
         if nms:
             plab = ops.largest_cc(plab)                                    # per-class 8-connected largest component
-        plab_own = plab
-        if plab_override is not None:
-            plab = ops.to_u8_labels(plab_override).contiguous()
-        plab_a, plab_b = plab[:us], plab[us:]
+    with torch.no_grad():
         if box is None:
             box = _acdc_box(img_a.shape)
         mixed = torch.empty((ls + us,) + tuple(volume.shape[1:]), dtype=torch.float32, device=volume.device)
         ops.mask_mix(uimg_a, img_a, box, out=mixed[:us])                   # net_input_unl
         ops.mask_mix(img_b, uimg_b, box, out=mixed[us:])                   # net_input_l
     out = model(mixed, groups=2)
+    tp.join(pre, plab, plab_raw)
+    plab_own = plab
+    if plab_override is not None:
+        plab = ops.to_u8_labels(plab_override).contiguous()
+    plab_a, plab_b = plab[:us], plab[us:]
     r_unl = ops.MixLoss.apply(out[:us], plab_a, lab_a, box, None, 1, u_weight, 1.0)     # unlab=True
     r_l = ops.MixLoss.apply(out[us:], lab_b, plab_b, box, None, 1, 1.0, u_weight)
     loss_dice, loss_ce = r_unl[1] + r_l[1], r_unl[2] + r_l[2]
@@ -195,20 +215,22 @@ def pan_self_train_step(net, ema_net, optimizer, img_a, lab_a, img_b, lab_b, uni
                         connect_mode=2, box=None, plab_override=None):
     lab_a, lab_b = ops.to_u8_labels(lab_a), ops.to_u8_labels(lab_b)
     n = img_a.shape[0]
-    with torch.no_grad():
+    with torch.no_grad(), _TeacherPass(img_a.device) as tp:               # teacher pass next to the student's forward
         un = torch.cat([unimg_a, unimg_b])
         t_out = ema_net(un)[0]
         plab = ops.largest_cc(ops.pseudo_label(t_out, "thresh", 0.5), connectivity=connect_mode)
-        plab_own = plab
-        if plab_override is not None:
-            plab = ops.to_u8_labels(plab_override).contiguous()
-        plab_a, plab_b = plab[:n], plab[n:]
+    with torch.no_grad():
         if box is None:
             box = _pan_box(patch_size)
         mixed = torch.empty((2 * n,) + tuple(img_a.shape[1:]), dtype=torch.float32, device=img_a.device)
         ops.mask_mix(unimg_a, img_b, box, out=mixed[:n])                   # net3_input_l
         ops.mask_mix(img_a, unimg_b, box, out=mixed[n:])                   # net3_input_unlab
     out = net(mixed)[0]
+    tp.join(t_out, plab)
+    plab_own = plab
+    if plab_override is not None:
+        plab = ops.to_u8_labels(plab_override).contiguous()
+    plab_a, plab_b = plab[:n], plab[n:]
     loss_1 = ops.MixLoss.apply(out[:n], plab_a, lab_b, box, None, 0, 0.5, 1.0)[0]       # unlab=True, u_weight default .5
     loss_2 = ops.MixLoss.apply(out[n:], lab_a, plab_b, box, None, 0, 1.0, 0.5)[0]
     loss = loss_1 + loss_2
