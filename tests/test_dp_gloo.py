@@ -56,6 +56,7 @@ def _worker(rank, world, port, q):
         fb = _FusedBase.__new__(_FusedBase)
         fb.rt = _RT()
         fb.rt.grad_arena = flat.clone()
+        fb.dev = flat.device             # no weight-gradient side stream pending on the CPU
         fb._reduced_upto = None          # no bucket in flight: the whole arena goes in one collective
         w = fb._allreduce()
         q.put((rank, w, fb.rt.grad_arena.numpy().copy(), loss))
