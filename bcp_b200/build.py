@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbcp_b200.so")
-SOURCES = ["api.cu", "elementwise.cu", "norm.cu", "norm_fused.cu", "loss.cu", "conv_direct.cu", "conv_tc.cu", "pool.cu", "cc.cu", "window.cu", "augment.cu"]
+SOURCES = ["api.cu", "elementwise.cu", "norm.cu", "norm_fused.cu", "loss.cu", "conv_direct.cu", "conv_first_tma.cu", "conv_tc.cu", "pool.cu", "cc.cu", "window.cu", "augment.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]

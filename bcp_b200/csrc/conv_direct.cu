@@ -662,6 +662,14 @@ static int make_geom(Geom& g, int n, const int* in_dims, const int* kernel, cons
   return 0;
 }
 
+// conv_first_tma.cu: TMA-staged first-layer kernels.  launch: > 0 = launched (weight gradient: number of per-CTA partials),
+// 0 = shape not eligible -> the register-window kernels above, < 0 = error
+int first_wgrad_tma_chunks(int n, int cout, const int* dims, const int* kernel);
+int first_wgrad_tma_launch(const float* in, const void* outgrad, float* partial, int n, int cout, const int* dims,
+                           const int* kernel, cudaStream_t stream);
+int first_fwd_tma_launch(const float* in, const float* w, const float* bias, void* out, int n, int cout, const int* dims,
+                         const int* kernel, cudaStream_t stream);
+
 }  // namespace bcp
 
 using namespace bcp;
@@ -735,6 +743,11 @@ int bcp_conv_first_fwd(const float* in, const float* w, const float* bias, void*
   Geom g;
   BCP_REQUIRE(make_geom(g, n, dims, kernel, stride, pad, 0) == 0, "conv_first_fwd: bad geometry");
   BCP_REQUIRE((g.kx == 3 || g.kx == 1) && g.ky == 3 && g.kz == 3, "conv_first_fwd: kernel must be 3x3x3 or 1x3x3");
+  {
+    const int rc = first_fwd_tma_launch(in, w, bias, out, n, cout, dims, kernel, stream);
+    if (rc < 0) return rc;
+    if (rc == 1) return check_launch("conv_first_fwd");
+  }
   const int Cob = (cout + 7) / 8;
   const long long total = (long long)n * g.Xo * g.Yo * ((g.Zo + FIRST_ZR - 1) / FIRST_ZR);
   long long blocks = (total + 127) / 128;
@@ -749,8 +762,15 @@ int bcp_conv_first_fwd(const float* in, const float* w, const float* bias, void*
 }
 
 long long bcp_conv_first_wgrad_workspace_floats(int n, int cout, const int* dims, const int* kernel) {
-  const long long chunks = (long long)n * ((dims[2] + 31) / 32) * ((dims[0] + FIRST_WG_XC - 1) / FIRST_WG_XC);
+  long long chunks = (long long)n * ((dims[2] + 31) / 32) * ((dims[0] + FIRST_WG_XC - 1) / FIRST_WG_XC);
+  const long long tma = first_wgrad_tma_chunks(n, cout, dims, kernel);
+  if (tma > chunks) chunks = tma;
   return chunks * ((cout + 7) / 8) * kernel[0] * 72;
+}
+
+int bcp_conv_first_wgrad_tma_chunks(int n, int cout, const int* dims, const int* kernel) {
+  if (!dims || !kernel || kernel[1] != 3 || kernel[2] != 3 || (kernel[0] != 1 && kernel[0] != 3)) return 0;
+  return first_wgrad_tma_chunks(n, cout, dims, kernel);
 }
 
 int bcp_conv_first_wgrad(const float* in, const void* outgrad, float* dw, float* workspace, int n, int cout,
@@ -762,10 +782,14 @@ int bcp_conv_first_wgrad(const float* in, const void* outgrad, float* dw, float*
   BCP_REQUIRE(make_geom(g, n, dims, kernel, stride, pad, 0) == 0, "conv_first_wgrad: bad geometry");
   BCP_REQUIRE(g.ky == 3 && g.kz == 3 && (g.kx == 1 || g.kx == 3), "conv_first_wgrad: kernel must be 3x3x3 or 1x3x3");
   const int Cob = (cout + 7) / 8;
-  const int per_n = ((g.Zo + 31) / 32) * ((g.Xo + FIRST_WG_XC - 1) / FIRST_WG_XC);
-  const int chunks = per_n * n;
-  dim3 grid(per_n, n, Cob * g.kx);
-  conv_first_wgrad_partial_kernel<<<grid, 128, 0, stream>>>(in, (const uint4*)outgrad, workspace, g, cout);
+  int chunks = first_wgrad_tma_launch(in, outgrad, workspace, n, cout, dims, kernel, stream);
+  if (chunks < 0) return chunks;
+  if (chunks == 0) {
+    const int per_n = ((g.Zo + 31) / 32) * ((g.Xo + FIRST_WG_XC - 1) / FIRST_WG_XC);
+    chunks = per_n * n;
+    dim3 grid(per_n, n, Cob * g.kx);
+    conv_first_wgrad_partial_kernel<<<grid, 128, 0, stream>>>(in, (const uint4*)outgrad, workspace, g, cout);
+  }
   const int T = g.kx * g.ky * g.kz;
   conv_first_wgrad_finalize_kernel<<<(cout * T * 32 + 127) / 128, 128, 0, stream>>>(workspace, dw, chunks, cout, g.kx, g.ky, g.kz, accumulate);
   return check_launch("conv_first_wgrad");

@@ -161,6 +161,9 @@ int bcp_chan_sum(const void* x, float* out, float* workspace, int n, int c, long
 int bcp_conv_first_fwd(const float* in, const float* w, const float* bias, void* out, int n, int cout,
                        const int* dims, const int* kernel, cudaStream_t stream);
 long long bcp_conv_first_wgrad_workspace_floats(int n, int cout, const int* dims, const int* kernel);
+/* > 0 (the number of per-CTA partials) when bcp_conv_first_wgrad takes the TMA-staged kernel (conv_first_tma.cu) for this
+ * shape, 0 when it uses the register-window kernel (Z % 4 != 0, more than two channel octets, no tensor-map encoder). */
+int bcp_conv_first_wgrad_tma_chunks(int n, int cout, const int* dims, const int* kernel);
 int bcp_conv_first_wgrad(const float* in, const void* outgrad, float* dw, float* workspace, int n, int cout,
                          const int* dims, const int* kernel, int accumulate, cudaStream_t stream);
 int bcp_head_fwd(const void* in, const float* w, const float* bias, float* logits, int n, int cin, int ncls,

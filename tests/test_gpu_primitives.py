@@ -446,6 +446,34 @@ def test_conv_first_and_head(ops, dev):
         assert rel_rms(ga, ar.grad) <= 6e-3 and rel_rms(w.grad, wr.grad) <= 1e-4 and rel_rms(b.grad, br.grad) <= 1e-4
 
 
+@pytest.mark.parametrize("shape,kernel", [((2, 1, 10, 12, 16), (3, 3, 3)),      # one z tile, merged dy map, ragged last y tile
+                                          ((1, 1, 5, 9, 132), (3, 3, 3)),       # z run > 128: un-merged 5-D dy map
+                                          ((3, 1, 24, 260), (3, 3)),            # 2-D, three z tiles, ragged last one
+                                          ((2, 1, 40, 16), (3, 3))])            # 2-D, Cob*kx = 2 -> six splits per octet
+def test_conv_first_wgrad_tma_path(ops, dev, shape, kernel):
+    """The TMA-staged first-layer weight gradient (csrc/conv_first_tma.cu) on shapes that exercise its tiling: box loads
+    with out-of-bounds zero fill on every side, several z tiles, both dy tensor-map forms (autograd's dW of
+    networks/VNet.py:151 block_one / networks/unet.py:72 in_conv)."""
+    from bcp_b200._native import LIB, i3
+    torch.manual_seed(31)
+    two_d = len(shape) == 4
+    dims = (1,) + tuple(shape[2:]) if two_d else tuple(shape[2:])
+    k3 = (1,) + tuple(kernel) if two_d else tuple(kernel)
+    assert LIB.query("bcp_conv_first_wgrad_tma_chunks", shape[0], 16, i3(*dims), i3(*k3)) > 0
+    x = torch.randn(*shape, device=dev)
+    w = (torch.randn(16, 1, *kernel, device=dev) / 4).requires_grad_(True)
+    y = ops.ConvFirst.apply(x, w, None)
+    wr = w.detach().clone().requires_grad_(True)
+    yr = F.conv2d(x, wr, padding=1) if two_d else F.conv3d(x, wr, padding=1)
+    g = torch.randn_like(yr).to(torch.bfloat16).float()
+    yr.backward(g)
+    g5 = g.unsqueeze(2) if two_d else g
+    y.backward(cb8_from_planar(g5))
+    err = rel_rms(w.grad, wr.grad)
+    record("first_wgrad_tma_%s" % "x".join(map(str, shape)), err)
+    assert err <= 1e-5, err
+
+
 def test_pool_and_upsample(ops, dev):
     torch.manual_seed(13)
     x = torch.randn(2, 16, 12, 20, device=dev).to(torch.bfloat16).float()

@@ -1,0 +1,4 @@
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_primitives.py tests/test_gpu_conv_shapes.py -k "first" -q --timeout 300 > gpurun_out/first_pytest.log 2>&1; tail -8 gpurun_out/first_pytest.log | cut -c1-300
+timeout 120 python tools/time_first.py 2>&1 | tail -4
+timeout 300 python bench.py --steps 30 --warmup 5 --no-baselines 2>&1 | tail -1 | cut -c1-330
