@@ -29,6 +29,24 @@ constexpr int FW_NW = 12;                         // consumer warps
 constexpr int FW_THREADS = 32 * (FW_NW + 1);      // + the producer warp
 constexpr unsigned FW_SMEM_BUDGET = 200 * 1024;
 
+
+// (n, x, y tile, z tile) of a slab index, advanced by the grid stride with carries instead of three divisions per slab
+struct SlabPos {
+  int zt, yt, x, n;
+  __device__ __forceinline__ void set(int slab, int nzt, int nyt, int X) {
+    zt = slab % nzt; slab /= nzt;
+    yt = slab % nyt; slab /= nyt;
+    x = slab % X;
+    n = slab / X;
+  }
+  __device__ __forceinline__ void advance(const SlabPos& d, int nzt, int nyt, int X) {
+    zt += d.zt; if (zt >= nzt) { zt -= nzt; ++yt; }
+    yt += d.yt; if (yt >= nyt) { yt -= nyt; ++x; }
+    x += d.x;   if (x >= X) { x -= X; ++n; }
+    n += d.n;
+  }
+};
+
 struct FirstWgParams {
   int N, X, Y, Z, kx, Cob;
   int YR, ZT, ZP;            // slab rows / columns, padded window row length (floats)
@@ -45,7 +63,8 @@ __global__ void __launch_bounds__(FW_THREADS, 1)
 conv_first_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
                             float* __restrict__ partial, const FirstWgParams p) {
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  // aligned by pointer arithmetic on the __shared__ symbol (an integer round trip would turn every access into a generic load)
+  unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   __shared__ __align__(8) unsigned long long bars[16];
   __shared__ float red[FW_NW * 72];
   const uint32_t sbase = smem_u32(smem);
@@ -58,23 +77,20 @@ conv_first_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_dy) : "memory");
   }
   __syncthreads();
-  const int per_n = p.X * p.nyt * p.nzt;
 
   if (warp == FW_NW) {
     // ---------------------------------------------------------------- producer: two box loads per slab
     Ring r;
-    for (int slab = blockIdx.x; slab < p.nslabs; slab += gridDim.x) {
-      const int n = slab / per_n;
-      int q = slab - n * per_n;
-      const int zt = q % p.nzt; q /= p.nzt;
-      const int yt = q % p.nyt;
-      const int x = q / p.nyt;
+    SlabPos sp, step;
+    sp.set(blockIdx.x, p.nzt, p.nyt, p.X);
+    step.set(gridDim.x, p.nzt, p.nyt, p.X);
+    for (int slab = blockIdx.x; slab < p.nslabs; slab += gridDim.x, sp.advance(step, p.nzt, p.nyt, p.X)) {
       mbar_wait(empty + 8 * r.s, r.ph ^ 1);
       if (elect_one()) {
         const uint32_t dst = sbase + r.s * p.stage_bytes;
         mbar_expect_tx(full + 8 * r.s, p.x_box_bytes + p.dy_bytes);
-        tma_load_4d(dst, &tmap_x, full + 8 * r.s, zt * p.ZT - FIRST_ZLEAD, yt * p.YR - 1, x - (p.kx >> 1), n);
-        tma_load_cb8(dst + p.x_bytes, &tmap_dy, full + 8 * r.s, p.merged, zt * p.ZT, yt * p.YR, x, n * p.Cob);
+        tma_load_4d(dst, &tmap_x, full + 8 * r.s, sp.zt * p.ZT - FIRST_ZLEAD, sp.yt * p.YR - 1, sp.x - (p.kx >> 1), sp.n);
+        tma_load_cb8(dst + p.x_bytes, &tmap_dy, full + 8 * r.s, p.merged, sp.zt * p.ZT, sp.yt * p.YR, sp.x, sp.n * p.Cob);
       }
       __syncwarp();
       r.advance(p.NSTG);
@@ -245,7 +261,8 @@ __global__ void __launch_bounds__(FF_THREADS, 1)
 conv_first_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ w, const float* __restrict__ bias,
                           uint4* __restrict__ out, const FirstFwdParams p) {
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  // aligned by pointer arithmetic on the __shared__ symbol (an integer round trip would turn every access into a generic load)
+  unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   __shared__ __align__(8) unsigned long long bars[16];
   __shared__ __align__(16) float wsm[27 * 16 + 16];          // [T][16 co], then the bias
   const uint32_t sbase = smem_u32(smem);
@@ -263,20 +280,17 @@ conv_first_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const floa
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
   }
   __syncthreads();
-  const int per_n = p.X * p.nyt * p.nzt;
 
   if (warp == FF_NW) {
     Ring r;
-    for (int slab = blockIdx.x; slab < p.nslabs; slab += gridDim.x) {
-      const int n = slab / per_n;
-      int q = slab - n * per_n;
-      const int zt = q % p.nzt; q /= p.nzt;
-      const int yt = q % p.nyt;
-      const int x = q / p.nyt;
+    SlabPos sp, step;
+    sp.set(blockIdx.x, p.nzt, p.nyt, p.X);
+    step.set(gridDim.x, p.nzt, p.nyt, p.X);
+    for (int slab = blockIdx.x; slab < p.nslabs; slab += gridDim.x, sp.advance(step, p.nzt, p.nyt, p.X)) {
       mbar_wait(empty + 8 * r.s, r.ph ^ 1);
       if (elect_one()) {
         mbar_expect_tx(full + 8 * r.s, p.box_bytes);
-        tma_load_4d(sbase + r.s * p.stage_bytes, &tmap_x, full + 8 * r.s, zt * p.ZT - FIRST_ZLEAD, yt * p.YR - 1, x - (p.kx >> 1), n);
+        tma_load_4d(sbase + r.s * p.stage_bytes, &tmap_x, full + 8 * r.s, sp.zt * p.ZT - FIRST_ZLEAD, sp.yt * p.YR - 1, sp.x - (p.kx >> 1), sp.n);
       }
       __syncwarp();
       r.advance(p.NSTG);
@@ -289,14 +303,13 @@ conv_first_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const floa
     const long long S = (long long)p.X * p.Y * p.Z;
     const int ZP = p.ZP, rows = p.YR + 2;
     Ring r;
-    for (int slab = blockIdx.x; slab < p.nslabs; slab += gridDim.x) {
-      const int n = slab / per_n;
-      int q = slab - n * per_n;
-      const int zt = q % p.nzt; q /= p.nzt;
-      const int yt = q % p.nyt;
-      const int x = q / p.nyt;
+    SlabPos sp, step;
+    sp.set(blockIdx.x, p.nzt, p.nyt, p.X);
+    step.set(gridDim.x, p.nzt, p.nyt, p.X);
+    for (int slab = blockIdx.x; slab < p.nslabs; slab += gridDim.x, sp.advance(step, p.nzt, p.nyt, p.X)) {
+      const int n = sp.n, x = sp.x;
       mbar_wait(full + 8 * r.s, r.ph);
-      const int y = yt * p.YR + yy, z = zt * p.ZT + zz;
+      const int y = sp.yt * p.YR + yy, z = sp.zt * p.ZT + zz;
       if (active && y < p.Y && z < p.Z) {
         const float* xs = reinterpret_cast<const float*>(smem + (size_t)r.s * p.stage_bytes) + yy * ZP + zz;
         float acc[FF_ZR][16];
