@@ -753,6 +753,36 @@ conv_tc_s2_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16*
         const int iy = ry % p.BY, ix = ry / p.BY;
         const int x = bx * p.BX + ix, y = by * p.BY + iy, z = bz * p.BZ + iz;
         const bool valid = (L < p.rows) && (x < p.Xh) && (y < p.Yh) && (z < p.Zh);
+        if (p.mode == 2 && (p.TPc & 1) == 0) {
+          // scatter, tap pairs: taps t (even) and t + 1 differ only in dz, so their outputs are the z-neighbours 2z and
+          // 2z + 1 -- ONE 32-byte store per channel octet.  Consecutive lanes are consecutive half-resolution z, so a warp
+          // writes 1 KB contiguous per instruction; per-tap 16-byte stores at a 32-byte stride half-filled every sector
+          // twice (82 us for the 128 MB full-resolution output of the 32 -> 16 up-convolution).
+          for (int tp = 0; tp < p.TPc; tp += 2) {
+            const int t = piece * p.TPc + tp;
+            const int ox = 2 * x + (t >> 2), oy = 2 * y + ((t >> 1) & 1);
+            uint4* dst_t = out + (long long)n * Cob * So + ((long long)ox * Yo + oy) * Zo + 2 * z;
+            for (int cg = 0; cg < p.Cout; cg += 16) {
+              uint32_t v0[16], v1[16];
+              tmem_ld16(d0 + (uint32_t)(mt * p.Npiece + tp * p.Cout + cg), v0);
+              tmem_ld16(d0 + (uint32_t)(mt * p.Npiece + (tp + 1) * p.Cout + cg), v1);
+              tmem_ld_wait();
+              if (valid) {
+                float f0[16], f1[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                  const float b = bias ? __ldg(bias + cg + k) : 0.f;
+                  f0[k] = __uint_as_float(v0[k]) + b;
+                  f1[k] = __uint_as_float(v1[k]) + b;
+                }
+                uint4* dst = dst_t + (long long)(cg >> 3) * So;
+                stg256(dst, pack8(f0), pack8(f1));
+                stg256(dst + So, pack8(f0 + 8), pack8(f1 + 8));
+              }
+            }
+          }
+          continue;
+        }
         for (int c16 = 0; c16 < p.Npiece; c16 += 16) {
           uint32_t v[16];
           tmem_ld16(d0 + (uint32_t)(mt * p.Npiece + c16), v);

@@ -113,4 +113,11 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
          (1ull << 46);
 }
 
+// one 32-byte store (st.global.v8.b32, sm_100): `p` must be 32-byte aligned
+__device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
 }  // namespace bcp
