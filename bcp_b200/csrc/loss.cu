@@ -48,25 +48,23 @@ __global__ void __launch_bounds__(LT) mix_loss_fwd_kernel(const float* __restric
   constexpr int K = 2 * C * 3 + 4;
   const BoxArgs box = load_box(box_dev, X, Y, Z);
   const int n = blockIdx.y, blocks = gridDim.x;
-  const long long per = (V + blocks - 1) / blocks;
-  const long long v0 = (long long)blockIdx.x * per, v1 = min(V, v0 + per);
+  const bool vec4 = (Z % 4 == 0) && ((((uintptr_t)logits | (uintptr_t)lab_img | (uintptr_t)lab_patch | (uintptr_t)mask) & 15) == 0);
+  long long per = (V + blocks - 1) / blocks;
+  if (vec4) per = (per + 3) & ~3ll;
+  const long long v0 = min(V, (long long)blockIdx.x * per), v1 = min(V, v0 + per);
   const float* lg = logits + (long long)n * C * V;
   float acc[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) acc[k] = 0.f;
-#pragma unroll 2
-  for (long long v = v0 + threadIdx.x; v < v1; v += LT) {
-    float x[C];
+  auto voxel = [&](const float (&x)[C], int s, int t) {
     float m = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < C; ++c) { x[c] = lg[(long long)c * V + v]; m = fmaxf(m, x[c]); }
+    for (int c = 0; c < C; ++c) m = fmaxf(m, x[c]);
     float p[C];
     float sum = 0.f;
 #pragma unroll
     for (int c = 0; c < C; ++c) { p[c] = expf(x[c] - m); sum += p[c]; }
     const float inv = 1.f / sum, lse = m + logf(sum);
-    const int s = mask ? (mask[(long long)n * V + v] ? 0 : 1) : in_box(v, box);
-    const int t = s ? lab_patch[(long long)n * V + v] : lab_img[(long long)n * V + v];
     float ce = 0.f;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
@@ -85,6 +83,47 @@ __global__ void __launch_bounds__(LT) mix_loss_fwd_kernel(const float* __restric
     acc[2 * C * 3 + 1] += (float)s * ce;
     acc[2 * C * 3 + 2] += 1.f - (float)s;      // voxel counts per set (exact in fp32 up to 2^24 per thread)
     acc[2 * C * 3 + 3] += (float)s;
+  };
+  if (vec4) {
+    // four consecutive z per thread (Z % 4 == 0: a run never leaves its row): 16-byte logit loads, 4-byte label loads,
+    // one (x, y) decomposition per run -- four times the bytes in flight per thread of the scalar loop
+    for (long long v = v0 + 4 * threadIdx.x; v < v1; v += 4 * LT) {
+      float4 xv[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) xv[c] = *reinterpret_cast<const float4*>(lg + (long long)c * V + v);
+      const uchar4 li = *reinterpret_cast<const uchar4*>(lab_img + (long long)n * V + v);
+      const uchar4 lp = *reinterpret_cast<const uchar4*>(lab_patch + (long long)n * V + v);
+      int s4[4];
+      if (mask) {
+        const uchar4 mk = *reinterpret_cast<const uchar4*>(mask + (long long)n * V + v);
+        s4[0] = mk.x ? 0 : 1; s4[1] = mk.y ? 0 : 1; s4[2] = mk.z ? 0 : 1; s4[3] = mk.w ? 0 : 1;
+      } else {
+        const int z = (int)(v % box.Z);
+        const long long r = v / box.Z;
+        const int y = (int)(r % box.Y), xx = (int)(r / box.Y);
+        const int xy = (xx >= box.x0) & (xx < box.x1) & (y >= box.y0) & (y < box.y1);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s4[k] = xy & (z + k >= box.z0) & (z + k < box.z1);
+      }
+      const int ti[4] = {li.x, li.y, li.z, li.w}, tp[4] = {lp.x, lp.y, lp.z, lp.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float x[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) x[c] = reinterpret_cast<const float*>(&xv[c])[k];
+        voxel(x, s4[k], s4[k] ? tp[k] : ti[k]);
+      }
+    }
+  } else {
+#pragma unroll 2
+    for (long long v = v0 + threadIdx.x; v < v1; v += LT) {
+      float x[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) x[c] = lg[(long long)c * V + v];
+      const int s = mask ? (mask[(long long)n * V + v] ? 0 : 1) : in_box(v, box);
+      const int t = s ? lab_patch[(long long)n * V + v] : lab_img[(long long)n * V + v];
+      voxel(x, s, t);
+    }
   }
   __shared__ float red[K * (LT / 32)];
   block_sum<K, LT>(acc, red);
@@ -204,19 +243,15 @@ __global__ void __launch_bounds__(LT) mix_loss_bwd_kernel(const float* __restric
   const long long total = (long long)N * V;
   const long long stride = (long long)gridDim.x * LT;
   const float* tab = ctx + 6;
-  for (long long i = (long long)blockIdx.x * LT + threadIdx.x; i < total; i += stride) {
-    const long long n = i / V, v = i - n * V;
-    const float* lg = logits + n * C * V + v;
-    float x[C], p[C], g[C];
+  auto voxel = [&](const float (&x)[C], long long n, int s, int t, float (&d)[C]) {
+    float p[C], g[C];
     float m = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < C; ++c) { x[c] = lg[(long long)c * V]; m = fmaxf(m, x[c]); }
+    for (int c = 0; c < C; ++c) m = fmaxf(m, x[c]);
     float sum = 0.f;
 #pragma unroll
     for (int c = 0; c < C; ++c) { p[c] = expf(x[c] - m); sum += p[c]; }
     const float inv = 1.f / sum;
-    const int s = mask ? (mask[n * V + v] ? 0 : 1) : in_box(v, box);
-    const int t = s ? lab_patch[n * V + v] : lab_img[n * V + v];
     const float cec = gc * ctx[4 + s];
     const float* tb = tab + ((n * 2 + s) * C) * 3;
     float dot = 0.f;
@@ -230,8 +265,58 @@ __global__ void __launch_bounds__(LT) mix_loss_bwd_kernel(const float* __restric
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       const float oh = (t == c) ? 1.f : 0.f;
-      dlogits[n * C * V + (long long)c * V + v] = p[c] * (g[c] - dot) + cec * (p[c] - oh);
+      d[c] = p[c] * (g[c] - dot) + cec * (p[c] - oh);
     }
+  };
+  const bool vec4 = (Z % 4 == 0) &&
+                    ((((uintptr_t)logits | (uintptr_t)dlogits | (uintptr_t)lab_img | (uintptr_t)lab_patch | (uintptr_t)mask) & 15) == 0);
+  if (vec4) {
+    for (long long i = 4 * ((long long)blockIdx.x * LT + threadIdx.x); i < total; i += 4 * stride) {
+      const long long n = i / V, v = i - n * V;
+      const float* lg = logits + n * C * V + v;
+      float4 xv[C], dv[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) xv[c] = *reinterpret_cast<const float4*>(lg + (long long)c * V);
+      const uchar4 li = *reinterpret_cast<const uchar4*>(lab_img + n * V + v);
+      const uchar4 lp = *reinterpret_cast<const uchar4*>(lab_patch + n * V + v);
+      int s4[4];
+      if (mask) {
+        const uchar4 mk = *reinterpret_cast<const uchar4*>(mask + n * V + v);
+        s4[0] = mk.x ? 0 : 1; s4[1] = mk.y ? 0 : 1; s4[2] = mk.z ? 0 : 1; s4[3] = mk.w ? 0 : 1;
+      } else {
+        const int z = (int)(v % box.Z);
+        const long long r = v / box.Z;
+        const int y = (int)(r % box.Y), xx = (int)(r / box.Y);
+        const int xy = (xx >= box.x0) & (xx < box.x1) & (y >= box.y0) & (y < box.y1);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s4[k] = xy & (z + k >= box.z0) & (z + k < box.z1);
+      }
+      const int ti[4] = {li.x, li.y, li.z, li.w}, tp[4] = {lp.x, lp.y, lp.z, lp.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float x[C], d[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) x[c] = reinterpret_cast<const float*>(&xv[c])[k];
+        voxel(x, n, s4[k], s4[k] ? tp[k] : ti[k], d);
+#pragma unroll
+        for (int c = 0; c < C; ++c) reinterpret_cast<float*>(&dv[c])[k] = d[c];
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) *reinterpret_cast<float4*>(dlogits + n * C * V + (long long)c * V + v) = dv[c];
+    }
+    return;
+  }
+  for (long long i = (long long)blockIdx.x * LT + threadIdx.x; i < total; i += stride) {
+    const long long n = i / V, v = i - n * V;
+    const float* lg = logits + n * C * V + v;
+    float x[C], d[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) x[c] = lg[(long long)c * V];
+    const int s = mask ? (mask[n * V + v] ? 0 : 1) : in_box(v, box);
+    const int t = s ? lab_patch[n * V + v] : lab_img[n * V + v];
+    voxel(x, n, s, t, d);
+#pragma unroll
+    for (int c = 0; c < C; ++c) dlogits[n * C * V + (long long)c * V + v] = d[c];
   }
 }
 
