@@ -32,7 +32,14 @@ def _norm_bwd_kernels(args):
     return 2 if (stats_grad or args[8] or args[9]) else 1
 
 
+def _tc_wgrad_kernels(args):
+    """bcp_conv_tc_wgrad launches one kernel per z-window (z-lines longer than a TMA box: 254 columns)."""
+    z = int(args[8][2])
+    return 1 if z + 2 <= 256 else (z + 127) // 128
+
+
 KERNELS_PER_CALL = {
+    "bcp_conv_tc_wgrad": _tc_wgrad_kernels,
     "bcp_norm_stats": 1, "bcp_norm_bwd": _norm_bwd_kernels, "bcp_mix_loss_fwd": 2, "bcp_conv_direct_wgrad": 2,
     "bcp_chan_sum": 2, "bcp_dice_prob_fwd": 2, "bcp_conv_first_wgrad": 2, "bcp_head_wgrad": 2, "bcp_largest_cc": 5,
 }

@@ -834,6 +834,7 @@ struct WgParams {
   int T, TP, npass_t, MH, PL;     // taps, taps per pass, tap passes, M halves, dy planes loaded per brick
   int S, splits, tmem_cols;
   int s2;                         // 1: stride-2 family (B bricks are per-tap strided gathers of the full-res tensor)
+  int zoff;                       // z-tiled launch (z-lines longer than a TMA box): first column of this launch's window
   int MM, m64map;                 // MMA M (128 or 64) and the TMEM row->lane map assumed for M = 64
   unsigned a_tx_bytes, dy_tx_bytes, a_alloc_bytes, dy_alloc_bytes, slot_bytes, offBar, tap_bytes;
   int mergedA, mergedD;
@@ -943,7 +944,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           }
         } else {
           mbar_expect_tx(full + 8 * s, p.a_tx_bytes + p.dy_tx_bytes);
-          tma_load_cb8(slot, &map_a, full + 8 * s, p.mergedA, -1, by * p.BY - 1, bx * p.BX - (p.kx >> 1), n * Cib);
+          tma_load_cb8(slot, &map_a, full + 8 * s, p.mergedA, p.zoff - 1, by * p.BY - 1, bx * p.BX - (p.kx >> 1), n * Cib);
         }
         if (p.fz == 3) {
           const uint32_t copy_bytes = (uint32_t)Cob * (uint32_t)p.rows_dy * 16u;
@@ -1294,19 +1295,22 @@ EncodeTiledFn tma_encoder() { return get_encode(); }
 // depends on (a 16-byte inner box caps a SM's TMA at roughly 8-10 B/clk -- measured on the c64..c256 layers).
 // Out-of-bounds z (the conv padding) still zero-fills because z*2 stays the coordinate of its own dimension.
 CUresult encode_cb8(EncodeTiledFn enc, CUtensorMap* map, const void* base, long long Z, long long Y, long long X,
-                           long long planes, int bz, int by, int bx, int bp, int* merged) {
+                    long long planes, int bz, int by, int bx, int bp, int* merged, long long Zpitch) {
+  // Zpitch != 0: `base` points at a z-window of a wider tensor -- Z is the window's extent (out-of-bounds beyond it),
+  // Zpitch the real row length the strides follow (z-tiled weight gradient)
   const int want = (bz <= 128) ? 1 : 0;
   *merged = want;
+  const long long ZS = Zpitch ? Zpitch : Z;
   if (want) {
     const cuuint64_t gdim[4] = {(cuuint64_t)(2 * Z), (cuuint64_t)Y, (cuuint64_t)X, (cuuint64_t)planes};
-    const cuuint64_t gstr[3] = {(cuuint64_t)Z * 16, (cuuint64_t)Z * Y * 16, (cuuint64_t)Z * Y * X * 16};
+    const cuuint64_t gstr[3] = {(cuuint64_t)ZS * 16, (cuuint64_t)ZS * Y * 16, (cuuint64_t)ZS * Y * X * 16};
     const cuuint32_t box[4] = {(cuuint32_t)(2 * bz), (cuuint32_t)by, (cuuint32_t)bx, (cuuint32_t)bp};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
   const cuuint64_t gdim[5] = {8, (cuuint64_t)Z, (cuuint64_t)Y, (cuuint64_t)X, (cuuint64_t)planes};
-  const cuuint64_t gstr[4] = {16, (cuuint64_t)Z * 16, (cuuint64_t)Z * Y * 16, (cuuint64_t)Z * Y * X * 16};
+  const cuuint64_t gstr[4] = {16, (cuuint64_t)ZS * 16, (cuuint64_t)ZS * Y * 16, (cuuint64_t)ZS * Y * X * 16};
   const cuuint32_t box[5] = {8, (cuuint32_t)bz, (cuuint32_t)by, (cuuint32_t)bx, (cuuint32_t)bp};
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -1480,9 +1484,18 @@ static bool s2_plan(S2Params& p) {
 // (tests/test_gpu_primitives.py::test_conv_production_shapes); the kernel keeps the other two conventions for reference.
 static constexpr int wg_m64_mode() { return 0; }
 
+// A z-line (+halo) must fit a TMA box of 256 rows.  Longer lines (the 256-wide ACDC slices) are cut into windows of at most
+// 128 columns, one launch per window: the dy map is based at the window (nothing outside it contributes), the `a` map keeps
+// the whole line and the kernel shifts its z coordinate by WgParams::zoff, so the halo columns are the real neighbours;
+// launches after the first accumulate into dw.
+static int wg_ztiles(int Z) { return (Z + 2 <= 256) ? 1 : (Z + 127) / 128; }
+static int wg_tile_width(int Z) {
+  const int nt = wg_ztiles(Z);
+  return nt == 1 ? Z : ((Z + nt - 1) / nt + 15) / 16 * 16;
+}
 static bool wg_shape_ok(int cin, int cout, const int* dims, const int* kernel) {
   if (!shape_ok(cin, cout, dims, kernel)) return false;
-  if (dims[2] + 2 > 256) return false;                 // one z-line (+halo) must fit a TMA box
+  if (wg_tile_width(dims[2]) + 2 > 256) return false;
   return true;
 }
 
@@ -1970,8 +1983,10 @@ int bcp_conv_tc_wgrad_supported(int cin, int cout, const int* dims, const int* k
 
 static int wg_setup(WgParams& p, int n, int cin, int cout, const int* dims, const int* kernel, int max_splits = 0) {
   p = WgParams{};
-  p.N = n; p.X = dims[0]; p.Y = dims[1]; p.Z = dims[2]; p.Cin = cin; p.Cout = cout; p.kx = kernel[0];
-  return wg_plan(p, sm_count(), max_splits) ? 0 : -1;
+  p.N = n; p.X = dims[0]; p.Y = dims[1]; p.Z = wg_tile_width(dims[2]); p.Cin = cin; p.Cout = cout; p.kx = kernel[0];
+  if (!wg_plan(p, sm_count(), max_splits)) return -1;
+  if (wg_ztiles(dims[2]) > 1 && p.s2 != 0) return -1;          // windows exist for the halo-brick path only
+  return 0;
 }
 
 long long bcp_conv_tc_wgrad_workspace_floats(int n, int cin, int cout, const int* dims, const int* kernel) {
@@ -2005,18 +2020,25 @@ static int conv_tc_wgrad_impl(const void* a, const void* dy, float* dw, float* w
   WgParams p{};
   if (wg_setup(p, n, cin, cout, dims, kernel, max_splits) != 0) { set_last_error("conv_tc_wgrad: no brick shape fits"); return BCP_ERR_UNSUPPORTED; }
   CUtensorMap map_a, map_dy;
+  const int Zfull = dims[2], nt = wg_ztiles(Zfull), tw = p.Z;
   {
     const CUresult cr = (p.s2 == 2)
-        ? encode_cb8(enc, &map_a, a, p.Z, p.Y, p.X, (long long)n * (cin / 8), p.Z, p.BY, p.BX, (cin / 8) / p.NH, &p.mergedA)
-        : encode_cb8(enc, &map_a, a, p.Z, p.Y, p.X, (long long)n * (cin / 8), p.HZ, p.HY, p.HX, cin / 8, &p.mergedA);
+        ? encode_cb8(enc, &map_a, a, Zfull, p.Y, p.X, (long long)n * (cin / 8), p.Z, p.BY, p.BX, (cin / 8) / p.NH, &p.mergedA)
+        : encode_cb8(enc, &map_a, a, Zfull, p.Y, p.X, (long long)n * (cin / 8), p.HZ, p.HY, p.HX, cin / 8, &p.mergedA);
     if (cr != CUDA_SUCCESS) { set_last_error("conv_tc_wgrad: tensor map (a) failed (%d)", (int)cr); return BCP_ERR_CUDA; }
   }
-  {
-    const CUresult cr = encode_cb8(enc, &map_dy, dy, p.Z, p.Y, p.X, (long long)n * (cout / 8), p.ZP, p.BY, p.BX, p.PL, &p.mergedD);
+  for (int t = 0; t < nt; ++t) {
+    const int zoff = t * tw;
+    const int ext = (Zfull - zoff < tw) ? Zfull - zoff : tw;
+    const CUresult cr = encode_cb8(enc, &map_dy, (const char*)dy + (size_t)zoff * 16, ext, p.Y, p.X, (long long)n * (cout / 8), p.ZP, p.BY,
+                                   p.BX, p.PL, &p.mergedD, Zfull);
     if (cr != CUDA_SUCCESS) { set_last_error("conv_tc_wgrad: tensor map (dy) failed (%d)", (int)cr); return BCP_ERR_CUDA; }
+    p.zoff = zoff;
+    p.accumulate = (t == 0) ? accumulate : 1;
+    const int rc = wg_launch(map_a, map_dy, workspace, dw, counter, p, stream, "conv_tc_wgrad");
+    if (rc != 0) return rc;
   }
-  p.accumulate = accumulate;
-  return wg_launch(map_a, map_dy, workspace, dw, counter, p, stream, "conv_tc_wgrad");
+  return BCP_OK;
 }
 
 // ---- stride-2 family.  half_dims = dims of the half-resolution grid (full = 2x).  mode 1 (gather): `in` is full-res with

@@ -13,7 +13,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn tma_encoder();
 // tensor map over a CB8 tensor [planes][X][Y][Z][8] bf16 for a box of (bp planes, bx, by, bz voxels); defined in conv_tc.cu
 CUresult encode_cb8(EncodeTiledFn enc, CUtensorMap* map, const void* base, long long Z, long long Y, long long X,
-                    long long planes, int bz, int by, int bx, int bp, int* merged);
+                    long long planes, int bz, int by, int bx, int bp, int* merged, long long Zpitch = 0);
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -380,6 +380,33 @@ def test_conv_same_direct(ops, dev, cin, cout, dims, kernel):
                 dict(x=planar_from_cb8(xcb.grad, cin), w=w.grad, b=b.grad), dict(x=xr.grad, w=wr.grad, b=br.grad))
 
 
+@pytest.mark.parametrize("cin,cout,dims,kernel", [(16, 16, (1, 12, 260), (1, 3, 3)),       # three windows of 96 columns, ragged last one
+                                                  (32, 16, (1, 6, 256), (1, 3, 3)),        # the ACDC full-resolution decoder layer
+                                                  (16, 32, (3, 5, 272), (3, 3, 3))])       # 3-D, dx-folded plan per window
+def test_conv_wgrad_z_windows(ops, dev, cin, cout, dims, kernel):
+    """tcgen05 weight gradient on z-lines longer than a TMA box (> 254 columns): one launch per window of <= 128 columns,
+    dy map based at the window, `a` map shifted by WgParams::zoff so the halo columns are the real neighbours
+    (csrc/conv_tc.cu conv_tc_wgrad_impl; autograd's dW of networks/unet.py:20,24 at 256 x 256)."""
+    from bcp_b200._native import LIB, i3
+    assert LIB.query("bcp_conv_tc_wgrad_supported", cin, cout, i3(*dims), i3(*kernel)) == 1
+    torch.manual_seed(cin + cout + dims[2])
+    n = 2
+    x = torch.randn(n, cin, *dims, device=dev).to(torch.bfloat16).float()
+    g = torch.randn(n, cout, *dims, device=dev).to(torch.bfloat16).float()
+    w = torch.zeros(cout, cin, *kernel, device=dev, requires_grad=True)
+    pad = tuple(k // 2 for k in kernel)
+    F.conv3d(x, w, None, padding=pad).backward(g)
+    a, dy = cb8_from_planar(x), cb8_from_planar(g)
+    d_t = ops._wgrad(a, dy, cin, cout, dims, kernel, (1, 1, 1), pad, w.shape, allow_tc=True)
+    d_d = ops._wgrad(a, dy, cin, cout, dims, kernel, (1, 1, 1), pad, w.shape, allow_tc=False)
+    # accumulate mode: a second call adds the same gradient again
+    acc = d_t.clone()
+    ops._wgrad(a, dy, cin, cout, dims, kernel, (1, 1, 1), pad, w.shape, allow_tc=True, into=acc)
+    e_t, e_d, e_a = rel_rms(d_t, w.grad), rel_rms(d_d, w.grad), rel_rms(acc, 2 * w.grad)
+    record("wgrad_zwin_%d_%d_%s" % (cin, cout, "x".join(map(str, dims))), e_t)
+    assert e_t <= 1e-4 and e_d <= 1e-4 and e_a <= 1e-4, (e_t, e_d, e_a)
+
+
 def test_conv_stride2_family(ops, dev):
     torch.manual_seed(11)
     n, cin, cout = 2, 16, 32
