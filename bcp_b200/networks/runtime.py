@@ -95,6 +95,20 @@ class NetRuntime:
         self.n_param = self.n_train + sum(t.numel() for _, t in other)
         self.n_total = total
         self.int_buffers = [b for _, b in ints]
+        # the int64 buffers (BatchNorm num_batches_tracked) as views of ONE flat buffer: the state_dict EMA of the ACDC entry
+        # point (optim._after) is then one launch instead of one per normalisation layer
+        self.int_arena = None
+        if ints:
+            ia = torch.empty(sum(b.numel() for _, b in ints), dtype=torch.int64, device=dev)
+            ioff = 0
+            with torch.no_grad():
+                for _, b in ints:
+                    n = b.numel()
+                    view = ia[ioff:ioff + n].view(b.shape)
+                    view.copy_(b.data)
+                    b.data = view
+                    ioff += n
+            self.int_arena = ia
         self.grad_arena = None
         self._build_packs()
         self.dirty = True

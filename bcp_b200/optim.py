@@ -118,8 +118,12 @@ class _FusedBase:
     def _after(self):
         if self.ert is not None and self.ema_mode == "state_dict":
             a = self.ema_alpha
-            for e, m in zip(self.ert.int_buffers, self.rt.int_buffers):
-                LIB.call("bcp_ema_i64", ptr(e), ptr(m), e.numel(), a, 1.0 - a, stream())
+            ea, ma = getattr(self.ert, "int_arena", None), getattr(self.rt, "int_arena", None)
+            if ea is not None and ma is not None and ea.numel() == ma.numel():
+                LIB.call("bcp_ema_i64", ptr(ea), ptr(ma), ea.numel(), a, 1.0 - a, stream())      # all counters, one launch
+            else:
+                for e, m in zip(self.ert.int_buffers, self.rt.int_buffers):
+                    LIB.call("bcp_ema_i64", ptr(e), ptr(m), e.numel(), a, 1.0 - a, stream())
         self.rt.dirty = True
         if self.ert is not None:
             self.ert.dirty = True

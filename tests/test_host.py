@@ -106,7 +106,11 @@ def test_launch_count_rules():
     assert _norm_bwd_kernels(base + [4, 256, 245, 2, 0.0, 1, 0, 0]) == 1          # tiny layer: reduce+apply in one launch
     assert _norm_bwd_kernels(base + [4, 16, 1003520, 2, 0.0, 1, 0, 0]) == 2        # reduce pass + apply pass
     assert _norm_bwd_kernels([0] * 8 + [None, None] + [0, 0, 0] + [4, 16, 1003520, 2, 0.0, 0, 0, 0]) == 1   # no statistics gradient
-    assert KERNELS_PER_CALL["bcp_largest_cc"] == 5 and "bcp_conv_tc_wgrad" not in KERNELS_PER_CALL   # wgrad finalises in-kernel
+    assert KERNELS_PER_CALL["bcp_largest_cc"] == 5
+    import ctypes
+    wg = KERNELS_PER_CALL["bcp_conv_tc_wgrad"]          # finalises in-kernel: one launch per z-window (<= 254 columns: one)
+    args = lambda z: [0] * 8 + [(ctypes.c_int * 3)(1, 256, z)]
+    assert wg(args(80)) == 1 and wg(args(254)) == 1 and wg(args(256)) == 2 and wg(args(260)) == 3
 
 
 def test_box_draw_order_matches_reference():
