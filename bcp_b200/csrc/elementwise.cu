@@ -323,38 +323,21 @@ __global__ void ema_i64_kernel(long long* __restrict__ e, const long long* __res
 //   kind 3: [A/8][T][B][8]  inner = A index            -- stride-2 "scatter" operand of the tcgen05 kernel
 // Channel counts that are not multiples of 8 are zero-padded in the blocked dimension.
 // ------------------------------------------------------------------------------------------
-constexpr int REPACK_MAX_JOBS = 1024;
 __global__ void __launch_bounds__(128) repack_kernel(const float* __restrict__ arena, __nv_bfloat16* __restrict__ packed,
                                                      const bcp_repack_job* __restrict__ jobs, int njobs) {
   // One 8(a) x 8(b) x T tile of the PyTorch-layout weight [A][B][T] per iteration: read as eight contiguous runs of
   // 8*T floats, staged in shared memory, written as T runs of 64 bf16 (128 bytes) -- both sides coalesced.
   //   kind 0: dst [T][ceil(B/8)][A][8]  (inner = b)          kind 3: dst [ceil(A/8)][T][B][8]  (inner = a)
   //   kind 1/2: dst [T][ceil(A/8)][B][8] (inner = a), kind 1 flips the taps
-  // Work = the 8x8xT tiles of ALL jobs in one flat list (a 256x256x27 layer has 1024 tiles, a 16x16x27 layer four): every
-  // block builds the per-job tile prefix once and then strides the flat list, so the blocks stay busy whatever the mix of
-  // layer sizes (one block row per job left the six largest layers to 256 blocks each while most blocks exited at once).
   __shared__ float tile[64 * 27];
-  __shared__ int prefix[REPACK_MAX_JOBS + 1];
-  for (int i = threadIdx.x; i < njobs; i += 128) prefix[i + 1] = ((jobs[i].dim_a + 7) / 8) * ((jobs[i].dim_b + 7) / 8);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int acc = 0;
-    prefix[0] = 0;
-    for (int i = 1; i <= njobs; ++i) { acc += prefix[i]; prefix[i] = acc; }
-  }
-  __syncthreads();
-  const int total = prefix[njobs];
-  int j = 0;
-  for (int g = blockIdx.x; g < total; g += gridDim.x) {
-    while (g >= prefix[j + 1]) ++j;                     // g only grows: the job cursor never moves back
+  for (int j = blockIdx.y; j < njobs; j += gridDim.y) {
     const bcp_repack_job job = jobs[j];
     const float* src = arena + job.src_off;
     __nv_bfloat16* dst = packed + job.dst_off;
     const int A = job.dim_a, B = job.dim_b, T = job.taps;
     const int Ab = (A + 7) / 8, Bb = (B + 7) / 8;
     const int n64 = 64 * T;
-    {
-      const int tl = g - prefix[j];
+    for (int tl = blockIdx.x; tl < Ab * Bb; tl += gridDim.x) {
       const int ab = tl / Bb, bb = tl - ab * Bb;
       __syncthreads();
       for (int i = threadIdx.x; i < n64; i += 128) {
@@ -522,8 +505,10 @@ int bcp_ema_i64(long long* ema, const long long* model, int n, float alpha, floa
 int bcp_weights_repack(const float* arena, void* packed, const bcp_repack_job* jobs_dev, int njobs,
                        cudaStream_t stream) {
   BCP_REQUIRE(arena && packed && jobs_dev && njobs > 0, "weights_repack: bad args");
-  BCP_REQUIRE(njobs <= REPACK_MAX_JOBS, "weights_repack: more than %d jobs", REPACK_MAX_JOBS);
-  repack_kernel<<<sm_count() * 8, 128, 0, stream>>>(arena, (__nv_bfloat16*)packed, jobs_dev, njobs);
+  // x covers the 8x8 tiles of the largest layers (256x256 -> 1024 tiles) in a few iterations; blocks beyond a small
+  // layer's tile count exit at once
+  dim3 grid(256, njobs < 512 ? njobs : 512);
+  repack_kernel<<<grid, 128, 0, stream>>>(arena, (__nv_bfloat16*)packed, jobs_dev, njobs);
   return check_launch("weights_repack");
 }
 

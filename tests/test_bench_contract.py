@@ -52,14 +52,15 @@ def test_committed_traffic_profile_matches_its_launch_list():
     """profiles/conv_traffic.json (read by bench.py for roofline.traffic) is what tools/traffic_from_ncu.py derives from
     the committed ncu launch list of the same round."""
     tp = os.path.join(ROOT, "profiles", "conv_traffic.json")
-    csvp = os.path.join(ROOT, "profiles", "launches_r01g.csv")
+    csvp = os.path.join(ROOT, "profiles", "launches_r02_final.csv")
     if not (os.path.exists(tp) and os.path.exists(csvp)):
         pytest.skip("profile artefacts not committed yet")
     out = os.path.join(ROOT, "gpurun_out", "_traffic_check.json")
     os.makedirs(os.path.dirname(out), exist_ok=True)
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "traffic_from_ncu.py"), csvp, out], capture_output=True, text=True)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "traffic_from_ncu.py"), csvp, out, "conv_tc_kernel", "conv_tc_fold_kernel",
+                        "conv_tc_wgrad_kernel"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     a, b = json.load(open(tp)), json.load(open(out))
-    for k in ("conv_tc_kernel", "conv_tc_wgrad_kernel"):
+    for k in ("conv_tc_kernel", "conv_tc_fold_kernel", "conv_tc_wgrad_kernel"):
         assert a[k]["launches"] == b[k]["launches"]
         assert abs(a[k]["dram_bytes_per_launch"] - b[k]["dram_bytes_per_launch"]) <= 1e-6 * b[k]["dram_bytes_per_launch"]
