@@ -125,3 +125,34 @@ def test_box_draw_order_matches_reference():
     assert b2 == O.generate_mask_acdc(torch.zeros(6, 1, 256, 256), np.random.RandomState(7))[2]
     np.random.seed(9)
     assert _pan_box(64) == O.generate_mask_pan(torch.zeros(2, 1, 96, 96, 96), 64, np.random.RandomState(9))[2]
+
+
+def test_z_window_weight_gradient_decomposition():
+    """The identity the z-windowed tcgen05 weight gradient (csrc/conv_tc.cu conv_tc_wgrad_impl) rests on: with the output
+    gradient cut into windows of <= 128 columns and the layer input read with its REAL neighbour columns as halo (zero only
+    outside the tensor), the per-window weight gradients sum to the full one.  Window width = the C planner's rule."""
+    import torch.nn.functional as F
+
+    def tile_width(Z):                                   # wg_ztiles / wg_tile_width
+        nt = 1 if Z + 2 <= 256 else (Z + 127) // 128
+        return Z if nt == 1 else ((Z + nt - 1) // nt + 15) // 16 * 16, nt
+
+    assert tile_width(80) == (80, 1) and tile_width(254) == (254, 1) and tile_width(256) == (128, 2) and tile_width(260) == (96, 3)
+    torch.manual_seed(4)
+    for dims, kernel in (((1, 6, 260), (1, 3, 3)), ((3, 4, 272), (3, 3, 3))):
+        cin, cout, Z = 3, 2, dims[2]
+        pad = tuple(k // 2 for k in kernel)
+        a = torch.randn(2, cin, *dims, dtype=torch.float64)
+        g = torch.randn(2, cout, *dims, dtype=torch.float64)
+        w = torch.zeros(cout, cin, *kernel, dtype=torch.float64, requires_grad=True)
+        F.conv3d(a, w, None, padding=pad).backward(g)
+        tw, nt = tile_width(Z)
+        total = torch.zeros_like(w)
+        for t in range(nt):
+            z0, z1 = t * tw, min(Z, (t + 1) * tw)
+            lo, hi = max(z0 - 1, 0), min(z1 + 1, Z)
+            aw = F.pad(a[..., lo:hi], (1 if z0 == 0 else 0, 1 if z1 == Z else 0))       # zero halo only at the tensor's edges
+            ww = torch.zeros_like(w).requires_grad_(True)
+            F.conv3d(aw, ww, None, padding=(pad[0], pad[1], 0)).backward(g[..., z0:z1].contiguous())
+            total += ww.grad
+        assert torch.allclose(total, w.grad, rtol=1e-12, atol=1e-12)
