@@ -161,3 +161,154 @@ class TwoStreamLoader:
 
     def __len__(self):
         return len(self.sampler)
+
+
+# ======================================================================================================================
+# ACDC (2-D) input pipeline: ``BaseDataSets`` (dataloaders/dataset.py:15-50), ``random_rot_flip`` (:52-59),
+# ``random_rotate`` (:62-66), ``RandomGenerator`` (:69-88).
+#
+# The slices have different sizes (216x256, 232x256, ...) and the reference resamples every one of them to the patch size
+# with scipy's nearest-neighbour ``zoom`` / ``rotate`` in DataLoader workers.  This mirror keeps that arithmetic on the host
+# -- the SAME scipy calls, so batches are bit-identical to the reference's under the same ``random`` / ``np.random`` streams
+# (num_workers=0 order; tests/golden/acdc_dataset.npz) -- but reads the training set once into host memory, emits uint8
+# labels, and hands batches over in pinned double buffers that the step's H2D copy stream consumes (bcp_b200/graph.py).
+# A device-side resampler is the next step for this row; at 24 slices of 256x256 per step the host
+# transform is ~2 ms of numpy per batch, so ``SliceLoader`` prepares batch k+1 on a worker thread while step k runs.
+# ======================================================================================================================
+def random_rot_flip(image, label):
+    """rot90 by a random quarter turn, then a flip along a random axis (draws: randint(0,4), randint(0,2))."""
+    k = np.random.randint(0, 4)
+    axis = np.random.randint(0, 2)          # drawn after the rotation in the reference, which consumes no randomness in between
+    image, label = np.rot90(image, k), np.rot90(label, k)
+    return np.flip(image, axis=axis).copy(), np.flip(label, axis=axis).copy()
+
+
+def random_rotate(image, label):
+    """nearest-neighbour rotation by an integer angle in [-20, 20), output shape kept."""
+    from scipy import ndimage
+    angle = np.random.randint(-20, 20)
+    return (ndimage.rotate(image, angle, order=0, reshape=False),
+            ndimage.rotate(label, angle, order=0, reshape=False))
+
+
+class RandomGenerator:
+    """Augment one {'image','label'} slice and resample it to ``output_size`` (nearest neighbour).  Draw order as in the
+    reference: ``random.random()`` > 0.5 -> rot/flip, else a second ``random.random()`` > 0.5 -> small rotation."""
+
+    def __init__(self, output_size):
+        self.output_size = output_size
+
+    def __call__(self, sample):
+        import random
+        from scipy.ndimage import zoom
+        image, label = sample["image"], sample["label"]
+        if random.random() > 0.5:
+            image, label = random_rot_flip(image, label)
+        elif random.random() > 0.5:
+            image, label = random_rotate(image, label)
+        x, y = image.shape
+        fx, fy = self.output_size[0] / x, self.output_size[1] / y
+        image = zoom(image, (fx, fy), order=0)
+        label = zoom(label, (fx, fy), order=0)
+        return {"image": torch.from_numpy(image.astype(np.float32)).unsqueeze(0),
+                "label": torch.from_numpy(label.astype(np.uint8))}
+
+
+class BaseDataSets:
+    """ACDC slices ('train': ``train_slices.list`` -> ``data/slices/<case>.h5``) or volumes ('val': ``val.list`` ->
+    ``data/<case>.h5``), read ONCE into host memory (h5py where available, else ``<case>.npz`` next to where the h5 would
+    be).  ``slices=[(image, label), ...]`` serves in-memory data (tests, synthetic runs)."""
+
+    def __init__(self, base_dir=None, split="train", num=None, transform=None, slices=None):
+        self._base_dir, self.split, self.transform = base_dir, split, transform
+        if slices is not None:
+            self.sample_list = ["mem%d" % i for i in range(len(slices))]
+        else:
+            name = "train_slices.list" if split == "train" else "val.list"
+            with open(os.path.join(base_dir, name), "r") as f:
+                self.sample_list = [item.replace("\n", "") for item in f.readlines()]
+        if num is not None and split == "train":
+            self.sample_list = self.sample_list[:num]
+            if slices is not None:
+                slices = slices[:num]
+        print("total {} samples".format(len(self.sample_list)))
+        self._data = list(slices) if slices is not None else [self._read(c) for c in self.sample_list]
+
+    def _read(self, case):
+        stem = os.path.join(self._base_dir, "data", "slices" if self.split == "train" else "", case)
+        if os.path.exists(stem + ".h5"):
+            import h5py                      # not part of this image; present wherever the real ACDC h5 files are
+            with h5py.File(stem + ".h5", "r") as f:
+                return f["image"][:], f["label"][:]
+        z = np.load(stem + ".npz")
+        return z["image"], z["label"]
+
+    def __len__(self):
+        return len(self.sample_list)
+
+    def __getitem__(self, idx):
+        image, label = self._data[idx]
+        sample = {"image": image, "label": label}
+        if self.split == "train" and self.transform is not None:
+            sample = self.transform(sample)
+        sample["case"] = self.sample_list[idx]
+        return sample
+
+
+def patients_to_slices(dataset, patiens_num):
+    """Labeled-slice count for a number of labeled patients (ACDC_BCP_train.py:70-79)."""
+    if "ACDC" in dataset:
+        ref_dict = {"1": 32, "3": 68, "7": 136, "14": 256, "21": 396, "28": 512, "35": 664, "140": 1312}
+    elif "Prostate" in dataset:
+        ref_dict = {"2": 27, "4": 53, "8": 120, "12": 179, "16": 256, "21": 312, "42": 623}
+    else:
+        raise ValueError("unknown dataset %r" % (dataset,))
+    return ref_dict[str(patiens_num)]
+
+
+class SliceLoader:
+    """``DataLoader(db, batch_sampler=TwoStreamBatchSampler(...), num_workers=0)`` for the 2-D pipeline: yields
+    {'image': [B,1,H,W] fp32, 'label': [B,H,W] uint8} in PINNED host memory so the graphed step's copy stream can take it
+    without a staging copy.  The buffers form a ring of RING = 4: ``GraphedStep.load`` of batch k+2 returns only after the
+    H2D copy of batch k has finished (bcp_b200/graph.py), and with ``prefetch=True`` batch k+4 is being written while the
+    consumer is at most inside ``load`` of batch k+2 -- so a buffer is never rewritten under a copy in flight.
+    ``prefetch=True`` builds the next batch on a worker thread; the draws stay in the single-process order because only that
+    thread touches the RNG streams while it runs."""
+    RING = 4
+
+    def __init__(self, db: BaseDataSets, batch_sampler: TwoStreamBatchSampler, pin=None, prefetch=False):
+        self.db, self.sampler, self.prefetch = db, batch_sampler, prefetch
+        self.pin = torch.cuda.is_available() if pin is None else pin
+        self._bufs, self._turn = None, 0
+
+    def _collate(self, indices):
+        samples = [self.db[int(i)] for i in indices]
+        img0, lab0 = samples[0]["image"], samples[0]["label"]
+        if self._bufs is None:
+            mk = lambda t: torch.empty((len(samples),) + tuple(t.shape), dtype=t.dtype, pin_memory=self.pin)
+            self._bufs = [(mk(img0), mk(lab0)) for _ in range(self.RING)]
+        img, lab = self._bufs[self._turn]
+        self._turn = (self._turn + 1) % self.RING
+        for b, s in enumerate(samples):
+            img[b].copy_(s["image"])
+            lab[b].copy_(s["label"])
+        return {"image": img, "label": lab, "case": [s["case"] for s in samples]}
+
+    def __iter__(self):
+        it = iter(self.sampler)
+        if not self.prefetch:
+            for indices in it:
+                yield self._collate(indices)
+            return
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            nxt = next(it, None)
+            fut = pool.submit(self._collate, nxt) if nxt is not None else None
+            while fut is not None:
+                batch = fut.result()
+                nxt = next(it, None)                    # the sampler's draws stay between two batches' transform draws
+                fut = pool.submit(self._collate, nxt) if nxt is not None else None
+                yield batch
+
+    def __len__(self):
+        return len(self.sampler)

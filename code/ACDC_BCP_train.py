@@ -5,7 +5,9 @@ Keeps the CLI flags/defaults and the two-stage schedule of the reference's ``cod
 (/root/reference/code/ACDC_BCP_train.py:33-56,445-477).  The self-training step body is
 ``bcp_b200.step.acdc_self_train_step`` (reference :354-390); pre-training (:237-255) mixes two labeled slices and reuses
 ``mix_loss(u_weight=1.0, unlab=True)`` exactly like the reference.  ``--synthetic 1`` (default) generates seeded 256x256
-slices because the ACDC h5 data / h5py are not available here; validation (val_2d.py + medpy) is out of scope.
+slices because the ACDC data is not available here; ``--synthetic 0`` reads ``--root_path`` through
+``bcp_b200.dataloaders.dataset`` (BaseDataSets / RandomGenerator / TwoStreamBatchSampler, bit-exact against the reference's
+batches: tests/golden/acdc_dataset.npz).
 """
 import argparse
 import logging
@@ -73,9 +75,26 @@ class SyntheticACDC:
 
 
 def make_loader(args, device, rank):
+    """--synthetic 0: the reference's loader construction (ACDC_BCP_train.py:207-219 / :318-330) on
+    bcp_b200.dataloaders.dataset -- slices read once into host memory (h5py, or <case>.npz where h5py is absent), the
+    reference's RandomGenerator arithmetic on a prefetch thread, uint8 labels, pinned ring buffers for the step's H2D
+    copy stream; epochs are chained for ever (the stage loop stops at its iteration budget)."""
     if args.synthetic:
         return SyntheticACDC(args.batch_size, args.patch_size, args.seed + rank, device)
-    raise RuntimeError("real ACDC data needs h5py and the dataset at --root_path (use --synthetic 1)")
+    from bcp_b200.dataloaders.dataset import BaseDataSets, RandomGenerator, SliceLoader, TwoStreamBatchSampler, patients_to_slices
+    db_train = BaseDataSets(base_dir=args.root_path, split="train", num=None, transform=RandomGenerator(args.patch_size))
+    total_slices = len(db_train)
+    labeled_slice = patients_to_slices(args.root_path, args.labelnum)
+    logging.info("Total slices is: {}, labeled slices is:{}".format(total_slices, labeled_slice))
+    batch_sampler = TwoStreamBatchSampler(list(range(0, labeled_slice)), list(range(labeled_slice, total_slices)), args.batch_size,
+                                          args.batch_size - args.labeled_bs)
+    loader = SliceLoader(db_train, batch_sampler, prefetch=True)
+
+    def epochs():
+        while True:
+            for batch in loader:
+                yield batch
+    return epochs()
 
 
 def run_stage(args, stage, model, ema_model, optimizer, snapshot_path, device, rank, max_iterations):
@@ -165,7 +184,7 @@ if __name__ == "__main__":
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
     if args.deterministic:
-        random.seed(args.seed)
+        random.seed(args.seed + rank)            # rank 0 = the reference's streams; replicas draw different batches
         np.random.seed(args.seed + rank)
         torch.manual_seed(args.seed)
         torch.cuda.manual_seed(args.seed)

@@ -70,3 +70,22 @@ def synthetic_la_volumes(n, seed, lo=(20, 18, 14), hi=(40, 36, 30)):
         shape = tuple(int(rs.randint(lo[i], hi[i])) for i in range(3))
         vols.append((rs.standard_normal(shape).astype(np.float32), (rs.random_sample(shape) > 0.8).astype(np.uint8)))
     return vols
+
+
+def synthetic_acdc_slices(n, seed, lo=(40, 36), hi=(72, 70)):
+    """Seeded raw 2-D 'slices' of varying size (the ACDC slices are 216x256, 232x256, ...): smooth-ish images in [0, 1]
+    and 4-class label maps with connected regions, so nearest-neighbour rotation / zoom moves class boundaries visibly."""
+    rs = np.random.RandomState(seed)
+    out = []
+    for _ in range(n):
+        h, w = int(rs.randint(lo[0], hi[0])), int(rs.randint(lo[1], hi[1]))
+        yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+        img = (np.sin(yy / rs.uniform(3, 9)) * np.cos(xx / rs.uniform(3, 9)) * 0.5 + 0.5 + 0.05 * rs.standard_normal((h, w))).astype(np.float32)
+        cy, cx, r = rs.uniform(0.3, 0.7) * h, rs.uniform(0.3, 0.7) * w, rs.uniform(0.15, 0.3) * min(h, w)
+        d = np.sqrt((yy - cy) ** 2 + (xx - cx) ** 2)
+        lab = np.zeros((h, w), np.uint8)
+        lab[d < r] = 1
+        lab[d < 0.66 * r] = 2
+        lab[d < 0.33 * r] = 3
+        out.append((img, lab))
+    return out

@@ -669,13 +669,64 @@ def gen_dataset():
     save("dataset", **out)
 
 
+def gen_acdc_dataset():
+    """dataloaders/dataset.py:15-88: the reference's BaseDataSets + RandomGenerator + TwoStreamBatchSampler driven by a
+    single-process torch DataLoader over seeded in-memory slices of varying size (stub ``h5py.File`` keyed by case name;
+    every line of the reference module runs unmodified, scipy's rotate / zoom included)."""
+    import importlib.util
+    import random
+    import tempfile
+    import types
+    from oracle import dataset_oracle as D
+    slices = D.synthetic_acdc_slices(10, 777)
+    names = ["patient%03d_slice_%d" % (i // 3, i % 3) for i in range(len(slices))]
+
+    class _File(dict):
+        def __init__(self, path, mode="r"):
+            name = os.path.splitext(os.path.basename(path))[0]
+            im, lb = slices[names.index(name)]
+            super().__init__(image=im, label=lb)
+    h5 = types.ModuleType("h5py")
+    h5.File = _File
+    sys.modules["h5py"] = h5
+    ref_shims._install_stubs()
+    if not hasattr(sys.modules["skimage"], "transform"):
+        tr = types.ModuleType("skimage.transform")
+        sys.modules["skimage"].transform = tr
+        sys.modules["skimage.transform"] = tr
+    spec = importlib.util.spec_from_file_location("ref_dataloaders_dataset_acdc", os.path.join(ref_shims.REF_CODE, "dataloaders", "dataset.py"))
+    ds = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ds)
+    from torchvision import transforms as TV
+    patch = (48, 40)
+    out = dict(patch=np.array(patch), nslices=len(slices), slice_seed=777, np_seed=31, py_seed=5, labeled=4, batch_size=4, labeled_bs=2, epochs=3)
+    with tempfile.TemporaryDirectory() as d:
+        with open(os.path.join(d, "train_slices.list"), "w") as f:
+            f.write("\n".join(names) + "\n")
+        db = ds.BaseDataSets(base_dir=d, split="train", num=None, transform=TV.Compose([ds.RandomGenerator(patch)]))
+        sampler = ds.TwoStreamBatchSampler(list(range(4)), list(range(4, 10)), 4, 4 - 2)
+        loader = torch.utils.data.DataLoader(db, batch_sampler=sampler, num_workers=0)
+        np.random.seed(31)
+        random.seed(5)
+        b = 0
+        for epoch in range(3):
+            for batch in loader:
+                out[f"b{b}_image"] = batch["image"].numpy().astype(np.float32)
+                out[f"b{b}_label"] = batch["label"].numpy().astype(np.uint8)
+                b += 1
+        out["nbatches"] = b
+    save("acdc_dataset", **out)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["functions", "networks", "la_small", "la_pre", "acdc", "la_full", "pan", "acdc_pre", "pan_pre", "sliding",
-                             "ckpt_weights", "la_ckpt", "acdc_ckpt", "dataset", "val_2d"]
+                             "ckpt_weights", "la_ckpt", "acdc_ckpt", "dataset", "val_2d", "acdc_dataset"]
     if "dataset" in which:
         gen_dataset()
     if "val_2d" in which:
         gen_val_2d()
+    if "acdc_dataset" in which:
+        gen_acdc_dataset()
     if "ckpt_weights" in which:
         gen_ckpt_weights()
     if "la_ckpt" in which:

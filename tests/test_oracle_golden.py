@@ -460,3 +460,33 @@ def test_metric_closed_forms():
         assert V.dc(p, q) == M.dc(p, q) and V.hd95(p, q) == M.hd95(p, q)
         assert V.calculate_metric_percase(p.astype(np.int64) * 3, q.astype(np.int64)) == (M.dc(p, q), M.hd95(p, q))
     assert V.calculate_metric_percase(np.zeros((3, 3)), np.ones((3, 3))) == (0, 0)
+
+
+@pytest.mark.parametrize("prefetch", [False, True])
+def test_acdc_pipeline_matches_reference_batches(prefetch):
+    """bcp_b200.dataloaders.dataset BaseDataSets + RandomGenerator + TwoStreamBatchSampler + SliceLoader against
+    tests/golden/acdc_dataset.npz: the batches the reference's own classes (dataloaders/dataset.py:15-88,280-307) produced
+    under a single-process DataLoader with the same ``np.random`` / ``random`` seeds.  Host-side mirror (scipy nearest-neighbour
+    rotate / zoom, as the reference's workers run it): bit-exact, labels uint8, with and without the prefetch thread."""
+    import random
+    from bcp_b200.dataloaders import dataset as P
+    from oracle import dataset_oracle as D
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "acdc_dataset.npz"))
+    slices = D.synthetic_acdc_slices(int(g["nslices"]), int(g["slice_seed"]))
+    patch = tuple(int(v) for v in g["patch"])
+    db = P.BaseDataSets(split="train", transform=P.RandomGenerator(patch), slices=slices)
+    nl, bs, lbs = int(g["labeled"]), int(g["batch_size"]), int(g["labeled_bs"])
+    sampler = P.TwoStreamBatchSampler(list(range(nl)), list(range(nl, len(slices))), bs, bs - lbs)
+    loader = P.SliceLoader(db, sampler, pin=False, prefetch=prefetch)
+    np.random.seed(int(g["np_seed"]))
+    random.seed(int(g["py_seed"]))
+    b = 0
+    for _ in range(int(g["epochs"])):
+        for batch in loader:
+            assert batch["image"].dtype == torch.float32 and batch["label"].dtype == torch.uint8
+            assert batch["image"].shape == (bs, 1) + patch and batch["label"].shape == (bs,) + patch
+            assert np.array_equal(batch["image"].numpy(), g[f"b{b}_image"]), b
+            assert np.array_equal(batch["label"].numpy(), g[f"b{b}_label"]), b
+            b += 1
+    assert b == int(g["nbatches"]) and b >= 6
+    assert P.patients_to_slices("ACDC", 7) == 136 and P.patients_to_slices("/data/ACDC", 140) == 1312
