@@ -193,25 +193,39 @@ def random_rotate(image, label):
 
 class RandomGenerator:
     """Augment one {'image','label'} slice and resample it to ``output_size`` (nearest neighbour).  Draw order as in the
-    reference: ``random.random()`` > 0.5 -> rot/flip, else a second ``random.random()`` > 0.5 -> small rotation."""
+    reference: ``random.random()`` > 0.5 -> rot/flip, else a second ``random.random()`` > 0.5 -> small rotation.
+    ``draw()`` makes exactly those draws and ``apply()`` is deterministic given them, so a loader can draw in the reference's
+    order on one thread and run the (expensive) scipy resampling of a batch in parallel workers (``SliceLoader(workers=)``)."""
 
     def __init__(self, output_size):
         self.output_size = output_size
 
-    def __call__(self, sample):
+    @staticmethod
+    def draw():
         import random
-        from scipy.ndimage import zoom
-        image, label = sample["image"], sample["label"]
         if random.random() > 0.5:
-            image, label = random_rot_flip(image, label)
-        elif random.random() > 0.5:
-            image, label = random_rotate(image, label)
+            k = int(np.random.randint(0, 4))
+            return ("rot_flip", k, int(np.random.randint(0, 2)))
+        if random.random() > 0.5:
+            return ("rotate", int(np.random.randint(-20, 20)))
+        return ("none",)
+
+    def apply(self, image, label, params):
+        from scipy import ndimage
+        from scipy.ndimage import zoom
+        if params[0] == "rot_flip":
+            _, k, axis = params
+            image, label = np.flip(np.rot90(image, k), axis=axis).copy(), np.flip(np.rot90(label, k), axis=axis).copy()
+        elif params[0] == "rotate":
+            image = ndimage.rotate(image, params[1], order=0, reshape=False)
+            label = ndimage.rotate(label, params[1], order=0, reshape=False)
         x, y = image.shape
         fx, fy = self.output_size[0] / x, self.output_size[1] / y
-        image = zoom(image, (fx, fy), order=0)
-        label = zoom(label, (fx, fy), order=0)
-        return {"image": torch.from_numpy(image.astype(np.float32)).unsqueeze(0),
-                "label": torch.from_numpy(label.astype(np.uint8))}
+        return zoom(image, (fx, fy), order=0).astype(np.float32), zoom(label, (fx, fy), order=0).astype(np.uint8)
+
+    def __call__(self, sample):
+        image, label = self.apply(sample["image"], sample["label"], self.draw())
+        return {"image": torch.from_numpy(image).unsqueeze(0), "label": torch.from_numpy(label)}
 
 
 class BaseDataSets:
@@ -266,6 +280,23 @@ def patients_to_slices(dataset, patiens_num):
     return ref_dict[str(patiens_num)]
 
 
+_WORKER = {}
+
+
+def _worker_init(data, output_size, sh_img, sh_lab):
+    _WORKER["data"], _WORKER["gen"] = data, RandomGenerator(output_size)
+    _WORKER["img"], _WORKER["lab"] = sh_img.numpy(), sh_lab.numpy()          # shared-memory batch, inherited through fork
+
+
+def _worker_apply(job):
+    b, idx, params = job
+    image, label = _WORKER["data"][idx]
+    im, lb = _WORKER["gen"].apply(image, label, params)
+    _WORKER["img"][b, 0] = im                                                 # results go straight into the shared batch:
+    _WORKER["lab"][b] = lb                                                    # nothing but the job tuple crosses the pipe
+    return b
+
+
 class SliceLoader:
     """``DataLoader(db, batch_sampler=TwoStreamBatchSampler(...), num_workers=0)`` for the 2-D pipeline: yields
     {'image': [B,1,H,W] fp32, 'label': [B,H,W] uint8} in PINNED host memory so the graphed step's copy stream can take it
@@ -273,22 +304,54 @@ class SliceLoader:
     H2D copy of batch k has finished (bcp_b200/graph.py), and with ``prefetch=True`` batch k+4 is being written while the
     consumer is at most inside ``load`` of batch k+2 -- so a buffer is never rewritten under a copy in flight.
     ``prefetch=True`` builds the next batch on a worker thread; the draws stay in the single-process order because only that
-    thread touches the RNG streams while it runs."""
+    thread touches the RNG streams while it runs.  ``workers=N`` (the dataset's transform must be a ``RandomGenerator``): the
+    random draws of a batch are still made here, sample by sample in the reference's order, but the scipy resampling (which
+    holds the GIL) runs in N forked worker processes that hold the raw slices and write into one shared-memory batch -- same
+    batches, bit for bit."""
     RING = 4
 
-    def __init__(self, db: BaseDataSets, batch_sampler: TwoStreamBatchSampler, pin=None, prefetch=False):
+    def __init__(self, db: BaseDataSets, batch_sampler: TwoStreamBatchSampler, pin=None, prefetch=False, workers=0):
         self.db, self.sampler, self.prefetch = db, batch_sampler, prefetch
         self.pin = torch.cuda.is_available() if pin is None else pin
         self._bufs, self._turn = None, 0
+        self._pool = None
+        if workers > 0:
+            assert isinstance(db.transform, RandomGenerator) and db.split == "train", "workers need a RandomGenerator transform"
+            import multiprocessing as mp
+            B = batch_sampler.primary_batch_size + batch_sampler.secondary_batch_size
+            H, W = (int(v) for v in db.transform.output_size)
+            self._sh_img = torch.empty((B, 1, H, W), dtype=torch.float32).share_memory_()
+            self._sh_lab = torch.empty((B, H, W), dtype=torch.uint8).share_memory_()
+            self._pool = mp.get_context("fork").Pool(workers, initializer=_worker_init,
+                                                     initargs=(db._data, db.transform.output_size, self._sh_img, self._sh_lab))
 
-    def _collate(self, indices):
-        samples = [self.db[int(i)] for i in indices]
-        img0, lab0 = samples[0]["image"], samples[0]["label"]
+    def close(self):
+        if self._pool is not None:
+            self._pool.terminate()
+            self._pool = None
+
+    def __del__(self):
+        self.close()
+
+    def _next_buffers(self, img_shape, lab_shape):
         if self._bufs is None:
-            mk = lambda t: torch.empty((len(samples),) + tuple(t.shape), dtype=t.dtype, pin_memory=self.pin)
-            self._bufs = [(mk(img0), mk(lab0)) for _ in range(self.RING)]
+            self._bufs = [(torch.empty(tuple(img_shape), dtype=torch.float32, pin_memory=self.pin),
+                           torch.empty(tuple(lab_shape), dtype=torch.uint8, pin_memory=self.pin)) for _ in range(self.RING)]
         img, lab = self._bufs[self._turn]
         self._turn = (self._turn + 1) % self.RING
+        return img, lab
+
+    def _collate(self, indices):
+        if self._pool is not None:
+            jobs = [(b, int(i), RandomGenerator.draw()) for b, i in enumerate(indices)]      # draws in index order, this thread only
+            self._pool.map(_worker_apply, jobs)
+            img, lab = self._next_buffers(self._sh_img.shape, self._sh_lab.shape)
+            img.copy_(self._sh_img)
+            lab.copy_(self._sh_lab)
+            return {"image": img, "label": lab, "case": [self.db.sample_list[i] for _, i, _ in jobs]}
+        samples = [self.db[int(i)] for i in indices]
+        img0, lab0 = samples[0]["image"], samples[0]["label"]
+        img, lab = self._next_buffers((len(samples),) + tuple(img0.shape), (len(samples),) + tuple(lab0.shape))
         for b, s in enumerate(samples):
             img[b].copy_(s["image"])
             lab[b].copy_(s["label"])

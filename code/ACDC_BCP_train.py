@@ -42,6 +42,8 @@ parser.add_argument('--consistency_rampup', type=float, default=200.0, help='con
 parser.add_argument('--magnitude', type=float, default=6.0, help='magnitude')
 parser.add_argument('--s_param', type=int, default=6, help='multinum of random masks')
 parser.add_argument('--synthetic', type=int, default=1)
+parser.add_argument('--loader_workers', type=int, default=0,
+                    help='--synthetic 0: processes for the host resampling (scipy rotate/zoom); 0 = on the prefetch thread')
 parser.add_argument('--max_steps', type=int, default=0)
 parser.add_argument('--log_every', type=int, default=10)
 parser.add_argument('--graph', type=int, default=1, help='replay each step as one CUDA graph (0: eager step functions)')
@@ -88,7 +90,7 @@ def make_loader(args, device, rank):
     logging.info("Total slices is: {}, labeled slices is:{}".format(total_slices, labeled_slice))
     batch_sampler = TwoStreamBatchSampler(list(range(0, labeled_slice)), list(range(labeled_slice, total_slices)), args.batch_size,
                                           args.batch_size - args.labeled_bs)
-    loader = SliceLoader(db_train, batch_sampler, prefetch=True)
+    loader = SliceLoader(db_train, batch_sampler, prefetch=True, workers=args.loader_workers)
 
     def epochs():
         while True:

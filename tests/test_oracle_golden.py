@@ -462,12 +462,13 @@ def test_metric_closed_forms():
     assert V.calculate_metric_percase(np.zeros((3, 3)), np.ones((3, 3))) == (0, 0)
 
 
-@pytest.mark.parametrize("prefetch", [False, True])
-def test_acdc_pipeline_matches_reference_batches(prefetch):
+@pytest.mark.parametrize("prefetch,workers", [(False, 0), (True, 0), (True, 2)])
+def test_acdc_pipeline_matches_reference_batches(prefetch, workers):
     """bcp_b200.dataloaders.dataset BaseDataSets + RandomGenerator + TwoStreamBatchSampler + SliceLoader against
     tests/golden/acdc_dataset.npz: the batches the reference's own classes (dataloaders/dataset.py:15-88,280-307) produced
     under a single-process DataLoader with the same ``np.random`` / ``random`` seeds.  Host-side mirror (scipy nearest-neighbour
-    rotate / zoom, as the reference's workers run it): bit-exact, labels uint8, with and without the prefetch thread."""
+    rotate / zoom, as the reference's workers run it): bit-exact, labels uint8, with and without the prefetch thread and with the
+    resampling farmed out to worker processes (draws stay on one thread, in the reference's order)."""
     import random
     from bcp_b200.dataloaders import dataset as P
     from oracle import dataset_oracle as D
@@ -477,7 +478,7 @@ def test_acdc_pipeline_matches_reference_batches(prefetch):
     db = P.BaseDataSets(split="train", transform=P.RandomGenerator(patch), slices=slices)
     nl, bs, lbs = int(g["labeled"]), int(g["batch_size"]), int(g["labeled_bs"])
     sampler = P.TwoStreamBatchSampler(list(range(nl)), list(range(nl, len(slices))), bs, bs - lbs)
-    loader = P.SliceLoader(db, sampler, pin=False, prefetch=prefetch)
+    loader = P.SliceLoader(db, sampler, pin=False, prefetch=prefetch, workers=workers)
     np.random.seed(int(g["np_seed"]))
     random.seed(int(g["py_seed"]))
     b = 0
@@ -488,5 +489,6 @@ def test_acdc_pipeline_matches_reference_batches(prefetch):
             assert np.array_equal(batch["image"].numpy(), g[f"b{b}_image"]), b
             assert np.array_equal(batch["label"].numpy(), g[f"b{b}_label"]), b
             b += 1
+    loader.close()
     assert b == int(g["nbatches"]) and b >= 6
     assert P.patients_to_slices("ACDC", 7) == 136 and P.patients_to_slices("/data/ACDC", 140) == 1312
