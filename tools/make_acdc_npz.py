@@ -6,12 +6,13 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-from oracle import dataset_oracle as D
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from _synth import acdc_slices
 
 root, n = sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 96
 os.makedirs(os.path.join(root, "data", "slices"), exist_ok=True)
 names = ["patient%03d_frame01_slice_%d" % (i // 8, i % 8) for i in range(n)]
-for name, (im, lb) in zip(names, D.synthetic_acdc_slices(n, 11, lo=(200, 200), hi=(260, 260))):
+for name, (im, lb) in zip(names, acdc_slices(n, 11)):
     np.savez(os.path.join(root, "data", "slices", name + ".npz"), image=im, label=lb)
 with open(os.path.join(root, "train_slices.list"), "w") as f:
     f.write("\n".join(names) + "\n")

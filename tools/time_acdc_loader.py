@@ -2,10 +2,11 @@
 import os, sys, time, random
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import numpy as np
-from oracle import dataset_oracle as D
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from _synth import acdc_slices
 from bcp_b200.dataloaders import dataset as P
 
-slices = D.synthetic_acdc_slices(192, 11, lo=(200, 200), hi=(260, 260))
+slices = acdc_slices(192, 11)
 for workers in (0, 4, 8, 12):
     db = P.BaseDataSets(split="train", transform=P.RandomGenerator((256, 256)), slices=slices)
     sampler = P.TwoStreamBatchSampler(list(range(48)), list(range(48, 192)), 24, 12)
